@@ -1,0 +1,819 @@
+// capi.cu -- C ABI of libcovfn_b200.so (include/covfn_b200.h): handles, validation, kernel-program lowering,
+// launch planning, multi-device row sharding.  No C++ exception crosses the boundary; there is no CPU path.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/covfn_b200.h"
+#include "cf_lower.h"
+#include "cf_registry.h"
+#include "cf_extra.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CF_CUDA(call)                                                                               \
+    do {                                                                                            \
+        cudaError_t e__ = (call);                                                                   \
+        if (e__ != cudaSuccess) return fail(CF_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
+    } while (0)
+
+// ---- devices --------------------------------------------------------------------------------------------
+struct DeviceCtx {
+    int dev = -1;
+    double* exp2_tbl = nullptr;
+    int sms = 0;
+};
+std::mutex g_mu;
+std::vector<int> g_devices;          // devices new handles shard over (empty: current device)
+std::vector<DeviceCtx> g_ctx;        // lazily created, indexed by position
+
+int get_ctx(int dev, DeviceCtx** out) {
+    std::lock_guard<std::mutex> lk(g_mu);
+    for (auto& c : g_ctx)
+        if (c.dev == dev) { *out = &c; return CF_OK; }
+    DeviceCtx c;
+    c.dev = dev;
+    CF_CUDA(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CF_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10)
+        return fail(CF_ERR_CUDA, "device %d is sm_%d%d; this library contains sm_100a code only", dev, prop.major, prop.minor);
+    c.sms = prop.multiProcessorCount;
+    double tbl[CF_EXP_TBL];
+    for (int j = 0; j < CF_EXP_TBL; j++) tbl[j] = (double)exp2l((long double)j / CF_EXP_TBL);
+    CF_CUDA(cudaMalloc(&c.exp2_tbl, sizeof(tbl)));
+    CF_CUDA(cudaMemcpy(c.exp2_tbl, tbl, sizeof(tbl), cudaMemcpyHostToDevice));
+    g_ctx.reserve(64);
+    g_ctx.push_back(c);
+    *out = &g_ctx.back();
+    return CF_OK;
+}
+
+const cf_kernel_entry* find_entry(int d) {
+    const cf_kernel_entry* all[] = {cf_kernels_d1(), cf_kernels_d2(), cf_kernels_d3(),  cf_kernels_d4(),  cf_kernels_d6(),
+                                    cf_kernels_d8(), cf_kernels_d12(), cf_kernels_d16(), cf_kernels_d24(), cf_kernels_d32()};
+    for (auto* e : all)
+        if (e->D >= d) return e;
+    return nullptr;
+}
+
+// ---- handle ---------------------------------------------------------------------------------------------
+struct Buf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return CF_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        CF_CUDA(cudaMalloc(&p, bytes));
+        cap = bytes;
+        return CF_OK;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+struct Shard {
+    DeviceCtx* ctx = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    void* X = nullptr;  // n x D padded points (all rows, replicated)
+    void* Y = nullptr;  // m x D (== X when symmetric)
+    cf_program* d_prog = nullptr;
+    Buf a, y, partial, apad, ypad, cg[6];
+    int64_t r0 = 0, r1 = 0; // rows owned
+};
+
+}  // namespace
+
+struct cf_gramian_s {
+    int dtype = CF_F64, d = 0, D = 0;
+    int64_t n = 0, m = 0;
+    bool symmetric = false;
+    int64_t row_begin = 0, row_end = 0;
+    cf_program prog;
+    int kind = CF_ATOM_SOP; // kernel kind used for the value MVM
+    double coef = 1.0;      // leading constant when prog.single
+    const cf_kernel_entry* entry = nullptr;
+    std::vector<Shard> shards;
+    std::mutex mu;
+    float last_ms = 0;
+    int last_launches = 0;
+};
+
+namespace {
+
+size_t esize(int dtype) { return dtype == CF_F64 ? 8 : 4; }
+
+void split_rows(cf_gramian_s* g) {
+    const int S = (int)g->shards.size();
+    const int64_t rows = g->row_end - g->row_begin;
+    for (int s = 0; s < S; s++) {
+        g->shards[s].r0 = g->row_begin + rows * s / S;
+        g->shards[s].r1 = g->row_begin + rows * (s + 1) / S;
+    }
+}
+
+// choose the number of column chunks so that the grid fills the machine in (nearly) whole waves
+struct Plan { int row_tiles; int chunks; int64_t cols_per_chunk; };
+Plan make_plan(int64_t nrows, int64_t m, const cf_mvm_config& cfg, int sms) {
+    Plan p;
+    p.row_tiles = (int)((nrows + cfg.rows_per_cta - 1) / cfg.rows_per_cta);
+    if (p.row_tiles < 1) p.row_tiles = 1;
+    const int64_t col_tiles = std::max<int64_t>(1, (m + cfg.tj - 1) / cfg.tj);
+    const double conc = (double)sms * cfg.min_blocks;
+    int64_t smin = (int64_t)std::ceil(6.0 * conc / p.row_tiles);
+    smin = std::max<int64_t>(1, std::min<int64_t>(smin, col_tiles));
+    int64_t best = smin;
+    double best_eff = -1;
+    for (int64_t s = smin; s <= std::min<int64_t>(col_tiles, 2 * smin + 4); s++) {
+        const int64_t cpc = ((col_tiles + s - 1) / s) * cfg.tj;
+        const int64_t real_s = (m + cpc - 1) / cpc;
+        const double w = (double)p.row_tiles * real_s / conc;
+        const double eff = w / std::ceil(w);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+    }
+    p.cols_per_chunk = ((col_tiles + best - 1) / best) * cfg.tj;
+    p.chunks = (int)std::max<int64_t>(1, (m + p.cols_per_chunk - 1) / p.cols_per_chunk);
+    return p;
+}
+
+int check_handle(cf_gramian_t g) {
+    if (!g) return fail(CF_ERR_BAD_ARGUMENT, "NULL Gramian handle");
+    return CF_OK;
+}
+
+int launch_scale(int dtype, void* y, const void* yin, int64_t n, double beta, cudaStream_t stream) {
+    if (n <= 0) return CF_OK;
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, 4096);
+    if (dtype == CF_F64) cf_scale_kernel<double><<<blocks, 256, 0, stream>>>((double*)y, (const double*)yin, n, beta);
+    else cf_scale_kernel<float><<<blocks, 256, 0, stream>>>((float*)y, (const float*)yin, n, beta);
+    CF_CUDA(cudaGetLastError());
+    return CF_OK;
+}
+
+// dense tile: rows of the shard x columns [j0, j0 + nj), column-major with leading dimension ld
+int launch_dense(cf_gramian_s* g, Shard& sh, void* d_M, int64_t ld, int64_t j0, int64_t nj, cudaStream_t stream) {
+    const int64_t nrows = sh.r1 - sh.r0;
+    if (nrows <= 0 || nj <= 0) return CF_OK;
+    const int blocks = (int)std::min<int64_t>((nrows * nj + 255) / 256, 148 * 16);
+    if (g->dtype == CF_F64)
+        gram_dense_kernel<double><<<blocks, 256, 0, stream>>>((const double*)sh.X, (const double*)sh.Y, g->D, sh.d_prog,
+                                                              sh.ctx->exp2_tbl, sh.r0, nrows, j0, nj, (double*)d_M, ld);
+    else
+        gram_dense_kernel<float><<<blocks, 256, 0, stream>>>((const float*)sh.X, (const float*)sh.Y, g->D, sh.d_prog,
+                                                             sh.ctx->exp2_tbl, sh.r0, nrows, j0, nj, (float*)d_M, ld);
+    CF_CUDA(cudaGetLastError());
+    return CF_OK;
+}
+
+// B <- alpha K A + beta B, device pointers, column-major with leading dimensions (elements)
+int launch_mm(cf_gramian_s* g, Shard& sh, void* d_B, int64_t ldb, const void* d_A, int64_t lda, int64_t nrhs, double alpha,
+              double beta, cudaStream_t stream) {
+    const int64_t nrows = sh.r1 - sh.r0;
+    if (nrows <= 0) return CF_OK;
+    const size_t es = esize(g->dtype);
+    if (g->m == 0) {
+        for (int64_t c = 0; c < nrhs; c++)
+            if (int rc = launch_scale(g->dtype, (char*)d_B + c * ldb * es, (char*)d_B + c * ldb * es, nrows, beta, stream)) return rc;
+        return CF_OK;
+    }
+    cf_mm_params P;
+    std::memset(&P, 0, sizeof(P));
+    P.X = sh.X; P.Y = sh.Y;
+    P.exp2_tbl = sh.ctx->exp2_tbl; P.prog = sh.d_prog;
+    P.row0 = sh.r0; P.nrows = nrows; P.m = g->m; P.lda = lda; P.ldb = ldb;
+    P.alpha = alpha; P.beta = beta;
+    const int row_tiles = (int)((nrows + CF_MM_TI - 1) / CF_MM_TI);
+    for (int64_t c0 = 0; c0 < nrhs; c0 += CF_MM_PC) {
+        P.nrhs = (int)std::min<int64_t>(CF_MM_PC, nrhs - c0);
+        P.A = (const char*)d_A + c0 * lda * es;
+        P.B = (char*)d_B + c0 * ldb * es;
+        CF_CUDA(g->entry->mm[g->dtype](P, row_tiles, stream));
+        g->last_launches++;
+    }
+    return CF_OK;
+}
+
+int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const void* d_a, double alpha, double beta,
+               cudaStream_t stream);
+int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, const double* d_a, double alpha, double beta,
+                cudaStream_t stream);
+
+// conjugate gradients on (sigma2 I + K) x = b; restates IterativeSolvers.cg! 0.9.2 [upstream] behind
+// ldiv!(x, ::LazyMatrixSum, b) (reference src/lazy_linear_algebra.jl:126-144).  State lives on shard 0; with several shards
+// the search direction is broadcast to every device and the row blocks of K u are gathered back once per iteration
+// (peer copies over NVLink).
+int cg_solve_impl(cf_gramian_s* g, double sigma2, double* x, const double* b, double reltol, int maxiter, bool gradient,
+                  int* iters, double* resnorm) {
+    const int64_t blk = gradient ? g->d : 1;
+    const int64_t N = g->n * blk;
+    if (reltol <= 0) reltol = std::sqrt(2.220446049250313e-16);
+    if (maxiter <= 0) maxiter = (int)std::min<int64_t>(N, 2147483647);
+    if (N == 0) { if (iters) *iters = 0; if (resnorm) *resnorm = 0; return CF_OK; }
+    Shard& s0 = g->shards[0];
+    CF_CUDA(cudaSetDevice(s0.ctx->dev));
+    for (int q = 0; q < 5; q++)
+        if (int rc = s0.cg[q].ensure((size_t)N * 8)) return rc;
+    if (int rc = s0.cg[5].ensure(64)) return rc;
+    double *dx = (double*)s0.cg[0].p, *dr = (double*)s0.cg[1].p, *du = (double*)s0.cg[2].p, *dc = (double*)s0.cg[3].p,
+           *db = (double*)s0.cg[4].p, *dscal = (double*)s0.cg[5].p;
+    cudaStream_t st = s0.stream;
+    const int vb = (int)std::min<int64_t>((N + 255) / 256, 4096);
+    CF_CUDA(cudaMemcpyAsync(dx, x, N * 8, cudaMemcpyHostToDevice, st));
+    CF_CUDA(cudaMemcpyAsync(db, b, N * 8, cudaMemcpyHostToDevice, st));
+    CF_CUDA(cudaMemsetAsync(du, 0, N * 8, st));
+    g->last_launches = 0;
+
+    // c = sigma2 * v + K v   (LazyMatrixSum mul!: y = 0; y += D v; y += G v)
+    auto apply = [&](double* out, const double* v) -> int {
+        cf_axpby_kernel<<<vb, 256, 0, st>>>(out, sigma2, v, 0.0, v, N);
+        CF_CUDA(cudaGetLastError());
+        if (g->shards.size() == 1) {
+            return gradient ? launch_grad(g, s0, out, out, v, 1.0, 1.0, st) : launch_mvm(g, s0, out, out, v, 1.0, 1.0, st);
+        }
+        CF_CUDA(cudaStreamSynchronize(st));
+        for (size_t q = 0; q < g->shards.size(); q++) {
+            Shard& sh = g->shards[q];
+            const int64_t srows = (sh.r1 - sh.r0) * blk;
+            CF_CUDA(cudaSetDevice(sh.ctx->dev));
+            if (int rc = sh.a.ensure((size_t)N * 8)) return rc;
+            if (int rc = sh.y.ensure(std::max<size_t>(16, (size_t)srows * 8))) return rc;
+            CF_CUDA(cudaMemcpyPeerAsync(sh.a.p, sh.ctx->dev, v, s0.ctx->dev, N * 8, sh.stream));
+            if (srows == 0) continue;
+            int rc = gradient ? launch_grad(g, sh, (double*)sh.y.p, nullptr, (const double*)sh.a.p, 1.0, 0.0, sh.stream)
+                              : launch_mvm(g, sh, sh.y.p, nullptr, sh.a.p, 1.0, 0.0, sh.stream);
+            if (rc) return rc;
+            // gather this row block next to the sigma2 term (scratch: cg[4] is b, so use shard-0 partial-free buffer)
+        }
+        // gather: copy every block into a scratch vector on device 0 and add
+        if (int rc = s0.ypad.ensure((size_t)N * 8)) return rc;
+        for (size_t q = 0; q < g->shards.size(); q++) {
+            Shard& sh = g->shards[q];
+            const int64_t srows = (sh.r1 - sh.r0) * blk;
+            if (srows == 0) continue;
+            CF_CUDA(cudaSetDevice(sh.ctx->dev));
+            CF_CUDA(cudaMemcpyPeerAsync((double*)s0.ypad.p + sh.r0 * blk, s0.ctx->dev, sh.y.p, sh.ctx->dev, srows * 8, sh.stream));
+            CF_CUDA(cudaStreamSynchronize(sh.stream));
+        }
+        CF_CUDA(cudaSetDevice(s0.ctx->dev));
+        cf_axpby_kernel<<<vb, 256, 0, st>>>(out, 1.0, out, 1.0, (const double*)s0.ypad.p, N);
+        CF_CUDA(cudaGetLastError());
+        return CF_OK;
+    };
+    auto dot = [&](const double* u, const double* v, double* host) -> int {
+        cf_dot_kernel<<<1, 1024, 0, st>>>(u, v, N, dscal);
+        CF_CUDA(cudaGetLastError());
+        CF_CUDA(cudaMemcpyAsync(host, dscal, 8, cudaMemcpyDeviceToHost, st));
+        CF_CUDA(cudaStreamSynchronize(st));
+        return CF_OK;
+    };
+
+    if (int rc = apply(dc, dx)) return rc;                       // r = b - A x
+    cf_axpby_kernel<<<vb, 256, 0, st>>>(dr, 1.0, db, -1.0, dc, N);
+    CF_CUDA(cudaGetLastError());
+    double rr = 0;
+    if (int rc = dot(dr, dr, &rr)) return rc;
+    double residual = std::sqrt(rr), prev_residual = 1.0;
+    const double tol = reltol * residual;
+    int it = 0;
+    while (residual > tol && it < maxiter) {
+        const double beta = (residual * residual) / (prev_residual * prev_residual);
+        cf_axpby_kernel<<<vb, 256, 0, st>>>(du, 1.0, dr, beta, du, N);   // u = r + beta u
+        CF_CUDA(cudaGetLastError());
+        if (int rc = apply(dc, du)) return rc;                           // c = A u
+        double uc = 0;
+        if (int rc = dot(du, dc, &uc)) return rc;
+        const double alpha = (residual * residual) / uc;
+        cf_axpby_kernel<<<vb, 256, 0, st>>>(dx, 1.0, dx, alpha, du, N);   // x += alpha u
+        cf_axpby_kernel<<<vb, 256, 0, st>>>(dr, 1.0, dr, -alpha, dc, N);  // r -= alpha c
+        CF_CUDA(cudaGetLastError());
+        prev_residual = residual;
+        if (int rc = dot(dr, dr, &rr)) return rc;
+        residual = std::sqrt(rr);
+        it++;
+    }
+    CF_CUDA(cudaMemcpyAsync(x, dx, N * 8, cudaMemcpyDeviceToHost, st));
+    CF_CUDA(cudaStreamSynchronize(st));
+    if (iters) *iters = it;
+    if (resnorm) *resnorm = residual;
+    return CF_OK;
+}
+
+int peak_probe_impl(int kind, int iters, double* lane_ops_per_s, float* ms_out) {
+    int dev = 0;
+    CF_CUDA(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    CF_CUDA(cudaGetDeviceProperties(&prop, dev));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    void* out = nullptr;
+    CF_CUDA(cudaMalloc(&out, (size_t)blocks * threads * 8));
+    cudaEvent_t e0, e1;
+    CF_CUDA(cudaEventCreate(&e0));
+    CF_CUDA(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 4; rep++) {
+        CF_CUDA(cudaEventRecord(e0, 0));
+        if (kind == 0) cf_peak_dfma_kernel<<<blocks, threads>>>((double*)out, iters, 0.999999, 1e-7);
+        else if (kind == 1) cf_peak_ffma_kernel<<<blocks, threads>>>((float*)out, iters, 0.999999f, 1e-7f);
+        else cf_peak_mufu_kernel<<<blocks, threads>>>((float*)out, iters, 0.5f);
+        CF_CUDA(cudaGetLastError());
+        CF_CUDA(cudaEventRecord(e1, 0));
+        CF_CUDA(cudaEventSynchronize(e1));
+        float ms = 0;
+        CF_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        if (rep > 0) best = std::min(best, ms);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    if (ms_out) *ms_out = best;
+    if (lane_ops_per_s) *lane_ops_per_s = (double)blocks * threads * (double)iters * 8.0 / (best * 1e-3);
+    return CF_OK;
+}
+
+// one column of  y <- alpha K a + beta y  on one shard; device pointers; asynchronous on sh.stream
+int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const void* d_a, double alpha, double beta,
+               cudaStream_t stream) {
+    const int64_t nrows = sh.r1 - sh.r0;
+    if (nrows <= 0) return CF_OK;
+    const int dt = g->dtype;
+    if (g->m == 0) { // empty sum: y = beta*y
+        launch_scale(dt, d_y, d_yin, nrows, beta, stream);
+        return CF_OK;
+    }
+    const cf_mvm_config& cfg = g->entry->mvm_cfg[dt];
+    Plan pl = make_plan(nrows, g->m, cfg, sh.ctx->sms);
+    cf_mvm_params P;
+    std::memset(&P, 0, sizeof(P));
+    P.X = sh.X; P.Y = sh.Y; P.a = d_a;
+    P.exp2_tbl = sh.ctx->exp2_tbl;
+    P.prog = sh.d_prog;
+    P.row0 = sh.r0; P.nrows = nrows; P.m = g->m;
+    P.cols_per_chunk = pl.cols_per_chunk;
+    P.alpha = alpha * g->coef; P.beta = beta;
+    P.coef = g->coef;
+    P.use_tma = (((uintptr_t)d_a) % 16 == 0) ? 1 : 0;
+    if (g->prog.single) P.atom = g->prog.atoms[g->prog.terms[0].fac[0].atom];
+    P.direct = (pl.chunks == 1) ? 1 : 0;
+    if (P.direct) {
+        P.out = d_y; P.yin = d_yin;
+    } else {
+        int rc = sh.partial.ensure((size_t)pl.chunks * nrows * sizeof(double));
+        if (rc) return rc;
+        P.out = sh.partial.p;
+    }
+    cf_mvm_launch_fn fn = g->entry->mvm[dt][cf_kind_slot(g->kind)];
+    CF_CUDA(fn(P, dim3(pl.row_tiles, pl.chunks), stream));
+    g->last_launches++;
+    if (!P.direct) {
+        const int blocks = (int)std::min<int64_t>((nrows + 255) / 256, 4096);
+        if (dt == CF_F64)
+            gram_reduce_partials<double><<<blocks, 256, 0, stream>>>((const double*)sh.partial.p, pl.chunks, nrows, (double*)d_y,
+                                                                      (const double*)d_yin, alpha * g->coef, beta);
+        else
+            gram_reduce_partials<float><<<blocks, 256, 0, stream>>>((const double*)sh.partial.p, pl.chunks, nrows, (float*)d_y,
+                                                                     (const float*)d_yin, alpha * g->coef, beta);
+        CF_CUDA(cudaGetLastError());
+        g->last_launches++;
+    }
+    return CF_OK;
+}
+
+// gradient operator, one right-hand side, device pointers (unpadded flat vectors)
+int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, const double* d_a, double alpha, double beta,
+                cudaStream_t stream) {
+    const int64_t nrows = sh.r1 - sh.r0;
+    if (nrows <= 0) return CF_OK;
+    const int d = g->d, D = g->D;
+    if (g->m == 0) {
+        launch_scale(CF_F64, d_y, d_yin, nrows * d, beta, stream);
+        return CF_OK;
+    }
+    const cf_mvm_config& cfg = g->entry->grad_cfg;
+    Plan pl = make_plan(nrows, g->m, cfg, sh.ctx->sms);
+    const double* a_use = d_a;
+    if (D != d || (((uintptr_t)d_a) % 16) != 0) {
+        int rc = sh.apad.ensure((size_t)g->m * D * sizeof(double));
+        if (rc) return rc;
+        const int blocks = (int)std::min<int64_t>((g->m * D + 255) / 256, 8192);
+        cf_pad_points<double><<<blocks, 256, 0, stream>>>(d_a, d, d, (double*)sh.apad.p, D, g->m);
+        CF_CUDA(cudaGetLastError());
+        g->last_launches++;
+        a_use = (const double*)sh.apad.p;
+    }
+    int rc = sh.partial.ensure((size_t)pl.chunks * nrows * D * sizeof(double));
+    if (rc) return rc;
+    cf_grad_params P;
+    std::memset(&P, 0, sizeof(P));
+    P.X = (const double*)sh.X; P.Y = (const double*)sh.Y; P.a = a_use;
+    P.partial = (double*)sh.partial.p;
+    P.exp2_tbl = sh.ctx->exp2_tbl;
+    P.prog = sh.d_prog;
+    P.row0 = sh.r0; P.nrows = nrows; P.m = g->m; P.cols_per_chunk = pl.cols_per_chunk;
+    P.single = g->prog.single;
+    P.coef = g->coef;
+    if (g->prog.single) P.atom = g->prog.atoms[g->prog.terms[0].fac[0].atom];
+    CF_CUDA(g->entry->grad(P, dim3(pl.row_tiles, pl.chunks), stream));
+    g->last_launches++;
+    const int blocks = (int)std::min<int64_t>((nrows * d + 255) / 256, 8192);
+    grad_reduce_partials<<<blocks, 256, 0, stream>>>((const double*)sh.partial.p, pl.chunks, nrows, D, d, d_y, d_yin, 0, alpha, beta);
+    CF_CUDA(cudaGetLastError());
+    g->last_launches++;
+    return CF_OK;
+}
+
+template <typename T>
+int pack_points(const T* X, int64_t ldx, int64_t n, int d, int D, std::vector<T>& out) {
+    out.assign((size_t)n * D, (T)0);
+    for (int64_t i = 0; i < n; i++)
+        for (int c = 0; c < d; c++) {
+            T v = X[i * ldx + c];
+            if (!std::isfinite((double)v)) return fail(CF_ERR_NONFINITE, "point %lld coordinate %d is not finite", (long long)i, c);
+            out[(size_t)i * D + c] = v;
+        }
+    return CF_OK;
+}
+
+int destroy_impl(cf_gramian_s* g) {
+    for (auto& sh : g->shards) {
+        if (sh.ctx) cudaSetDevice(sh.ctx->dev);
+        if (sh.Y && sh.Y != sh.X) cudaFree(sh.Y);
+        if (sh.X) cudaFree(sh.X);
+        if (sh.d_prog) cudaFree(sh.d_prog);
+        sh.a.release(); sh.y.release(); sh.partial.release(); sh.apad.release(); sh.ypad.release();
+        for (auto& b : sh.cg) b.release();
+        if (sh.ev0) cudaEventDestroy(sh.ev0);
+        if (sh.ev1) cudaEventDestroy(sh.ev1);
+        if (sh.stream) cudaStreamDestroy(sh.stream);
+    }
+    delete g;
+    return CF_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int cf_version(void) { return CF_VERSION; }
+const char* cf_last_error(void) { return g_err.c_str(); }
+
+int cf_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int cf_init(int ngpus, const int* devices) {
+    int have = cf_device_count();
+    if (ngpus < 1) return fail(CF_ERR_BAD_ARGUMENT, "cf_init: ngpus must be >= 1");
+    if (have < 1) return fail(CF_ERR_CUDA, "cf_init: no CUDA device available (this library has no CPU path)");
+    std::vector<int> devs;
+    for (int i = 0; i < ngpus; i++) {
+        int dv = devices ? devices[i] : i;
+        if (dv < 0 || dv >= have) return fail(CF_ERR_BAD_ARGUMENT, "cf_init: device %d out of range (have %d)", dv, have);
+        devs.push_back(dv);
+    }
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_devices = devs;
+    return CF_OK;
+}
+
+int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int dtype, int d, int64_t n, const void* X,
+                      int64_t ldx, int64_t m, const void* Y, int64_t ldy) {
+    if (!out) return fail(CF_ERR_BAD_ARGUMENT, "cf_gramian_create: out is NULL");
+    *out = nullptr;
+    if (dtype != CF_F32 && dtype != CF_F64) return fail(CF_ERR_BAD_ARGUMENT, "cf_gramian_create: dtype must be CF_F32 or CF_F64");
+    if (d < 1) return fail(CF_ERR_DIMENSION, "cf_gramian_create: point dimension d = %d must be >= 1", d);
+    if (n < 0 || m < 0) return fail(CF_ERR_BAD_ARGUMENT, "cf_gramian_create: negative size");
+    if ((n > 0 && !X) || (Y == nullptr && m != n)) return fail(CF_ERR_BAD_ARGUMENT, "cf_gramian_create: X is NULL, or Y is NULL with m != n");
+    if (ldx < d || (Y && ldy < d)) return fail(CF_ERR_DIMENSION, "cf_gramian_create: leading dimension smaller than d");
+    cf_program lowered;
+    try {
+        lowered = cf::lower(prog, nnodes);
+    } catch (const cf::LowerError& e) {
+        return fail(e.code, "cf_gramian_create: %s", e.msg.c_str());
+    } catch (...) {
+        return fail(CF_ERR_INTERNAL, "cf_gramian_create: unexpected failure while lowering the kernel program");
+    }
+    const cf_kernel_entry* entry = find_entry(d);
+    if (!entry) return fail(CF_ERR_UNSUPPORTED, "cf_gramian_create: d = %d > 32 is not supported yet", d);
+    if (cf_device_count() < 1) return fail(CF_ERR_CUDA, "cf_gramian_create: no CUDA device available (this library has no CPU path)");
+
+    cf_gramian_s* g = new (std::nothrow) cf_gramian_s;
+    if (!g) return fail(CF_ERR_INTERNAL, "out of host memory");
+    g->dtype = dtype; g->d = d; g->D = entry->D; g->n = n; g->m = m;
+    g->symmetric = (Y == nullptr);
+    g->row_begin = 0; g->row_end = n;
+    g->prog = lowered;
+    g->entry = entry;
+    if (lowered.single) {
+        const cf_atom& A = lowered.atoms[lowered.terms[0].fac[0].atom];
+        g->coef = lowered.terms[0].coef;
+        g->kind = (A.kind == CF_ATOM_EQ || A.kind == CF_ATOM_MATERN || A.kind == CF_ATOM_RQ_INT) ? A.kind : CF_ATOM_SOP;
+        if (g->kind == CF_ATOM_SOP) g->coef = 1.0; // generic path applies the coefficient itself
+    } else {
+        g->kind = CF_ATOM_SOP;
+        g->coef = 1.0;
+    }
+
+    std::vector<int> devs;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        devs = g_devices;
+    }
+    if (devs.empty()) {
+        int cur = 0;
+        if (cudaGetDevice(&cur) != cudaSuccess) { delete g; return fail(CF_ERR_CUDA, "cudaGetDevice failed"); }
+        devs.push_back(cur);
+    }
+    // host packing (+ finiteness validation)
+    std::vector<double> xd, yd;
+    std::vector<float> xf, yf;
+    int rc = CF_OK;
+    if (dtype == CF_F64) {
+        rc = pack_points<double>((const double*)X, ldx, n, d, g->D, xd);
+        if (!rc && Y) rc = pack_points<double>((const double*)Y, ldy, m, d, g->D, yd);
+    } else {
+        rc = pack_points<float>((const float*)X, ldx, n, d, g->D, xf);
+        if (!rc && Y) rc = pack_points<float>((const float*)Y, ldy, m, d, g->D, yf);
+    }
+    if (rc) { delete g; return rc; }
+    const void* hx = dtype == CF_F64 ? (const void*)xd.data() : (const void*)xf.data();
+    const void* hy = dtype == CF_F64 ? (const void*)yd.data() : (const void*)yf.data();
+    const size_t es = esize(dtype);
+
+    g->shards.resize(devs.size());
+    for (size_t s = 0; s < devs.size(); s++) {
+        Shard& sh = g->shards[s];
+        rc = get_ctx(devs[s], &sh.ctx);
+        if (rc) { destroy_impl(g); return rc; }
+#define CF_CREATE_CUDA(call)                                                                                  \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess) {                                                                             \
+            destroy_impl(g);                                                                                  \
+            return fail(CF_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));                        \
+        }                                                                                                     \
+    } while (0)
+        CF_CREATE_CUDA(cudaSetDevice(devs[s]));
+        CF_CREATE_CUDA(cudaStreamCreateWithFlags(&sh.stream, cudaStreamNonBlocking));
+        CF_CREATE_CUDA(cudaEventCreate(&sh.ev0));
+        CF_CREATE_CUDA(cudaEventCreate(&sh.ev1));
+        CF_CREATE_CUDA(cudaMalloc(&sh.X, std::max<size_t>(16, (size_t)n * g->D * es)));
+        if (n) CF_CREATE_CUDA(cudaMemcpy(sh.X, hx, (size_t)n * g->D * es, cudaMemcpyHostToDevice));
+        if (Y) {
+            CF_CREATE_CUDA(cudaMalloc(&sh.Y, std::max<size_t>(16, (size_t)m * g->D * es)));
+            if (m) CF_CREATE_CUDA(cudaMemcpy(sh.Y, hy, (size_t)m * g->D * es, cudaMemcpyHostToDevice));
+        } else {
+            sh.Y = sh.X;
+        }
+        CF_CREATE_CUDA(cudaMalloc(&sh.d_prog, sizeof(cf_program)));
+        CF_CREATE_CUDA(cudaMemcpy(sh.d_prog, &g->prog, sizeof(cf_program), cudaMemcpyHostToDevice));
+#undef CF_CREATE_CUDA
+    }
+    split_rows(g);
+    *out = g;
+    return CF_OK;
+}
+
+int cf_gramian_destroy(cf_gramian_t g) {
+    if (!g) return CF_OK;
+    return destroy_impl(g);
+}
+
+int cf_gramian_size(cf_gramian_t g, int64_t* n, int64_t* m, int* d, int* dtype) {
+    if (int rc = check_handle(g)) return rc;
+    if (n) *n = g->n;
+    if (m) *m = g->m;
+    if (d) *d = g->d;
+    if (dtype) *dtype = g->dtype;
+    return CF_OK;
+}
+
+int cf_gramian_set_row_range(cf_gramian_t g, int64_t row_begin, int64_t row_end) {
+    if (int rc = check_handle(g)) return rc;
+    if (row_begin < 0 || row_end < row_begin || row_end > g->n)
+        return fail(CF_ERR_DIMENSION, "cf_gramian_set_row_range: [%lld, %lld) is not inside [0, %lld)", (long long)row_begin,
+                    (long long)row_end, (long long)g->n);
+    std::lock_guard<std::mutex> lk(g->mu);
+    g->row_begin = row_begin; g->row_end = row_end;
+    split_rows(g);
+    return CF_OK;
+}
+
+static int mul_host_impl(cf_gramian_t g, void* y, int64_t ldy, const void* x, int64_t ldx, int64_t nrhs, double alpha,
+                         double beta, bool gradient) {
+    if (int rc = check_handle(g)) return rc;
+    if (nrhs < 0) return fail(CF_ERR_BAD_ARGUMENT, "nrhs is negative");
+    const int64_t blk = gradient ? g->d : 1;
+    const int64_t rows = (g->row_end - g->row_begin) * blk, cols = g->m * blk;
+    if (nrhs == 0 || rows == 0) return CF_OK;
+    if (!y || (!x && cols > 0)) return fail(CF_ERR_BAD_ARGUMENT, "NULL vector pointer");
+    if (nrhs > 1 && (ldy < rows || ldx < cols))
+        return fail(CF_ERR_DIMENSION, "leading dimension too small: ldy = %lld (rows %lld), ldx = %lld (cols %lld)", (long long)ldy,
+                    (long long)rows, (long long)ldx, (long long)cols);
+    if (gradient) {
+        if (g->dtype != CF_F64) return fail(CF_ERR_UNSUPPORTED, "gradient operator: Float64 only");
+        if (!g->prog.isotropic) return fail(CF_ERR_UNSUPPORTED, "gradient operator: kernel does not have the IsotropicInput trait");
+    }
+    if (nrhs == 1) { ldy = rows; ldx = cols; }
+    std::lock_guard<std::mutex> lk(g->mu);
+    const size_t es = esize(g->dtype);
+    g->last_launches = 0;
+    // stage 1: copies in + launches on every shard
+    for (auto& sh : g->shards) {
+        const int64_t srows = (sh.r1 - sh.r0) * blk;
+        CF_CUDA(cudaSetDevice(sh.ctx->dev));
+        if (int rc = sh.a.ensure(std::max<size_t>(16, (size_t)cols * nrhs * es))) return rc;
+        if (int rc = sh.y.ensure(std::max<size_t>(16, (size_t)srows * nrhs * es))) return rc;
+        if (cols > 0)
+            CF_CUDA(cudaMemcpy2DAsync(sh.a.p, cols * es, x, ldx * es, cols * es, nrhs, cudaMemcpyHostToDevice, sh.stream));
+        if (srows == 0) continue;
+        const int64_t off = (sh.r0 - g->row_begin) * blk;
+        if (beta != 0.0)
+            CF_CUDA(cudaMemcpy2DAsync(sh.y.p, srows * es, (const char*)y + off * es, ldy * es, srows * es, nrhs,
+                                      cudaMemcpyHostToDevice, sh.stream));
+        CF_CUDA(cudaEventRecord(sh.ev0, sh.stream));
+        if (!gradient && nrhs > 1) {
+            int rc = launch_mm(g, sh, sh.y.p, srows, sh.a.p, cols, nrhs, alpha, beta, sh.stream);
+            if (rc) return rc;
+        } else {
+            for (int64_t c = 0; c < nrhs; c++) {
+                void* yc = (char*)sh.y.p + (size_t)c * srows * es;
+                const void* ac = (const char*)sh.a.p + (size_t)c * cols * es;
+                int rc = gradient ? launch_grad(g, sh, (double*)yc, (const double*)yc, (const double*)ac, alpha, beta, sh.stream)
+                                  : launch_mvm(g, sh, yc, yc, ac, alpha, beta, sh.stream);
+                if (rc) return rc;
+            }
+        }
+        CF_CUDA(cudaEventRecord(sh.ev1, sh.stream));
+        CF_CUDA(cudaMemcpy2DAsync((char*)y + off * es, ldy * es, sh.y.p, srows * es, srows * es, nrhs, cudaMemcpyDeviceToHost,
+                                  sh.stream));
+    }
+    // stage 2: wait
+    float worst = 0;
+    for (auto& sh : g->shards) {
+        CF_CUDA(cudaSetDevice(sh.ctx->dev));
+        CF_CUDA(cudaStreamSynchronize(sh.stream));
+        if (sh.r1 > sh.r0) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, sh.ev0, sh.ev1) == cudaSuccess) worst = std::max(worst, ms);
+        }
+    }
+    g->last_ms = worst;
+    return CF_OK;
+}
+
+int cf_gramian_mul(cf_gramian_t g, void* y, int64_t ldy, const void* x, int64_t ldx, int64_t nrhs, double alpha, double beta) {
+    return mul_host_impl(g, y, ldy, x, ldx, nrhs, alpha, beta, false);
+}
+int cf_gradient_mul(cf_gramian_t g, void* y, int64_t ldy, const void* x, int64_t ldx, int64_t nrhs, double alpha, double beta) {
+    return mul_host_impl(g, y, ldy, x, ldx, nrhs, alpha, beta, true);
+}
+
+static int mul_device_impl(cf_gramian_t g, void* d_y, int64_t ldy, const void* d_x, int64_t ldx, int64_t nrhs, double alpha,
+                           double beta, void* stream, bool gradient) {
+    if (int rc = check_handle(g)) return rc;
+    if (g->shards.size() != 1) return fail(CF_ERR_UNSUPPORTED, "device-pointer multiply needs a single-device handle");
+    const int64_t blk = gradient ? g->d : 1;
+    const int64_t rows = (g->row_end - g->row_begin) * blk, cols = g->m * blk;
+    if (nrhs <= 0 || rows == 0) return CF_OK;
+    if (!d_y || (!d_x && cols > 0)) return fail(CF_ERR_BAD_ARGUMENT, "NULL device pointer");
+    if (nrhs == 1) { ldy = rows; ldx = cols; }
+    if (ldy < rows || ldx < cols) return fail(CF_ERR_DIMENSION, "leading dimension too small");
+    if (gradient) {
+        if (g->dtype != CF_F64) return fail(CF_ERR_UNSUPPORTED, "gradient operator: Float64 only");
+        if (!g->prog.isotropic) return fail(CF_ERR_UNSUPPORTED, "gradient operator: kernel does not have the IsotropicInput trait");
+    }
+    std::lock_guard<std::mutex> lk(g->mu);
+    Shard& sh = g->shards[0];
+    CF_CUDA(cudaSetDevice(sh.ctx->dev));
+    cudaStream_t st = stream ? (cudaStream_t)stream : sh.stream;
+    const size_t es = esize(g->dtype);
+    g->last_launches = 0;
+    CF_CUDA(cudaEventRecord(sh.ev0, st));
+    if (!gradient && nrhs > 1) {
+        int rc = launch_mm(g, sh, d_y, ldy, d_x, ldx, nrhs, alpha, beta, st);
+        if (rc) return rc;
+    } else {
+        for (int64_t c = 0; c < nrhs; c++) {
+            void* yc = (char*)d_y + (size_t)c * ldy * es;
+            const void* ac = (const char*)d_x + (size_t)c * ldx * es;
+            int rc = gradient ? launch_grad(g, sh, (double*)yc, (const double*)yc, (const double*)ac, alpha, beta, st)
+                              : launch_mvm(g, sh, yc, yc, ac, alpha, beta, st);
+            if (rc) return rc;
+        }
+    }
+    CF_CUDA(cudaEventRecord(sh.ev1, st));
+    if (!stream) {
+        CF_CUDA(cudaStreamSynchronize(st));
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, sh.ev0, sh.ev1) == cudaSuccess) g->last_ms = ms;
+    }
+    return CF_OK;
+}
+
+int cf_gramian_mul_device(cf_gramian_t g, void* d_y, int64_t ldy, const void* d_x, int64_t ldx, int64_t nrhs, double alpha,
+                          double beta, void* stream) {
+    return mul_device_impl(g, d_y, ldy, d_x, ldx, nrhs, alpha, beta, stream, false);
+}
+int cf_gradient_mul_device(cf_gramian_t g, void* d_y, int64_t ldy, const void* d_x, int64_t ldx, int64_t nrhs, double alpha,
+                           double beta, void* stream) {
+    return mul_device_impl(g, d_y, ldy, d_x, ldx, nrhs, alpha, beta, stream, true);
+}
+
+int cf_gramian_matrix(cf_gramian_t g, void* M, int64_t ldm) {
+    if (int rc = check_handle(g)) return rc;
+    const int64_t rows = g->row_end - g->row_begin;
+    if (rows == 0 || g->m == 0) return CF_OK;
+    if (!M) return fail(CF_ERR_BAD_ARGUMENT, "cf_gramian_matrix: M is NULL");
+    if (ldm < rows) return fail(CF_ERR_DIMENSION, "cf_gramian_matrix: ldm = %lld < rows = %lld", (long long)ldm, (long long)rows);
+    std::lock_guard<std::mutex> lk(g->mu);
+    const size_t es = esize(g->dtype);
+    for (auto& sh : g->shards) {
+        const int64_t srows = sh.r1 - sh.r0;
+        if (srows == 0) continue;
+        CF_CUDA(cudaSetDevice(sh.ctx->dev));
+        // column panels bounded to 256 MiB of device scratch
+        int64_t panel = std::max<int64_t>(1, std::min<int64_t>(g->m, (int64_t)((256u << 20) / (srows * es))));
+        if (int rc = sh.ypad.ensure((size_t)srows * panel * es)) return rc;
+        for (int64_t j0 = 0; j0 < g->m; j0 += panel) {
+            const int64_t nj = std::min(panel, g->m - j0);
+            int rc = launch_dense(g, sh, sh.ypad.p, srows, j0, nj, sh.stream);
+            if (rc) return rc;
+            CF_CUDA(cudaMemcpy2DAsync((char*)M + ((sh.r0 - g->row_begin) + j0 * ldm) * es, ldm * es, sh.ypad.p, srows * es,
+                                      srows * es, nj, cudaMemcpyDeviceToHost, sh.stream));
+            CF_CUDA(cudaStreamSynchronize(sh.stream));
+        }
+    }
+    return CF_OK;
+}
+
+int cf_gramian_getindex(cf_gramian_t g, int64_t i, int64_t j, double* out) {
+    if (int rc = check_handle(g)) return rc;
+    if (!out) return fail(CF_ERR_BAD_ARGUMENT, "cf_gramian_getindex: out is NULL");
+    if (i < 0 || i >= g->n || j < 0 || j >= g->m)
+        return fail(CF_ERR_DIMENSION, "BoundsError: attempt to access %lld x %lld Gramian at index [%lld, %lld]", (long long)g->n,
+                    (long long)g->m, (long long)i + 1, (long long)j + 1);
+    std::lock_guard<std::mutex> lk(g->mu);
+    Shard& sh = g->shards[0];
+    CF_CUDA(cudaSetDevice(sh.ctx->dev));
+    if (int rc = sh.ypad.ensure(16)) return rc;
+    Shard tmp = sh; // view of a single row
+    tmp.r0 = i; tmp.r1 = i + 1;
+    int rc = launch_dense(g, tmp, sh.ypad.p, 1, j, 1, sh.stream);
+    if (rc) return rc;
+    double v64 = 0; float v32 = 0;
+    if (g->dtype == CF_F64) CF_CUDA(cudaMemcpyAsync(&v64, sh.ypad.p, 8, cudaMemcpyDeviceToHost, sh.stream));
+    else CF_CUDA(cudaMemcpyAsync(&v32, sh.ypad.p, 4, cudaMemcpyDeviceToHost, sh.stream));
+    CF_CUDA(cudaStreamSynchronize(sh.stream));
+    *out = g->dtype == CF_F64 ? v64 : (double)v32;
+    return CF_OK;
+}
+
+int cf_cg_solve(cf_gramian_t g, double sigma2, void* x, const void* b, double reltol, int maxiter, int gradient, int* iters,
+                double* resnorm) {
+    if (int rc = check_handle(g)) return rc;
+    if (!x || !b) return fail(CF_ERR_BAD_ARGUMENT, "cf_cg_solve: NULL vector");
+    if (g->n != g->m) return fail(CF_ERR_DIMENSION, "cf_cg_solve: Gramian is %lld x %lld, not square", (long long)g->n, (long long)g->m);
+    if (g->dtype != CF_F64) return fail(CF_ERR_UNSUPPORTED, "cf_cg_solve: Float64 only");
+    if (g->row_begin != 0 || g->row_end != g->n) return fail(CF_ERR_UNSUPPORTED, "cf_cg_solve: handle is restricted to a row range");
+    if (gradient && !g->prog.isotropic) return fail(CF_ERR_UNSUPPORTED, "gradient operator: kernel does not have the IsotropicInput trait");
+    std::lock_guard<std::mutex> lk(g->mu);
+    return cg_solve_impl(g, sigma2, (double*)x, (const double*)b, reltol, maxiter, gradient != 0, iters, resnorm);
+}
+
+int cf_last_timing(cf_gramian_t g, float* kernel_ms, int* launches) {
+    if (int rc = check_handle(g)) return rc;
+    if (kernel_ms) *kernel_ms = g->last_ms;
+    if (launches) *launches = g->last_launches;
+    return CF_OK;
+}
+
+int cf_peak_probe(int kind, int iters, double* lane_ops_per_s, float* ms) {
+    if (cf_device_count() < 1) return fail(CF_ERR_CUDA, "cf_peak_probe: no CUDA device available");
+    if (kind < 0 || kind > 2 || iters < 1) return fail(CF_ERR_BAD_ARGUMENT, "cf_peak_probe: bad arguments");
+    return peak_probe_impl(kind, iters, lane_ops_per_s, ms);
+}
+
+}  // extern "C"

@@ -1,0 +1,31 @@
+// cf_inst.cu -- compiled once per padded dimension: nvcc -DCF_D=<D> ... -o cf_inst_d<D>.o
+#include "cf_registry.h"
+
+#ifndef CF_D
+#error "compile with -DCF_D=<dimension>"
+#endif
+#define CF_CAT2(a, b) a##b
+#define CF_CAT(a, b) CF_CAT2(a, b)
+
+namespace {
+constexpr int D = CF_D;
+using TU = cf_tune<D>;
+
+template <typename T, int KIND>
+constexpr cf_mvm_launch_fn mvm_fn() {
+    return &cf_mvm_launch<T, D, KIND, TU::R, TU::NT, TU::TJ, TU::NS, TU::MINB>;
+}
+
+const cf_kernel_entry entry = {
+    D,
+    {{mvm_fn<float, CF_ATOM_EQ>(), mvm_fn<float, CF_ATOM_MATERN>(), mvm_fn<float, CF_ATOM_RQ_INT>(), mvm_fn<float, CF_ATOM_SOP>()},
+     {mvm_fn<double, CF_ATOM_EQ>(), mvm_fn<double, CF_ATOM_MATERN>(), mvm_fn<double, CF_ATOM_RQ_INT>(), mvm_fn<double, CF_ATOM_SOP>()}},
+    {{TU::NT * TU::R, TU::TJ, cf_mvm_smem<float, D, TU::TJ, TU::NS>::total, TU::MINB},
+     {TU::NT * TU::R, TU::TJ, cf_mvm_smem<double, D, TU::TJ, TU::NS>::total, TU::MINB}},
+    &cf_grad_launch<D, TU::GR, TU::GNT, TU::GTJ, TU::NS, TU::GMINB>,
+    {TU::GNT * TU::GR, TU::GTJ, cf_grad_smem<D, TU::GTJ, TU::NS>::total, TU::GMINB},
+    {&cf_mm_launch<float, D>, &cf_mm_launch<double, D>},
+};
+}  // namespace
+
+const cf_kernel_entry* CF_CAT(cf_kernels_d, CF_D)() { return &entry; }

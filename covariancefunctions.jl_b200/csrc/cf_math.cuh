@@ -1,0 +1,260 @@
+// cf_math.cuh -- device arithmetic for the Gramian kernels (sm_100a).
+//
+// FP64: there is no FP64 SFU path on the chip (MUFU.EX2 is FP32-only), so exp is built from the FP64
+// FMA pipe: one magic-number rounding, a one-step Cody-Waite reduction against a 64-entry 2^(j/64)
+// table held in shared memory (replicated 16x so that every lane of a half-warp reads its own bank
+// pair: zero bank conflicts for any index pattern) and a degree-5 polynomial -- 9 FP64 issue slots
+// instead of the ~16-20 of a table-free exp.  sqrt and reciprocal take their seed from the SFU
+// (MUFU.RSQ64H / MUFU.RCP64H through rsqrt.approx.ftz.f64 / rcp.approx.ftz.f64) and are finished with
+// FMA Newton steps.  All results are accurate to ~1 ulp (tests/test_gpu_math.py measures it).
+// FP32: ex2.approx / rsqrt.approx / rcp.approx on the SFU.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "cf_program.h"
+
+#define CF_EXP_TBL 64
+#define CF_EXP_TBL_REP 16
+#define CF_EXP_TBL_DOUBLES (CF_EXP_TBL * CF_EXP_TBL_REP)
+#define CF_MAGIC 6755399441055744.0 /* 1.5 * 2^52 */
+
+// Copy the 2^(j/64) table (64 doubles in global memory, written once per device by the host, correctly
+// rounded from long double) into shared memory, 16 replicas per entry: entry j for lane l lives at
+// tbl[j*16 + (l & 15)].
+__device__ __forceinline__ void cf_fill_exp_table(double* tbl, const double* __restrict__ g_tbl, int tid, int nthreads) {
+    for (int i = tid; i < CF_EXP_TBL_DOUBLES; i += nthreads) tbl[i] = g_tbl[i >> 4];
+}
+
+// exp(c*v), v >= 0 (c < 0 folded into the constants).  tbl_lane = table + (lane & 15).
+// Non-FP64 work is kept to 6 ALU/LSU instructions per call: the clamp of v is ONE integer min on the high
+// word (v >= 0, so integer order of high words == floating-point order; the clamped value lies within
+// 2^-20 relative of E.vmax, where the result is ~1e-304, i.e. 0), the table address is an AND + a
+// shift-add, the 2^k scaling is a shift + integer multiply-add on the high word.
+__device__ __forceinline__ double cf_exp_cv(double v, const cf_exp_consts& E, const double* __restrict__ tbl_lane) {
+    v = __hiloint2double(min(__double2hiint(v), E.vmax_hi), __double2loint(v));
+    double t = fma(v, E.c1, CF_MAGIC);
+    int kk = __double2loint(t);
+    double kd = t - CF_MAGIC;
+    double u = fma(kd, E.c2, v);
+    double p = fma(E.q[4], u, E.q[3]);
+    p = fma(p, u, E.q[2]);
+    p = fma(p, u, E.q[1]);
+    p = fma(p, u, E.q[0]);
+    const double tj = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(tbl_lane) +
+                                                       ((unsigned)(kk & (CF_EXP_TBL - 1)) << 7));
+    double tu = tj * u;
+    double e = fma(tu, p, tj); // tj * (1 + u p)
+    int hi = (kk >> 6) * 0x100000 + __double2hiint(e);
+    return __hiloint2double(hi, __double2loint(e));
+}
+
+// sqrt(v) for v >= 0; v below 2^-1007 (incl. 0 and subnormals) returns ~2^-504 (i.e. 0 for our purposes).
+__device__ __forceinline__ double cf_sqrt_pos(double v) {
+    int hi = __double2hiint(v);
+    if (hi < 0x01000000) v = __hiloint2double(0x01000000, 0);
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(v));
+    double g = v * y, h = 0.5 * y;
+    double r = fma(-h, g, 0.5);
+    g = fma(g, r, g);
+    h = fma(h, r, h);
+    double dd = fma(-g, g, v);
+    return fma(dd, h, g);
+}
+
+// 1/b for normal b (here b >= 1)
+__device__ __forceinline__ double cf_rcp(double b) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(b));
+    double e = fma(-b, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-b, y, 1.0);
+    y = fma(y, e, y);
+    return y;
+}
+
+__device__ __forceinline__ double cf_powi(double b, int p) { // p >= 1, repeated multiplication (uniform p)
+    double r = b;
+    for (int i = 1; i < p; i++) r *= b;
+    return r;
+}
+
+// ---- atom values (FP64) ------------------------------------------------------------------------
+__device__ __forceinline__ double cf_atom_eq(double r2, const cf_atom& A, const double* tbl_lane) {
+    return cf_exp_cv(r2, A.e, tbl_lane);
+}
+// M(g) exp(c g), g = sqrt(r2).  The reference's Taylor branch (src/stationary.jl:139-146) differs from this
+// closed form by < 1e-17 relative for every p, so the value path does not branch.
+__device__ __forceinline__ double cf_atom_matern(double r2, const cf_atom& A, const double* tbl_lane) {
+    double g = cf_sqrt_pos(r2);
+    double e = cf_exp_cv(g, A.e, tbl_lane);
+    int p = A.p;
+    if (p == 0) return e;
+    double mp = A.mat[p];
+    for (int i = p - 1; i >= 0; i--) mp = fma(mp, g, A.mat[i]);
+    return mp * e;
+}
+__device__ __forceinline__ double cf_atom_rq_int(double r2, const cf_atom& A) {
+    double base = fma(r2, A.w, 1.0);
+    return cf_powi(cf_rcp(base), A.p);
+}
+__device__ __forceinline__ double cf_atom_rq_real(double r2, const cf_atom& A) {
+    double base = fma(r2, A.w, 1.0);
+    return pow(base, -A.alpha);
+}
+
+template <int KIND>
+__device__ __forceinline__ double cf_atom_value(double r2, double dt, const cf_atom& A, const double* tbl_lane) {
+    if (KIND == CF_ATOM_EQ) return cf_atom_eq(r2, A, tbl_lane);
+    if (KIND == CF_ATOM_MATERN) return cf_atom_matern(r2, A, tbl_lane);
+    if (KIND == CF_ATOM_RQ_INT) return cf_atom_rq_int(r2, A);
+    if (KIND == CF_ATOM_RQ_REAL) return cf_atom_rq_real(r2, A);
+    return dt + A.sigma; // LINE
+}
+
+__device__ __forceinline__ double cf_atom_value_dyn(double r2, double dt, const cf_atom& A, const double* tbl_lane) {
+    switch (A.kind) {
+        case CF_ATOM_EQ: return cf_atom_eq(r2, A, tbl_lane);
+        case CF_ATOM_MATERN: return cf_atom_matern(r2, A, tbl_lane);
+        case CF_ATOM_RQ_INT: return cf_atom_rq_int(r2, A);
+        case CF_ATOM_RQ_REAL: return cf_atom_rq_real(r2, A);
+        default: return dt + A.sigma;
+    }
+}
+
+// generic sum of products (program in global memory, warp-uniform control flow)
+__device__ __forceinline__ double cf_sop_value(double r2, double dt, const cf_program* __restrict__ P, const double* tbl_lane) {
+    double val = 0.0;
+    const int nt = P->nterms;
+    for (int t = 0; t < nt; t++) {
+        const cf_term& T = P->terms[t];
+        double prod = T.coef;
+        for (int f = 0; f < T.nfac; f++) {
+            double a = cf_atom_value_dyn(r2, dt, P->atoms[T.fac[f].atom], tbl_lane);
+            prod *= cf_powi(a, T.fac[f].power);
+        }
+        val += prod;
+    }
+    return val;
+}
+
+// ---- derivatives with respect to r2 (gradient kernel; reference src/gradient.jl:589-600) -------------
+// returns k, k1 = dk/dr2, k2 = d2k/dr2^2 of one isotropic atom
+__device__ __forceinline__ void cf_atom_jet(double r2, const cf_atom& A, const double* tbl_lane, double& k, double& k1, double& k2) {
+    switch (A.kind) {
+        case CF_ATOM_EQ: {
+            k = cf_exp_cv(r2, A.e, tbl_lane);
+            k1 = A.e.c * k;
+            k2 = A.e.c * k1;
+            return;
+        }
+        case CF_ATOM_MATERN: {
+            const int p = A.p;
+            const double s = r2 * A.inv_l2; // the inner kernel sees r2 / l^2 (reference src/transformation.jl:19)
+            if (s < A.taylor_bound) { // reference src/stationary.jl:139-146 (differentiated through by ForwardDiff)
+                double v = 0, d1 = 0, d2 = 0;
+                for (int i = p; i >= 0; i--) { // Horner with derivatives
+                    d2 = fma(d2, s, 2.0 * d1);
+                    d1 = fma(d1, s, v);
+                    v = fma(v, s, A.tay[i]);
+                }
+                k = v; k1 = d1 * A.inv_l2; k2 = d2 * A.inv_l2 * A.inv_l2;
+                return;
+            }
+            double g = cf_sqrt_pos(r2);
+            double e = cf_exp_cv(g, A.e, tbl_lane);
+            double m = A.mat[p], a = (p >= 1) ? A.matA[p - 1] : 0.0, b = (p >= 2) ? A.matB[p - 2] : 0.0;
+            for (int i = p - 1; i >= 0; i--) m = fma(m, g, A.mat[i]);
+            for (int i = p - 2; i >= 0; i--) a = fma(a, g, A.matA[i]);
+            for (int i = p - 3; i >= 0; i--) b = fma(b, g, A.matB[i]);
+            if (A.am1 != 0.0 || A.bm[0] != 0.0 || A.bm[1] != 0.0 || A.bm[2] != 0.0) { // p <= 1: singular terms
+                double gi = 1.0 / g;
+                a = fma(A.am1, gi, a);
+                b += gi * (A.bm[0] + gi * (A.bm[1] + gi * A.bm[2]));
+            }
+            k = m * e; k1 = a * e; k2 = b * e;
+            return;
+        }
+        case CF_ATOM_RQ_INT:
+        case CF_ATOM_RQ_REAL: {
+            double base = fma(r2, A.w, 1.0);
+            double ib = 1.0 / base;
+            k = (A.kind == CF_ATOM_RQ_INT) ? cf_powi(ib, A.p) : pow(base, -A.alpha);
+            k1 = -A.alpha * A.w * k * ib;
+            k2 = -(A.alpha + 1.0) * A.w * k1 * ib;
+            return;
+        }
+        default: k = k1 = k2 = 0.0 / 0.0; return; // LINE is not isotropic
+    }
+}
+
+// jets of the generic isotropic sum of products: product rule over factors, powers by repeated multiplication
+__device__ __forceinline__ void cf_sop_jet(double r2, const cf_program* __restrict__ P, const double* tbl_lane, double& k,
+                                           double& k1, double& k2) {
+    double sv = 0, s1 = 0, s2 = 0;
+    for (int t = 0; t < P->nterms; t++) {
+        const cf_term& T = P->terms[t];
+        double pv = T.coef, p1 = 0, p2 = 0;
+        for (int f = 0; f < T.nfac; f++) {
+            double av, a1, a2;
+            cf_atom_jet(r2, P->atoms[T.fac[f].atom], tbl_lane, av, a1, a2);
+            for (int q = 0; q < T.fac[f].power; q++) {
+                double nv = pv * av;
+                double n1 = fma(p1, av, pv * a1);
+                double n2 = fma(p2, av, fma(2.0 * p1, a1, pv * a2));
+                pv = nv; p1 = n1; p2 = n2;
+            }
+        }
+        sv += pv; s1 += p1; s2 += p2;
+    }
+    k = sv; k1 = s1; k2 = s2;
+}
+
+// ---- FP32 ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float cf_ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float cf_rsqrtf(float x) { float y; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float cf_rcpf(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float cf_lg2f(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+#define CF_LOG2E_F 1.4426950408889634f
+
+__device__ __forceinline__ float cf_atom_value_f32(float r2, float dt, const cf_atom& A) {
+    switch (A.kind) {
+        case CF_ATOM_EQ: return cf_ex2f(r2 * (float)(A.e.c * 1.4426950408889634));
+        case CF_ATOM_MATERN: {
+            float g = (r2 > 0.f) ? r2 * cf_rsqrtf(r2) : 0.f;
+            float e = cf_ex2f(g * (float)(A.e.c * 1.4426950408889634));
+            int p = A.p;
+            if (p == 0) return e;
+            float mp = (float)A.mat[p];
+            for (int i = p - 1; i >= 0; i--) mp = fmaf(mp, g, (float)A.mat[i]);
+            return mp * e;
+        }
+        case CF_ATOM_RQ_INT: {
+            float ib = cf_rcpf(fmaf(r2, (float)A.w, 1.0f));
+            float r = ib;
+            for (int i = 1; i < A.p; i++) r *= ib;
+            return r;
+        }
+        case CF_ATOM_RQ_REAL: {
+            float base = fmaf(r2, (float)A.w, 1.0f);
+            return cf_ex2f(-(float)A.alpha * cf_lg2f(base));
+        }
+        default: return dt + (float)A.sigma;
+    }
+}
+__device__ __forceinline__ float cf_sop_value_f32(float r2, float dt, const cf_program* __restrict__ P) {
+    float val = 0.f;
+    for (int t = 0; t < P->nterms; t++) {
+        const cf_term& T = P->terms[t];
+        float prod = (float)T.coef;
+        for (int f = 0; f < T.nfac; f++) {
+            float a = cf_atom_value_f32(r2, dt, P->atoms[T.fac[f].atom]);
+            float r = a;
+            for (int q = 1; q < T.fac[f].power; q++) r *= a;
+            prod *= r;
+        }
+        val += prod;
+    }
+    return val;
+}

@@ -1,0 +1,49 @@
+// cf_registry.h -- table of compiled kernel instantiations, one entry per padded point dimension D.
+#pragma once
+#include "gram_mvm.cuh"
+#include "grad_mvm.cuh"
+#include "cf_extra.cuh"
+
+#define CF_NKINDS 4 /* EQ, MATERN, RQ_INT, SOP */
+inline int cf_kind_slot(int kind) {
+    switch (kind) {
+        case CF_ATOM_EQ: return 0;
+        case CF_ATOM_MATERN: return 1;
+        case CF_ATOM_RQ_INT: return 2;
+        default: return 3;
+    }
+}
+
+struct cf_kernel_entry {
+    int D;
+    cf_mvm_launch_fn mvm[2][CF_NKINDS]; // [dtype][kind slot]
+    cf_mvm_config mvm_cfg[2];
+    cf_grad_launch_fn grad;
+    cf_mvm_config grad_cfg;
+    cf_mm_launch_fn mm[2]; // [dtype]
+};
+
+// tuning per D: rows per thread R, threads NT, tile TJ, stages NS, min CTAs/SM
+template <int D> struct cf_tune {
+    static constexpr int R = (D <= 4) ? 4 : (D <= 16 ? 2 : 1);
+    static constexpr int NT = 256;
+    static constexpr int TJ = (D <= 8) ? 128 : 64;
+    static constexpr int NS = 3;
+    static constexpr int MINB = (D <= 8) ? 2 : 1;
+    // gradient kernel
+    static constexpr int GR = (D <= 4) ? 2 : 1;
+    static constexpr int GNT = (D <= 16) ? 256 : 128;
+    static constexpr int GTJ = (D <= 8) ? 128 : (D <= 16 ? 64 : 32);
+    static constexpr int GMINB = (D <= 6) ? 2 : 1;
+};
+
+const cf_kernel_entry* cf_kernels_d1();
+const cf_kernel_entry* cf_kernels_d2();
+const cf_kernel_entry* cf_kernels_d3();
+const cf_kernel_entry* cf_kernels_d4();
+const cf_kernel_entry* cf_kernels_d6();
+const cf_kernel_entry* cf_kernels_d8();
+const cf_kernel_entry* cf_kernels_d12();
+const cf_kernel_entry* cf_kernels_d16();
+const cf_kernel_entry* cf_kernels_d24();
+const cf_kernel_entry* cf_kernels_d32();

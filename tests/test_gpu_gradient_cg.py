@@ -1,0 +1,116 @@
+"""GPU parity for the isotropic GradientKernel MVM (reference src/gramian.jl:241-253, src/gradient.jl:86-92,
+tests test/gradient.jl:16-63) and the on-device CG solve (src/lazy_linear_algebra.jl:126-144)."""
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+
+
+def iso_kernels(cf):
+    return {
+        "EQ": cf.EQ(),
+        "MaternP(2)": cf.MaternP(2),
+        "MaternP(3)": cf.MaternP(3),
+        "MaternP(1)": cf.MaternP(1),
+        "RQ(2)": cf.RQ(2),
+        "RQ(1.5)": cf.RQ(1.5),
+        "0.7*EQ": 0.7 * cf.EQ(),
+        "Lengthscale(EQ,0.6)": cf.Lengthscale(cf.EQ(), 0.6),
+        "Lengthscale(MaternP(2),2.0)": cf.Lengthscale(cf.MaternP(2), 2.0),
+        "EQ+RQ(2)": cf.EQ() + cf.RQ(2),
+        "EQ*MaternP(2)": cf.EQ() * cf.MaternP(2),
+    }
+
+
+@pytest.mark.parametrize("name", list(iso_kernels(__import__("covfn_b200")).keys()))
+@pytest.mark.parametrize("d", [1, 2, 5, 16])
+def test_gradient_mvm_vs_oracle(cf, O, name, d):
+    k = iso_kernels(cf)[name]
+    rng = np.random.default_rng(zlib.crc32(f"{name}-{d}".encode()))
+    n, m = 70, 131
+    X = rng.standard_normal((n, d)) / np.sqrt(d)  # test/gradient.jl:18
+    Y = rng.standard_normal((m, d)) / np.sqrt(d)
+    a = rng.standard_normal(m * d)
+    G = cf.gramian(cf.GradientKernel(k), X.T.copy(), Y.T.copy())
+    assert G.shape == (n * d, m * d)  # test/gradient.jl:35
+    b = G @ a
+    ref = O.gradient_mul(k.program(), X, a, Y=Y)
+    assert relerr(b, ref) < 1e-12
+    # 5-argument mul! with random alpha, beta against the dense matrix (test/gradient.jl:47-52)
+    alpha, beta = rng.standard_normal(2)
+    y0 = rng.standard_normal(n * d)
+    y = y0.copy()
+    cf.mul_(y, G, a, alpha, beta)
+    M = O.gradient_matrix(k.program(), X, Y)
+    assert relerr(y, alpha * (M @ a) + beta * y0) < 1e-12
+
+
+def test_gradient_symmetric_diagonal_blocks(cf, O):
+    # x === y: diagonal blocks take k'(0), k''(0) -- the MaternP Taylor branch (src/stationary.jl:139-146)
+    rng = np.random.default_rng(21)
+    n, d = 90, 5
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    a = rng.standard_normal(n * d)
+    for k in (cf.EQ(), cf.MaternP(2), cf.MaternP(3), cf.RQ(2)):
+        G = cf.gramian(cf.GradientKernel(k), X.T.copy())
+        assert relerr(G @ a, O.gradient_mul(k.program(), X, a)) < 1e-12, repr(k)
+
+
+def test_gradient_config4_shape(cf, O):
+    # BASELINE config 4 shape at reduced n: GradientKernel(EQ), d = 16
+    rng = np.random.default_rng(22)
+    n, d = 2048, 16
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    a = rng.standard_normal(n * d)
+    k = cf.EQ()
+    G = cf.gramian(cf.GradientKernel(k), X.T.copy())
+    b = G @ a
+    rows = (100, 356)
+    ref = O.gradient_mul(k.program(), X, a, rows=rows)
+    assert relerr(b[rows[0] * d:rows[1] * d], ref) < 1e-12
+
+
+def test_gradient_rejects_dot(cf):
+    X = np.random.default_rng(0).standard_normal((3, 10))
+    G = cf.gramian(cf.GradientKernel(cf.Dot() ** 3), X)
+    with pytest.raises(cf.UnsupportedKernel):
+        G @ np.ones(30)
+
+
+def test_cg_solve(cf, O):
+    # config 5 at reduced size: (K + sigma2 I) \ y with MaternP(2), d = 8
+    rng = np.random.default_rng(31)
+    n, d = 1500, 8
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    y = rng.standard_normal(n)
+    k = cf.MaternP(2)
+    sigma2 = 1e-2
+    G = cf.gramian(k, X.T.copy())
+    A = sigma2 * cf.I(n) + G
+    assert isinstance(A, cf.LazyMatrixSum)  # test/gramian.jl:51-53
+    x, iters, res = A.solve(y)
+    xo, ito, reso, hist = O.cg_solve(k.program(), X, y, sigma2)
+    assert abs(iters - ito) <= 2
+    assert relerr(x, xo) < 1e-6  # CG amplifies rounding by the condition number; both satisfy the residual bound
+    r = y - (A @ x)
+    assert np.linalg.norm(r) / np.linalg.norm(y) < 1e-6  # test/gradient.jl:62
+    # operator product itself
+    v = rng.standard_normal(n)
+    assert relerr(A @ v, sigma2 * v + O.mul_vec(k.program(), X, v)) < 1e-12
+
+
+def test_cg_gradient_operator(cf, O):
+    rng = np.random.default_rng(32)
+    n, d = 60, 4
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    k = cf.MaternP(3)
+    G = cf.gramian(cf.GradientKernel(k), X.T.copy())
+    a = rng.standard_normal(n * d)
+    Ka = G @ a
+    A = 1e-8 * cf.I(n * d) + G
+    x, iters, res = A.solve(Ka, reltol=1e-10, maxiter=2000)
+    assert np.linalg.norm((G @ x) - Ka) / np.linalg.norm(Ka) < 1e-6  # test/gradient.jl:56-63

@@ -1,0 +1,208 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle on identical seeded inputs.
+
+Tolerance from BASELINE.json north_star: relative 2-norm <= 1e-12 in Float64, <= 1e-5 in Float32.
+Mirrors the reference's own tests: lazy product vs dense product on rectangular Gramians (test/gramian.jl:56-72),
+entries vs k(x[i], y[j]) (test/gramian.jl:75-80), kernel algebra (test/algebra.jl:28-51), Dot/Poly (test/mercer.jl:12-19).
+"""
+import zlib
+
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-12
+TOL32 = 1e-5
+
+
+def kernels(cf):
+    return {
+        "EQ": cf.EQ(),
+        "Exp": cf.Exp(),
+        "RQ(2)": cf.RQ(2),
+        "RQ(1)": cf.RQ(1),
+        "RQ(2.5)": cf.RQ(2.5),
+        "MaternP(0)": cf.MaternP(0),
+        "MaternP(1)": cf.MaternP(1),
+        "MaternP(2)": cf.MaternP(2),
+        "MaternP(3)": cf.MaternP(3),
+        "MaternP(5)": cf.MaternP(5),
+        "Dot": cf.Dot(),
+        "Dot^3": cf.Dot() ** 3,
+        "Poly(3,1)": cf.Poly(3, 1.0),
+        "Line(0.5)": cf.Line(0.5),
+        "0.5*EQ": 0.5 * cf.EQ(),
+        "EQ+Exp": cf.EQ() + cf.Exp(),
+        "EQ*RQ(2)": cf.EQ() * cf.RQ(2),
+        "C3": 0.5 * cf.RQ(2) + cf.Dot() ** 2,
+        "Lengthscale(EQ,0.7)": cf.Lengthscale(cf.EQ(), 0.7),
+        "Lengthscale(MaternP(2),1.3)": cf.Lengthscale(cf.MaternP(2), 1.3),
+        "(EQ+MaternP(1))^2": (cf.EQ() + cf.MaternP(1)) ** 2,
+        "2*EQ+1": 2 * cf.EQ() + 1,
+    }
+
+
+@pytest.mark.parametrize("name", list(kernels(__import__("covfn_b200")).keys()))
+@pytest.mark.parametrize("d", [1, 3, 5])
+def test_mvm_vs_oracle_f64(cf, O, name, d):
+    k = kernels(cf)[name]
+    rng = np.random.default_rng(zlib.crc32(f"{name}-{d}".encode()))
+    n, m = 257, 515  # rectangular, ragged against every tile size (test/gramian.jl:56-63)
+    X = rng.standard_normal((n, d))
+    Y = rng.standard_normal((m, d))
+    a = rng.standard_normal(m)
+    G = cf.gramian(k, X.T.copy(), Y.T.copy())
+    assert G.shape == (n, m)
+    b = G @ a
+    ref = O.mul_vec(k.program(), X, a, Y=Y)
+    assert relerr(b, ref) < TOL64
+    # 5-argument form with NaN-filled y and beta = 0 (src/gramian.jl:80), then alpha/beta
+    y = np.full(n, np.nan)
+    cf.mul_(y, G, a, 1.0, 0.0)
+    assert relerr(y, ref) < TOL64
+    y0 = rng.standard_normal(n)
+    y = y0.copy()
+    cf.mul_(y, G, a, -0.7, 1.9)
+    ref2 = O.mul_vec(k.program(), X, a, Y=Y, alpha=-0.7, beta=1.9, y0=y0)
+    assert relerr(y, ref2) < TOL64
+
+
+@pytest.mark.parametrize("d", [1, 2, 3, 4, 6, 7, 8, 11, 16, 20, 32])
+def test_mvm_all_dims(cf, O, d):
+    rng = np.random.default_rng(d)
+    n = 300
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    a = rng.standard_normal(n)
+    for k in (cf.EQ(), cf.MaternP(2), cf.RQ(2), 0.5 * cf.RQ(2) + cf.Dot() ** 2):
+        G = cf.gramian(k, X.T.copy())
+        assert relerr(G @ a, O.mul_vec(k.program(), X, a)) < TOL64
+
+
+def test_symmetric_large_two_level(cf, O):
+    # several column chunks + TMA ring wrap-around (n large enough for > 3 tiles per chunk)
+    rng = np.random.default_rng(7)
+    n, d = 16384, 3
+    X = rng.standard_normal((n, d))
+    a = rng.standard_normal(n)
+    k = cf.MaternP(2)  # BASELINE config 1
+    G = cf.gramian(k, X.T.copy())
+    b = np.zeros(n)
+    cf.mul_(b, G, a)
+    rows = (0, 2048)
+    ref = O.mul_vec(k.program(), X, a, rows=rows)
+    assert relerr(b[rows[0]:rows[1]], ref) < TOL64
+    truth = O.truth_mul_vec(k.program(), X, a, rows=rows)
+    # both are rounding-close to the exact product; ours must not be worse than 4x the oracle's own error
+    assert relerr(b[rows[0]:rows[1]], truth) < max(4 * relerr(ref, truth), 1e-14)
+
+
+def test_entries_and_dense(cf, O):
+    rng = np.random.default_rng(3)
+    X = rng.standard_normal((37, 3))
+    Y = rng.standard_normal((53, 3))
+    for name, k in kernels(cf).items():
+        G = cf.gramian(k, X.T.copy(), Y.T.copy())
+        M = G.Matrix()
+        Mo = O.matrix(k.program(), X, Y)
+        assert M.shape == (37, 53)
+        assert relerr(M, Mo) < 1e-13, name
+        for (i, j) in [(0, 0), (5, 7), (36, 52)]:
+            assert abs(G[i, j] - k(X[i], Y[j])) <= 1e-13 * max(1.0, abs(k(X[i], Y[j]))), name  # test/gramian.jl:75-80
+
+
+def test_multi_rhs(cf, O):
+    rng = np.random.default_rng(11)
+    n, m, d, p = 130, 260, 3, 3  # test/gramian.jl:65-72
+    X = rng.standard_normal((n, d))
+    Y = rng.standard_normal((m, d))
+    A = rng.standard_normal((m, p))
+    for k in (cf.EQ(), 0.5 * cf.RQ(2) + cf.Dot() ** 2):
+        G = cf.gramian(k, X.T.copy(), Y.T.copy())
+        B = G @ A
+        assert B.shape == (n, p)
+        ref = O.mul_mat(k.program(), X, A, Y=Y)
+        assert relerr(B, ref) < TOL64
+        B0 = rng.standard_normal((n, p))
+        B1 = np.asfortranarray(B0.copy())
+        cf.mul_(B1, G, A, 0.3, -1.1)
+        ref = O.mul_mat(k.program(), X, A, Y=Y, alpha=0.3, beta=-1.1, B0=B0)
+        assert relerr(B1, ref) < TOL64
+    # wide block: more than one 64-column pass, d = 32 (BASELINE config 3 shape, small n)
+    n, d, p = 200, 32, 70
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    A = rng.standard_normal((n, p))
+    k = 0.5 * cf.RQ(2) + cf.Dot() ** 2
+    G = cf.gramian(k, X.T.copy())
+    assert relerr(G @ A, O.mul_mat(k.program(), X, A)) < TOL64
+
+
+def test_float32(cf, O):
+    rng = np.random.default_rng(5)
+    n, m, d = 400, 300, 3
+    X = rng.standard_normal((n, d)).astype(np.float32)
+    Y = rng.standard_normal((m, d)).astype(np.float32)
+    a = rng.standard_normal(m).astype(np.float32)
+    for k in (cf.EQ(), cf.Exp(), cf.RQ(2), cf.MaternP(2), cf.Dot() ** 2, 0.5 * cf.RQ(2) + cf.Dot() ** 2):
+        G = cf.gramian(k, X.T.copy(), Y.T.copy())
+        assert G.eltype == np.float32
+        b = G @ a
+        assert b.dtype == np.float32
+        ref = O.mul_vec(k.program(), X, a, Y=Y, dtype=np.float32)
+        assert relerr(b, ref) < TOL32, repr(k)
+
+
+def test_edge_cases(cf, O):
+    rng = np.random.default_rng(9)
+    k = cf.EQ()
+    # single point, single column
+    X = rng.standard_normal((1, 3))
+    G = cf.gramian(k, X.T.copy())
+    assert relerr(G @ np.array([2.0]), np.array([2.0])) < 1e-15
+    # duplicated points (r2 == 0 off the diagonal) for the sqrt-based kernels
+    X = np.repeat(rng.standard_normal((5, 2)), 3, axis=0)
+    a = rng.standard_normal(15)
+    for kk in (cf.Exp(), cf.MaternP(2), cf.MaternP(1)):
+        Gd = cf.gramian(kk, X.T.copy())
+        assert relerr(Gd @ a, O.mul_vec(kk.program(), X, a)) < TOL64
+    # far-apart points: exp underflow must give 0, not garbage
+    X = np.array([[0.0, 0.0], [1e3, 0.0], [1e7, 1e7], [1e150, 0.0]])
+    a = np.ones(4)
+    for kk in (cf.EQ(), cf.Exp(), cf.MaternP(2)):
+        Gd = cf.gramian(kk, X.T.copy())
+        b = Gd @ a
+        assert np.all(np.isfinite(b))
+        assert relerr(b, O.mul_vec(kk.program(), X, a)) < TOL64
+    # empty column set: y = beta*y
+    G0 = cf.gramian(k, rng.standard_normal((3, 4)), rng.standard_normal((3, 0)))
+    y = np.ones(4)
+    cf.mul_(y, G0, np.zeros(0), 1.0, 2.0)
+    assert np.allclose(y, 2.0)
+    # NaN coordinate is rejected at create time
+    Xn = rng.standard_normal((4, 3))
+    Xn[2, 1] = np.nan
+    with pytest.raises(cf.DomainError):
+        cf.gramian(k, Xn.T.copy()) @ np.ones(4)
+    # NaN weights propagate like the reference
+    X = rng.standard_normal((8, 3))
+    a = rng.standard_normal(8)
+    a[3] = np.nan
+    assert np.all(np.isnan(cf.gramian(k, X.T.copy()) @ a))
+    # dimension mismatch
+    with pytest.raises(cf.DimensionMismatch):
+        cf.gramian(k, X.T.copy()) @ np.ones(9)
+
+
+def test_row_range(cf, O):
+    rng = np.random.default_rng(13)
+    n, d = 1000, 3
+    X = rng.standard_normal((n, d))
+    a = rng.standard_normal(n)
+    k = cf.MaternP(2)
+    full = cf.gramian(k, X.T.copy()) @ a
+    parts = []
+    for r in range(3):
+        G = cf.gramian(k, X.T.copy()).set_row_range(n * r // 3, n * (r + 1) // 3)
+        parts.append(G @ a)
+    assert np.array_equal(np.concatenate(parts), full)  # sharding does not change a single bit

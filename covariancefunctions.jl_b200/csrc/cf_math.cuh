@@ -85,8 +85,11 @@ __device__ __forceinline__ double cf_atom_eq(double r2, const cf_atom& A, const 
 }
 // M(g) exp(c g), g = sqrt(r2).  The reference's Taylor branch (src/stationary.jl:139-146) differs from this
 // closed form by < 1e-17 relative for every p, so the value path does not branch.
+__device__ __forceinline__ double cf_clamp_v(double v, const cf_exp_consts& E) {
+    return __hiloint2double(min(__double2hiint(v), E.vmax_hi), __double2loint(v));
+}
 __device__ __forceinline__ double cf_atom_matern(double r2, const cf_atom& A, const double* tbl_lane) {
-    double g = cf_sqrt_pos(r2);
+    double g = cf_clamp_v(cf_sqrt_pos(r2), A.e); // clamp BEFORE the polynomial: M(g) e^{cg} with g ~ 1e150 must be 0, not M(g) * 1e-304
     double e = cf_exp_cv(g, A.e, tbl_lane);
     int p = A.p;
     if (p == 0) return e;
@@ -161,7 +164,7 @@ __device__ __forceinline__ void cf_atom_jet(double r2, const cf_atom& A, const d
                 k = v; k1 = d1 * A.inv_l2; k2 = d2 * A.inv_l2 * A.inv_l2;
                 return;
             }
-            double g = cf_sqrt_pos(r2);
+            double g = cf_clamp_v(cf_sqrt_pos(r2), A.e);
             double e = cf_exp_cv(g, A.e, tbl_lane);
             double m = A.mat[p], a = (p >= 1) ? A.matA[p - 1] : 0.0, b = (p >= 2) ? A.matB[p - 2] : 0.0;
             for (int i = p - 1; i >= 0; i--) m = fma(m, g, A.mat[i]);
@@ -223,6 +226,7 @@ __device__ __forceinline__ float cf_atom_value_f32(float r2, float dt, const cf_
         case CF_ATOM_EQ: return cf_ex2f(r2 * (float)(A.e.c * 1.4426950408889634));
         case CF_ATOM_MATERN: {
             float g = (r2 > 0.f) ? r2 * cf_rsqrtf(r2) : 0.f;
+            g = fminf(g, (float)A.e.vmax * 0.125f); // e^{c g} < 1e-38 beyond this; keeps M(g) e^{cg} = 0 for far points
             float e = cf_ex2f(g * (float)(A.e.c * 1.4426950408889634));
             int p = A.p;
             if (p == 0) return e;

@@ -41,13 +41,17 @@ def _points(x, dtype=None):
 class Gramian:
     """Gramian{T,K,U,V} (src/gramian.jl:10-14): K[i, j] = k(x[i], y[j]), never instantiated."""
 
-    def __init__(self, k, x, y=None):
+    def __init__(self, k, x, y=None, _rows_are_points=False):
         if not isinstance(k, (AbstractKernel, GradientKernel)):
             raise TypeError("Gramian(k, x, y): k must be a kernel")
         self.k = k
-        self.x = _points(x)
         self._symmetric = y is None or y is x
-        self.y = self.x if self._symmetric else _points(y, self.x.dtype)
+        if _rows_are_points:  # internal: already (n, d) point arrays
+            self.x = x
+            self.y = x if self._symmetric else y
+        else:
+            self.x = _points(x)
+            self.y = self.x if self._symmetric else _points(y, self.x.dtype)
         if self.x.shape[1] != self.y.shape[1]:
             raise DimensionMismatch(
                 f"inputs have to have the same length: {self.x.shape[1]}, {self.y.shape[1]}")  # src/util.jl:41
@@ -78,7 +82,7 @@ class Gramian:
 
     @property
     def T(self):  # adjoint / transpose (src/gramian.jl:116-117)
-        return Gramian(self.k, self.y, self.x)
+        return Gramian(self.k, self.y, None if self._symmetric else self.x, _rows_are_points=True)
 
     # ---- device handle -----------------------------------------------------------------------------------------
     def handle(self):

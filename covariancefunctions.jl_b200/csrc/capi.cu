@@ -99,7 +99,9 @@ struct Shard {
     void* X = nullptr;  // n x D padded points (all rows, replicated)
     void* Y = nullptr;  // m x D (== X when symmetric)
     cf_program* d_prog = nullptr;
-    Buf a, y, partial, apad, ypad, cg[6];
+    void* xn = nullptr;  // squared norms of the padded points (multi-RHS kernel)
+    void* yn = nullptr;
+    Buf a, y, partial, apad, ypad, at, cg[6];
     int64_t r0 = 0, r1 = 0; // rows owned
 };
 
@@ -109,6 +111,7 @@ struct cf_gramian_s {
     int dtype = CF_F64, d = 0, D = 0;
     int64_t n = 0, m = 0;
     bool symmetric = false;
+    bool use_norms = false; // multi-RHS kernel may use r2 = |x|^2 + |y|^2 - 2 x.y (well-scaled data, d >= 8)
     int64_t row_begin = 0, row_end = 0;
     cf_program prog;
     int kind = CF_ATOM_SOP; // kernel kind used for the value MVM
@@ -197,19 +200,26 @@ int launch_mm(cf_gramian_s* g, Shard& sh, void* d_B, int64_t ldb, const void* d_
             if (int rc = launch_scale(g->dtype, (char*)d_B + c * ldb * es, (char*)d_B + c * ldb * es, nrows, beta, stream)) return rc;
         return CF_OK;
     }
+    if (int rc = sh.at.ensure((size_t)g->m * CF_MM_PC * es)) return rc;
     cf_mm_params P;
     std::memset(&P, 0, sizeof(P));
-    P.X = sh.X; P.Y = sh.Y;
+    P.X = sh.X; P.Y = sh.Y; P.xn = sh.xn; P.yn = sh.yn; P.At = sh.at.p;
     P.exp2_tbl = sh.ctx->exp2_tbl; P.prog = sh.d_prog;
-    P.row0 = sh.r0; P.nrows = nrows; P.m = g->m; P.lda = lda; P.ldb = ldb;
+    P.row0 = sh.r0; P.nrows = nrows; P.m = g->m; P.ldb = ldb;
     P.alpha = alpha; P.beta = beta;
+    P.use_norms = g->use_norms ? 1 : 0;
     const int row_tiles = (int)((nrows + CF_MM_TI - 1) / CF_MM_TI);
     for (int64_t c0 = 0; c0 < nrhs; c0 += CF_MM_PC) {
         P.nrhs = (int)std::min<int64_t>(CF_MM_PC, nrhs - c0);
-        P.A = (const char*)d_A + c0 * lda * es;
+        const dim3 tg((unsigned)((g->m + 31) / 32), CF_MM_PC / 32), tb(32, 8);
+        if (g->dtype == CF_F64)
+            cf_transpose_rhs<double><<<tg, tb, 0, stream>>>((const double*)d_A + c0 * lda, lda, g->m, P.nrhs, (double*)sh.at.p);
+        else
+            cf_transpose_rhs<float><<<tg, tb, 0, stream>>>((const float*)d_A + c0 * lda, lda, g->m, P.nrhs, (float*)sh.at.p);
+        CF_CUDA(cudaGetLastError());
         P.B = (char*)d_B + c0 * ldb * es;
         CF_CUDA(g->entry->mm[g->dtype](P, row_tiles, stream));
-        g->last_launches++;
+        g->last_launches += 2;
     }
     return CF_OK;
 }
@@ -347,7 +357,8 @@ int peak_probe_impl(int kind, int iters, double* lane_ops_per_s, float* ms_out) 
     cudaEventDestroy(e1);
     cudaFree(out);
     if (ms_out) *ms_out = best;
-    if (lane_ops_per_s) *lane_ops_per_s = (double)blocks * threads * (double)iters * 8.0 / (best * 1e-3);
+    iters = ((iters + 7) / 8) * 8;
+    if (lane_ops_per_s) *lane_ops_per_s = (double)blocks * threads * (double)iters * 16.0 / (best * 1e-3);
     return CF_OK;
 }
 
@@ -443,14 +454,18 @@ int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, co
 }
 
 template <typename T>
-int pack_points(const T* X, int64_t ldx, int64_t n, int d, int D, std::vector<T>& out) {
+int pack_points(const T* X, int64_t ldx, int64_t n, int d, int D, std::vector<T>& out, double* max_sqnorm) {
     out.assign((size_t)n * D, (T)0);
-    for (int64_t i = 0; i < n; i++)
+    for (int64_t i = 0; i < n; i++) {
+        double s = 0;
         for (int c = 0; c < d; c++) {
             T v = X[i * ldx + c];
             if (!std::isfinite((double)v)) return fail(CF_ERR_NONFINITE, "point %lld coordinate %d is not finite", (long long)i, c);
             out[(size_t)i * D + c] = v;
+            s += (double)v * (double)v;
         }
+        if (s > *max_sqnorm) *max_sqnorm = s;
+    }
     return CF_OK;
 }
 
@@ -460,7 +475,9 @@ int destroy_impl(cf_gramian_s* g) {
         if (sh.Y && sh.Y != sh.X) cudaFree(sh.Y);
         if (sh.X) cudaFree(sh.X);
         if (sh.d_prog) cudaFree(sh.d_prog);
-        sh.a.release(); sh.y.release(); sh.partial.release(); sh.apad.release(); sh.ypad.release();
+        if (sh.yn && sh.yn != sh.xn) cudaFree(sh.yn);
+        if (sh.xn) cudaFree(sh.xn);
+        sh.a.release(); sh.y.release(); sh.partial.release(); sh.apad.release(); sh.ypad.release(); sh.at.release();
         for (auto& b : sh.cg) b.release();
         if (sh.ev0) cudaEventDestroy(sh.ev0);
         if (sh.ev1) cudaEventDestroy(sh.ev1);
@@ -550,14 +567,21 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
     std::vector<double> xd, yd;
     std::vector<float> xf, yf;
     int rc = CF_OK;
+    double max_sq = 0;
     if (dtype == CF_F64) {
-        rc = pack_points<double>((const double*)X, ldx, n, d, g->D, xd);
-        if (!rc && Y) rc = pack_points<double>((const double*)Y, ldy, m, d, g->D, yd);
+        rc = pack_points<double>((const double*)X, ldx, n, d, g->D, xd, &max_sq);
+        if (!rc && Y) rc = pack_points<double>((const double*)Y, ldy, m, d, g->D, yd, &max_sq);
     } else {
-        rc = pack_points<float>((const float*)X, ldx, n, d, g->D, xf);
-        if (!rc && Y) rc = pack_points<float>((const float*)Y, ldy, m, d, g->D, yf);
+        rc = pack_points<float>((const float*)X, ldx, n, d, g->D, xf, &max_sq);
+        if (!rc && Y) rc = pack_points<float>((const float*)Y, ldy, m, d, g->D, yf, &max_sq);
     }
     if (rc) { delete g; return rc; }
+    // r2 from norms only for larger d and well-scaled data: |delta r2| <= (d + 2) eps (|x|^2 + |y|^2) must stay below 1e-13
+    {
+        const double eps = dtype == CF_F64 ? 2.220446049250313e-16 : 1.1920928955078125e-07;
+        const double bound = dtype == CF_F64 ? 1e-13 : 1e-5;
+        g->use_norms = (d >= 8) && ((d + 2) * eps * 2.0 * max_sq < bound);
+    }
     const void* hx = dtype == CF_F64 ? (const void*)xd.data() : (const void*)xf.data();
     const void* hy = dtype == CF_F64 ? (const void*)yd.data() : (const void*)yf.data();
     const size_t es = esize(dtype);
@@ -589,6 +613,21 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
         }
         CF_CREATE_CUDA(cudaMalloc(&sh.d_prog, sizeof(cf_program)));
         CF_CREATE_CUDA(cudaMemcpy(sh.d_prog, &g->prog, sizeof(cf_program), cudaMemcpyHostToDevice));
+        CF_CREATE_CUDA(cudaMalloc(&sh.xn, std::max<size_t>(16, (size_t)n * es)));
+        if (Y) CF_CREATE_CUDA(cudaMalloc(&sh.yn, std::max<size_t>(16, (size_t)m * es)));
+        else sh.yn = sh.xn;
+        {
+            const int nb = (int)std::min<int64_t>((std::max<int64_t>(n, m) + 255) / 256 + 1, 4096);
+            if (dtype == CF_F64) {
+                if (n) cf_sqnorm_kernel<double><<<nb, 256>>>((const double*)sh.X, g->D, n, (double*)sh.xn);
+                if (Y && m) cf_sqnorm_kernel<double><<<nb, 256>>>((const double*)sh.Y, g->D, m, (double*)sh.yn);
+            } else {
+                if (n) cf_sqnorm_kernel<float><<<nb, 256>>>((const float*)sh.X, g->D, n, (float*)sh.xn);
+                if (Y && m) cf_sqnorm_kernel<float><<<nb, 256>>>((const float*)sh.Y, g->D, m, (float*)sh.yn);
+            }
+            CF_CREATE_CUDA(cudaGetLastError());
+            CF_CREATE_CUDA(cudaDeviceSynchronize());
+        }
 #undef CF_CREATE_CUDA
     }
     split_rows(g);

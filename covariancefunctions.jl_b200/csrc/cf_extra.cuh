@@ -19,7 +19,7 @@ __global__ void gram_dense_kernel(const T* __restrict__ X, const T* __restrict__
     __shared__ double tbl[CF_EXP_TBL_DOUBLES];
     cf_fill_exp_table(tbl, exp2_tbl, threadIdx.x, blockDim.x);
     __syncthreads();
-    const double* tbl_lane = tbl + (threadIdx.x & 15);
+    const cf_tbl_t tbl_lane = cf_tbl_lane(tbl, threadIdx.x);
     const int64_t total = nrows * ncols;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
         const int64_t jj = q / nrows, ii = q - jj * nrows;
@@ -38,121 +38,216 @@ __global__ void gram_dense_kernel(const T* __restrict__ X, const T* __restrict__
     }
 }
 
-// ---- K4 (first version): B <- alpha K A + beta B with A m x p, every kernel entry evaluated ONCE -------------------
+// ---- K4: B <- alpha K A + beta B with A m x p: every kernel entry is evaluated ONCE and contracted with a p-wide slice ----
 // (the reference re-evaluates it for each of the p columns: src/gramian.jl:89-99).
-// CTA: TI = 64 rows, tiles of TJ = 64 columns, PC = 64 right-hand sides per pass.
-//   phase A: K tile (TI x TJ) -> shared memory; thread (i = t & 63, jg = t >> 6) evaluates 16 entries of its row with
-//            x_i in registers and y_j read as shared-memory broadcasts.
-//   phase B: B tile (TI x PC) += K tile . A tile with 4 x 4 register tiles per thread (FP64 FMA pipe).
-#define CF_MM_TI 64
-#define CF_MM_TJ 64
+// CTA = 256 threads, TI = 128 rows, tiles of TJ = 32 columns, PC = 64 right-hand sides per pass.
+//   stage  : (y tile, |y|^2 tile, A^T tile) arrive by three 1-D TMA bulk copies into a 2-stage mbarrier ring
+//            (A is transposed once per call to At[j][c] so that a tile is one contiguous block).
+//   phase A: K tile (TI x TJ) -> shared memory.  Thread (i = t & 127, jh = t >> 7) evaluates 16 entries of its row with
+//            x_i in registers; y_j is read as shared-memory broadcasts.  For d >= 8, and when the data is well scaled
+//            (host check: (d + 2) eps max|x|^2 < 1e-13), r2 = |x|^2 + |y|^2 - 2 x.y shares the d FMAs of the dot product
+//            ("r2 from norms"); otherwise direct differences as the reference does.
+//   phase B: B tile (TI x PC) += K tile . A tile with 8 x 4 register tiles per thread: per k, 4 + 2 LDS.128 feed 32 FMAs.
+#define CF_MM_TI 128
+#define CF_MM_TJ 32
 #define CF_MM_PC 64
-#define CF_MM_LDA (CF_MM_PC + 2)
+#define CF_MM_NS 2
 
 template <typename T, int D>
 struct cf_mm_smem {
     static constexpr int tbl_bytes = CF_EXP_TBL_DOUBLES * 8;
-    static constexpr int ks_bytes = CF_MM_TJ * CF_MM_TI * 8;     // Ks[j][i], double
-    static constexpr int as_bytes = CF_MM_TJ * CF_MM_LDA * 8;    // As[j][c], double
-    static constexpr int ys_bytes = CF_MM_TJ * D * (int)sizeof(T);
-    static constexpr int total = tbl_bytes + ks_bytes + as_bytes + ys_bytes;
+    static constexpr int bar_bytes = 128;
+    static constexpr int ks_bytes = CF_MM_TJ * CF_MM_TI * (int)sizeof(T);   // Ks[j][i]
+    static constexpr int y_bytes = CF_MM_TJ * D * (int)sizeof(T);
+    static constexpr int n_bytes = CF_MM_TJ * (int)sizeof(T);
+    static constexpr int a_bytes = CF_MM_TJ * CF_MM_PC * (int)sizeof(T);    // As[j][c]
+    static constexpr int stage_bytes = ((y_bytes + n_bytes + a_bytes + 127) / 128) * 128;
+    static constexpr int total = tbl_bytes + bar_bytes + ks_bytes + CF_MM_NS * stage_bytes;
 };
 
 struct cf_mm_params {
-    const void* X; const void* Y; const void* A; void* B;
+    const void* X; const void* Y; const void* xn; const void* yn; // points and squared norms
+    const void* At;   // transposed weights, m x PC (row j holds the PC columns of this pass, zero padded)
+    void* B;
     const double* exp2_tbl; const cf_program* prog;
-    int64_t row0, nrows, m, lda, ldb;
-    int nrhs;      // columns in this pass (<= CF_MM_PC)
+    int64_t row0, nrows, m, ldb;
+    int nrhs;         // columns in this pass (<= CF_MM_PC)
+    int use_norms;
     double alpha, beta;
 };
 
+// At[j][c] = c < nrhs ? A[j + lda c] : 0   (one pass of <= CF_MM_PC columns)
+template <typename T>
+__global__ void cf_transpose_rhs(const T* __restrict__ A, int64_t lda, int64_t m, int nrhs, T* __restrict__ At) {
+    __shared__ T tile[32][33];
+    const int64_t j0 = (int64_t)blockIdx.x * 32;
+    const int c0 = blockIdx.y * 32;
+    for (int cc = threadIdx.y; cc < 32; cc += blockDim.y) {
+        const int64_t j = j0 + threadIdx.x;
+        const int c = c0 + cc;
+        tile[cc][threadIdx.x] = (j < m && c < nrhs) ? A[j + lda * c] : (T)0;
+    }
+    __syncthreads();
+    for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
+        const int64_t j = j0 + jj;
+        const int c = c0 + threadIdx.x;
+        if (j < m && c < CF_MM_PC) At[j * CF_MM_PC + c] = tile[threadIdx.x][jj];
+    }
+}
+
+// squared norms of padded points
+template <typename T>
+__global__ void cf_sqnorm_kernel(const T* __restrict__ X, int D, int64_t n, T* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        T s = 0;
+        for (int c = 0; c < D; c++) s = fma(X[i * D + c], X[i * D + c], s);
+        out[i] = s;
+    }
+}
+
 template <typename T, int D>
-__global__ void __launch_bounds__(256) gram_mm_kernel(const __grid_constant__ cf_mm_params P) {
+__global__ void __launch_bounds__(256, 1) gram_mm_kernel(const __grid_constant__ cf_mm_params P) {
     using S = cf_mm_smem<T, D>;
     extern __shared__ __align__(128) unsigned char smem[];
     double* tbl = reinterpret_cast<double*>(smem);
-    double* Ks = reinterpret_cast<double*>(smem + S::tbl_bytes);
-    double* As = reinterpret_cast<double*>(smem + S::tbl_bytes + S::ks_bytes);
-    T* ys = reinterpret_cast<T*>(smem + S::tbl_bytes + S::ks_bytes + S::as_bytes);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::tbl_bytes);
+    T* Ks = reinterpret_cast<T*>(smem + S::tbl_bytes + S::bar_bytes);
+    unsigned char* stages = smem + S::tbl_bytes + S::bar_bytes + S::ks_bytes;
     const int tid = threadIdx.x;
-    const double* tbl_lane = tbl + (tid & 15);
+    const cf_tbl_t tbl_lane = cf_tbl_lane(tbl, tid);
     const T* __restrict__ Xg = static_cast<const T*>(P.X);
     const T* __restrict__ Yg = static_cast<const T*>(P.Y);
-    const T* __restrict__ Ag = static_cast<const T*>(P.A);
-    cf_fill_exp_table(tbl, P.exp2_tbl, tid, 256);
+    const T* __restrict__ yng = static_cast<const T*>(P.yn);
+    const T* __restrict__ Atg = static_cast<const T*>(P.At);
+    if (sizeof(T) == 8) cf_fill_exp_table(tbl, P.exp2_tbl, tid, 256);
+    if (tid == 0) {
+        for (int s = 0; s < CF_MM_NS; s++) cf_mbar_init(&bars[s], 1);
+        cf_fence_barrier_init();
+    }
+    __syncthreads();
+    const int nfull = (int)(P.m / CF_MM_TJ);
+    auto issue = [&](int tile) {
+        const int s = tile % CF_MM_NS;
+        unsigned char* st = stages + (size_t)s * S::stage_bytes;
+        const int64_t j0 = (int64_t)tile * CF_MM_TJ;
+        cf_mbar_expect_tx(&bars[s], (uint32_t)(S::y_bytes + S::n_bytes + S::a_bytes));
+        cf_tma_load_1d(st, Yg + j0 * D, (uint32_t)S::y_bytes, &bars[s]);
+        cf_tma_load_1d(st + S::y_bytes, yng + j0, (uint32_t)S::n_bytes, &bars[s]);
+        cf_tma_load_1d(st + S::y_bytes + S::n_bytes, Atg + j0 * CF_MM_PC, (uint32_t)S::a_bytes, &bars[s]);
+    };
+    if (tid == 0)
+        for (int t = 0; t < CF_MM_NS && t < nfull; t++) issue(t);
 
     const int64_t rbase = P.row0 + (int64_t)blockIdx.x * CF_MM_TI;
     const int64_t rend = P.row0 + P.nrows;
-    const int li = tid & 63, jg = tid >> 6;
-    T x[D];
+    const int li = tid & 127, jh = tid >> 7;
+    T x[D], xnorm;
     {
         int64_t i = rbase + li;
         if (i >= rend) i = rend - 1;
 #pragma unroll
         for (int c = 0; c < D; c++) x[c] = Xg[i * D + c];
+        xnorm = static_cast<const T*>(P.xn)[i];
     }
-    const int ri = tid & 15, ci = tid >> 4; // phase B tile: rows 4 ri.., cols 4 ci..
-    double acc[4][4];
+    const int rg = tid & 15, cg = tid >> 4; // phase B tile: rows 8 rg .. 8 rg + 7, columns 4 cg .. 4 cg + 3
+    T acc[8][4];
 #pragma unroll
-    for (int a = 0; a < 4; a++)
+    for (int a = 0; a < 8; a++)
 #pragma unroll
-        for (int b = 0; b < 4; b++) acc[a][b] = 0.0;
+        for (int b = 0; b < 4; b++) acc[a][b] = 0;
 
-    for (int64_t j0 = 0; j0 < P.m; j0 += CF_MM_TJ) {
-        const int cnt = (int)((P.m - j0 < CF_MM_TJ) ? P.m - j0 : CF_MM_TJ);
-        __syncthreads();
-        for (int q = tid; q < cnt * D; q += 256) ys[q] = Yg[j0 * D + q];
-        for (int q = tid; q < CF_MM_TJ * CF_MM_PC; q += 256) {
-            const int c = q / CF_MM_TJ, k = q - c * CF_MM_TJ; // consecutive threads: consecutive k (coalesced in A)
-            As[k * CF_MM_LDA + c] = (k < cnt && c < P.nrhs) ? (double)Ag[(j0 + k) + P.lda * c] : 0.0;
-        }
-        __syncthreads();
+    auto tile_compute = [&](const T* __restrict__ ys, const T* __restrict__ yns, const T* __restrict__ As, int cnt) {
         // phase A
 #pragma unroll 2
-        for (int q = 0; q < 16; q++) {
-            const int j = jg * 16 + q;
-            double kv = 0.0;
+        for (int q = 0; q < CF_MM_TJ / 2; q++) {
+            const int j = jh * (CF_MM_TJ / 2) + q;
+            T kv = 0;
             if (j < cnt) {
                 T r2 = 0, dt = 0;
+                if (P.use_norms) {
 #pragma unroll
-                for (int c = 0; c < D; c++) {
-                    T yv = ys[j * D + c];
-                    T df = x[c] - yv;
-                    r2 = (c == 0) ? df * df : fma(df, df, r2);
-                    dt = (c == 0) ? x[c] * yv : fma(x[c], yv, dt);
+                    for (int c = 0; c < D; c++) dt = (c == 0) ? x[c] * ys[j * D + c] : fma(x[c], ys[j * D + c], dt);
+                    r2 = fma((T)-2, dt, xnorm + yns[j]);
+                    r2 = (r2 > (T)0) ? r2 : (T)0;
+                } else {
+#pragma unroll
+                    for (int c = 0; c < D; c++) {
+                        const T yv = ys[j * D + c];
+                        const T df = x[c] - yv;
+                        r2 = (c == 0) ? df * df : fma(df, df, r2);
+                        dt = (c == 0) ? x[c] * yv : fma(x[c], yv, dt);
+                    }
                 }
                 if constexpr (sizeof(T) == 8) kv = cf_sop_value(r2, dt, P.prog, tbl_lane);
-                else kv = (double)cf_sop_value_f32(r2, dt, P.prog);
+                else kv = cf_sop_value_f32(r2, dt, P.prog);
             }
             Ks[j * CF_MM_TI + li] = kv;
         }
         __syncthreads();
         // phase B
-#pragma unroll 4
+#pragma unroll 2
         for (int k = 0; k < CF_MM_TJ; k++) {
-            const double2 k01 = *reinterpret_cast<const double2*>(&Ks[k * CF_MM_TI + 4 * ri]);
-            const double2 k23 = *reinterpret_cast<const double2*>(&Ks[k * CF_MM_TI + 4 * ri + 2]);
-            const double2 a01 = *reinterpret_cast<const double2*>(&As[k * CF_MM_LDA + 4 * ci]);
-            const double2 a23 = *reinterpret_cast<const double2*>(&As[k * CF_MM_LDA + 4 * ci + 2]);
-            const double kr[4] = {k01.x, k01.y, k23.x, k23.y};
-            const double ac[4] = {a01.x, a01.y, a23.x, a23.y};
+            T kr[8], ac[4];
+            if constexpr (sizeof(T) == 8) {
 #pragma unroll
-            for (int a = 0; a < 4; a++)
+                for (int h = 0; h < 4; h++) {
+                    const double2 v = *reinterpret_cast<const double2*>(&Ks[k * CF_MM_TI + 8 * rg + 2 * h]);
+                    kr[2 * h] = v.x; kr[2 * h + 1] = v.y;
+                }
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const double2 v = *reinterpret_cast<const double2*>(&As[k * CF_MM_PC + 4 * cg + 2 * h]);
+                    ac[2 * h] = v.x; ac[2 * h + 1] = v.y;
+                }
+            } else {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const float4 v = *reinterpret_cast<const float4*>(&Ks[k * CF_MM_TI + 8 * rg + 4 * h]);
+                    kr[4 * h] = v.x; kr[4 * h + 1] = v.y; kr[4 * h + 2] = v.z; kr[4 * h + 3] = v.w;
+                }
+                const float4 v = *reinterpret_cast<const float4*>(&As[k * CF_MM_PC + 4 * cg]);
+                ac[0] = v.x; ac[1] = v.y; ac[2] = v.z; ac[3] = v.w;
+            }
+#pragma unroll
+            for (int a = 0; a < 8; a++)
 #pragma unroll
                 for (int b = 0; b < 4; b++) acc[a][b] = fma(kr[a], ac[b], acc[a][b]);
         }
+    };
+
+    for (int t = 0; t < nfull; t++) {
+        const int s = t % CF_MM_NS;
+        cf_mbar_wait(&bars[s], (uint32_t)((t / CF_MM_NS) & 1));
+        const unsigned char* st = stages + (size_t)s * S::stage_bytes;
+        tile_compute(reinterpret_cast<const T*>(st), reinterpret_cast<const T*>(st + S::y_bytes),
+                     reinterpret_cast<const T*>(st + S::y_bytes + S::n_bytes), CF_MM_TJ);
+        __syncthreads(); // Ks and stage s are free again
+        if (tid == 0 && t + CF_MM_NS < nfull) issue(t + CF_MM_NS);
+    }
+    if ((int64_t)nfull * CF_MM_TJ < P.m) { // ragged last tile: cooperative loads, zero fill
+        const int64_t j0 = (int64_t)nfull * CF_MM_TJ;
+        const int cnt = (int)(P.m - j0);
+        T* ys = reinterpret_cast<T*>(stages);
+        T* yns = reinterpret_cast<T*>(stages + S::y_bytes);
+        T* As = reinterpret_cast<T*>(stages + S::y_bytes + S::n_bytes);
+        __syncthreads();
+        for (int q = tid; q < cnt * D; q += 256) ys[q] = Yg[j0 * D + q];
+        for (int q = tid; q < cnt; q += 256) yns[q] = yng[j0 + q];
+        for (int q = tid; q < CF_MM_TJ * CF_MM_PC; q += 256) As[q] = (q < cnt * CF_MM_PC) ? Atg[j0 * CF_MM_PC + q] : (T)0;
+        __syncthreads();
+        tile_compute(ys, yns, As, cnt);
     }
     T* Bg = static_cast<T*>(P.B);
 #pragma unroll
-    for (int a = 0; a < 4; a++) {
-        const int64_t i = rbase + 4 * ri + a;
-        if (i >= rend) continue;
+    for (int b = 0; b < 4; b++) {
+        const int c = 4 * cg + b;
+        if (c >= P.nrhs) continue;
 #pragma unroll
-        for (int b = 0; b < 4; b++) {
-            const int c = 4 * ci + b;
-            if (c >= P.nrhs) continue;
+        for (int a = 0; a < 8; a++) {
+            const int64_t i = rbase + 8 * rg + a;
+            if (i >= rend) continue;
             T* o = Bg + (i - P.row0) + P.ldb * c;
-            double v = P.alpha * acc[a][b];
+            double v = P.alpha * (double)acc[a][b];
             if (P.beta != 0.0) v += P.beta * (double)(*o);
             *o = (T)v;
         }
@@ -199,32 +294,37 @@ static __global__ void __launch_bounds__(1024) cf_dot_kernel(const double* __res
 }
 
 // ---- pipe peak probes ---------------------------------------------------------------------------------------------------
-// dependent-chain-free FMAs: 8 independent chains per thread, register resident.
-static __global__ void __launch_bounds__(256) cf_peak_dfma_kernel(double* out, int iters, double a, double b) {
-    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
-#pragma unroll 4
-    for (int i = 0; i < iters; i++) {
-        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
-    }
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
-}
-static __global__ void __launch_bounds__(256) cf_peak_ffma_kernel(float* out, int iters, float a, float b) {
-    float x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
-#pragma unroll 4
-    for (int i = 0; i < iters; i++) {
-        x0 = fmaf(x0, a, b); x1 = fmaf(x1, a, b); x2 = fmaf(x2, a, b); x3 = fmaf(x3, a, b);
-        x4 = fmaf(x4, a, b); x5 = fmaf(x5, a, b); x6 = fmaf(x6, a, b); x7 = fmaf(x7, a, b);
-    }
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
-}
+// dependent-chain-free FMAs: 16 independent chains per thread, register resident, 128 FMAs per loop trip so that the
+// loop overhead (3 non-FMA instructions) is < 2.5 % of the issue slots.
+#define CF_PROBE_BODY(T, FMA)                                                                                         \
+    T x[16];                                                                                                          \
+    _Pragma("unroll") for (int q = 0; q < 16; q++) x[q] = (T)(threadIdx.x + q);                                       \
+    for (int i = 0; i < iters; i += 8) {                                                                              \
+        _Pragma("unroll") for (int u = 0; u < 8; u++) {                                                               \
+            _Pragma("unroll") for (int q = 0; q < 16; q++) x[q] = FMA(x[q], a, b);                                    \
+        }                                                                                                             \
+    }                                                                                                                 \
+    T s = 0;                                                                                                          \
+    _Pragma("unroll") for (int q = 0; q < 16; q++) s += x[q];                                                         \
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
+
+static __global__ void __launch_bounds__(256) cf_peak_dfma_kernel(double* out, int iters, double a, double b) { CF_PROBE_BODY(double, fma) }
+static __global__ void __launch_bounds__(256) cf_peak_ffma_kernel(float* out, int iters, float a, float b) { CF_PROBE_BODY(float, fmaf) }
 static __global__ void __launch_bounds__(256) cf_peak_mufu_kernel(float* out, int iters, float a) {
-    float x0 = threadIdx.x * 1e-3f, x1 = x0 + .1f, x2 = x0 + .2f, x3 = x0 + .3f, x4 = x0 + .4f, x5 = x0 + .5f, x6 = x0 + .6f, x7 = x0 + .7f;
-#pragma unroll 4
-    for (int i = 0; i < iters; i++) {
-        x0 = cf_ex2f(x0) ; x1 = cf_ex2f(x1); x2 = cf_ex2f(x2); x3 = cf_ex2f(x3);
-        x4 = cf_ex2f(x4); x5 = cf_ex2f(x5); x6 = cf_ex2f(x6); x7 = cf_ex2f(x7);
-        x0 -= a; x1 -= a; x2 -= a; x3 -= a; x4 -= a; x5 -= a; x6 -= a; x7 -= a;
+    float x[16];
+#pragma unroll
+    for (int q = 0; q < 16; q++) x[q] = threadIdx.x * 1e-3f + 0.05f * q;
+    for (int i = 0; i < iters; i += 4) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+#pragma unroll
+            for (int q = 0; q < 16; q++) x[q] = cf_ex2f(x[q]);
+        }
+#pragma unroll
+        for (int q = 0; q < 16; q++) x[q] -= a; // keeps the values bounded; 16 FADD per 64 MUFU
     }
-    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    float s = 0;
+#pragma unroll
+    for (int q = 0; q < 16; q++) s += x[q];
+    out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 }

@@ -48,8 +48,8 @@ inline long double lbinom(int n, int k) { return lfact(n) / (lfact(k) * lfact(n 
 inline void fill_exp(cf_exp_consts& E, long double c) {
     const long double ln2 = 0.693147180559945309417232121458176568L;
     E.c = (double)c;
-    E.c1 = (double)(c * 64.0L / ln2);
-    E.c2 = (double)(-(ln2 / 64.0L) / c);
+    E.c1 = (double)(c * 256.0L / ln2);   // CF_EXP_TBL = 256 (cf_math.cuh)
+    E.c2 = (double)(-(ln2 / 256.0L) / c);
     long double ci = c;
     for (int i = 0; i < CF_EXP_POLY; i++) {
         E.q[i] = (double)(ci / lfact(i + 1));
@@ -299,7 +299,14 @@ inline cf_program lower(const cf_knode_t* prog, int nnodes) {
     if ((int)root.terms.size() > CF_MAX_TERMS) throw LowerError{CF_ERR_UNSUPPORTED, "kernel expands to too many terms"};
     P.nterms = (int)root.terms.size();
     P.natoms = (int)atoms.size();
-    for (int a = 0; a < P.natoms; a++) P.atoms[a] = atoms[a];
+    for (int a = 0; a < P.natoms; a++) {
+        cf_atom& A = atoms[a];
+        A.f_clog2e = (float)(A.e.c * 1.44269504088896340736);
+        A.f_gmax = (A.e.c != 0.0) ? (float)(-87.0 / A.e.c) : 3.0e38f;  // exp(-87) ~ 1.6e-38
+        A.f_w = (float)A.w; A.f_alpha = (float)A.alpha; A.f_sigma = (float)A.sigma; A.f_pad = 0; A.f_pad2 = 0;
+        for (int i = 0; i <= CF_MAX_MATERN_P; i++) A.f_mat[i] = (float)A.mat[i];
+        P.atoms[a] = A;
+    }
     bool used[CF_MAX_TERMS] = {false};
     for (int t = 0; t < P.nterms; t++) {
         const HTerm& ht = root.terms[t];

@@ -13,38 +13,46 @@
 #include <stdint.h>
 #include "cf_program.h"
 
-#define CF_EXP_TBL 64
+#define CF_EXP_TBL_BITS 8
+#define CF_EXP_TBL (1 << CF_EXP_TBL_BITS)  /* 256 entries: |reduced argument| <= ln2/512, degree-4 polynomial */
 #define CF_EXP_TBL_REP 16
-#define CF_EXP_TBL_DOUBLES (CF_EXP_TBL * CF_EXP_TBL_REP)
+#define CF_EXP_TBL_DOUBLES (CF_EXP_TBL * CF_EXP_TBL_REP)  /* 32 KB of shared memory */
 #define CF_MAGIC 6755399441055744.0 /* 1.5 * 2^52 */
 
-// Copy the 2^(j/64) table (64 doubles in global memory, written once per device by the host, correctly
+typedef uint32_t cf_tbl_t; // shared-space byte address of this lane's replica column of the exp table
+__device__ __forceinline__ uint32_t cf_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ cf_tbl_t cf_tbl_lane(const double* tbl, int tid) { return cf_smem_u32(tbl + (tid & 15)); }
+
+// Copy the 2^(j/256) table (256 doubles in global memory, written once per device by the host, correctly
 // rounded from long double) into shared memory, 16 replicas per entry: entry j for lane l lives at
-// tbl[j*16 + (l & 15)].
+// tbl[j*16 + (l & 15)], so the 16 lanes of a half-warp always hit 16 different bank pairs.
 __device__ __forceinline__ void cf_fill_exp_table(double* tbl, const double* __restrict__ g_tbl, int tid, int nthreads) {
     for (int i = tid; i < CF_EXP_TBL_DOUBLES; i += nthreads) tbl[i] = g_tbl[i >> 4];
 }
 
 // exp(c*v), v >= 0 (c < 0 folded into the constants).  tbl_lane = table + (lane & 15).
-// Non-FP64 work is kept to 6 ALU/LSU instructions per call: the clamp of v is ONE integer min on the high
-// word (v >= 0, so integer order of high words == floating-point order; the clamped value lies within
-// 2^-20 relative of E.vmax, where the result is ~1e-304, i.e. 0), the table address is an AND + a
-// shift-add, the 2^k scaling is a shift + integer multiply-add on the high word.
-__device__ __forceinline__ double cf_exp_cv(double v, const cf_exp_consts& E, const double* __restrict__ tbl_lane) {
+// The SM issues one instruction per cycle per sub-partition and an FP64 instruction holds the dispatch port for two
+// (measured: cycles = 2 * #FP64 + #other, profiles/), so the non-FP64 work is kept to 6 instructions per call:
+// the clamp of v is ONE integer min on the high word (v >= 0, so integer order of high words == floating-point
+// order; the clamped value lies within 2^-20 relative of E.vmax, where the result is ~1e-304, i.e. 0), the table
+// address is AND + multiply-add, the 2^k scaling is AND + multiply-add on the high word.
+__device__ __forceinline__ double cf_exp_cv(double v, const cf_exp_consts& E, cf_tbl_t tbl_lane) {
     v = __hiloint2double(min(__double2hiint(v), E.vmax_hi), __double2loint(v));
     double t = fma(v, E.c1, CF_MAGIC);
-    int kk = __double2loint(t);
+    const int kk = __double2loint(t);
     double kd = t - CF_MAGIC;
     double u = fma(kd, E.c2, v);
-    double p = fma(E.q[4], u, E.q[3]);
-    p = fma(p, u, E.q[2]);
+    double p = fma(E.q[3], u, E.q[2]);
     p = fma(p, u, E.q[1]);
     p = fma(p, u, E.q[0]);
-    const double tj = *reinterpret_cast<const double*>(reinterpret_cast<const char*>(tbl_lane) +
-                                                       ((unsigned)(kk & (CF_EXP_TBL - 1)) << 7));
+    int off;
+    double tj;
+    asm("mad.lo.s32 %0, %1, 128, %2;" : "=r"(off) : "r"(kk & (CF_EXP_TBL - 1)), "r"((int)tbl_lane));
+    asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(off)); // table is written once, before the first barrier
     double tu = tj * u;
     double e = fma(tu, p, tj); // tj * (1 + u p)
-    int hi = (kk >> 6) * 0x100000 + __double2hiint(e);
+    int hi;
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(hi) : "r"(kk & ~(CF_EXP_TBL - 1)), "r"(0x100000 >> CF_EXP_TBL_BITS), "r"(__double2hiint(e)));
     return __hiloint2double(hi, __double2loint(e));
 }
 
@@ -80,7 +88,7 @@ __device__ __forceinline__ double cf_powi(double b, int p) { // p >= 1, repeated
 }
 
 // ---- atom values (FP64) ------------------------------------------------------------------------
-__device__ __forceinline__ double cf_atom_eq(double r2, const cf_atom& A, const double* tbl_lane) {
+__device__ __forceinline__ double cf_atom_eq(double r2, const cf_atom& A, cf_tbl_t tbl_lane) {
     return cf_exp_cv(r2, A.e, tbl_lane);
 }
 // M(g) exp(c g), g = sqrt(r2).  The reference's Taylor branch (src/stationary.jl:139-146) differs from this
@@ -88,7 +96,7 @@ __device__ __forceinline__ double cf_atom_eq(double r2, const cf_atom& A, const 
 __device__ __forceinline__ double cf_clamp_v(double v, const cf_exp_consts& E) {
     return __hiloint2double(min(__double2hiint(v), E.vmax_hi), __double2loint(v));
 }
-__device__ __forceinline__ double cf_atom_matern(double r2, const cf_atom& A, const double* tbl_lane) {
+__device__ __forceinline__ double cf_atom_matern(double r2, const cf_atom& A, cf_tbl_t tbl_lane) {
     double g = cf_clamp_v(cf_sqrt_pos(r2), A.e); // clamp BEFORE the polynomial: M(g) e^{cg} with g ~ 1e150 must be 0, not M(g) * 1e-304
     double e = cf_exp_cv(g, A.e, tbl_lane);
     int p = A.p;
@@ -107,7 +115,7 @@ __device__ __forceinline__ double cf_atom_rq_real(double r2, const cf_atom& A) {
 }
 
 template <int KIND>
-__device__ __forceinline__ double cf_atom_value(double r2, double dt, const cf_atom& A, const double* tbl_lane) {
+__device__ __forceinline__ double cf_atom_value(double r2, double dt, const cf_atom& A, cf_tbl_t tbl_lane) {
     if (KIND == CF_ATOM_EQ) return cf_atom_eq(r2, A, tbl_lane);
     if (KIND == CF_ATOM_MATERN) return cf_atom_matern(r2, A, tbl_lane);
     if (KIND == CF_ATOM_RQ_INT) return cf_atom_rq_int(r2, A);
@@ -115,7 +123,7 @@ __device__ __forceinline__ double cf_atom_value(double r2, double dt, const cf_a
     return dt + A.sigma; // LINE
 }
 
-__device__ __forceinline__ double cf_atom_value_dyn(double r2, double dt, const cf_atom& A, const double* tbl_lane) {
+__device__ __forceinline__ double cf_atom_value_dyn(double r2, double dt, const cf_atom& A, cf_tbl_t tbl_lane) {
     switch (A.kind) {
         case CF_ATOM_EQ: return cf_atom_eq(r2, A, tbl_lane);
         case CF_ATOM_MATERN: return cf_atom_matern(r2, A, tbl_lane);
@@ -126,7 +134,7 @@ __device__ __forceinline__ double cf_atom_value_dyn(double r2, double dt, const 
 }
 
 // generic sum of products (program in global memory, warp-uniform control flow)
-__device__ __forceinline__ double cf_sop_value(double r2, double dt, const cf_program* __restrict__ P, const double* tbl_lane) {
+__device__ __forceinline__ double cf_sop_value(double r2, double dt, const cf_program* __restrict__ P, cf_tbl_t tbl_lane) {
     double val = 0.0;
     const int nt = P->nterms;
     for (int t = 0; t < nt; t++) {
@@ -143,7 +151,7 @@ __device__ __forceinline__ double cf_sop_value(double r2, double dt, const cf_pr
 
 // ---- derivatives with respect to r2 (gradient kernel; reference src/gradient.jl:589-600) -------------
 // returns k, k1 = dk/dr2, k2 = d2k/dr2^2 of one isotropic atom
-__device__ __forceinline__ void cf_atom_jet(double r2, const cf_atom& A, const double* tbl_lane, double& k, double& k1, double& k2) {
+__device__ __forceinline__ void cf_atom_jet(double r2, const cf_atom& A, cf_tbl_t tbl_lane, double& k, double& k1, double& k2) {
     switch (A.kind) {
         case CF_ATOM_EQ: {
             k = cf_exp_cv(r2, A.e, tbl_lane);
@@ -192,7 +200,7 @@ __device__ __forceinline__ void cf_atom_jet(double r2, const cf_atom& A, const d
 }
 
 // jets of the generic isotropic sum of products: product rule over factors, powers by repeated multiplication
-__device__ __forceinline__ void cf_sop_jet(double r2, const cf_program* __restrict__ P, const double* tbl_lane, double& k,
+__device__ __forceinline__ void cf_sop_jet(double r2, const cf_program* __restrict__ P, cf_tbl_t tbl_lane, double& k,
                                            double& k1, double& k2) {
     double sv = 0, s1 = 0, s2 = 0;
     for (int t = 0; t < P->nterms; t++) {
@@ -221,31 +229,29 @@ __device__ __forceinline__ float cf_lg2f(float x) { float y; asm("lg2.approx.ftz
 
 #define CF_LOG2E_F 1.4426950408889634f
 
+// KIND < 0: dispatch on A.kind at run time (generic sum of products)
+template <int KIND>
 __device__ __forceinline__ float cf_atom_value_f32(float r2, float dt, const cf_atom& A) {
-    switch (A.kind) {
-        case CF_ATOM_EQ: return cf_ex2f(r2 * (float)(A.e.c * 1.4426950408889634));
-        case CF_ATOM_MATERN: {
-            float g = (r2 > 0.f) ? r2 * cf_rsqrtf(r2) : 0.f;
-            g = fminf(g, (float)A.e.vmax * 0.125f); // e^{c g} < 1e-38 beyond this; keeps M(g) e^{cg} = 0 for far points
-            float e = cf_ex2f(g * (float)(A.e.c * 1.4426950408889634));
-            int p = A.p;
-            if (p == 0) return e;
-            float mp = (float)A.mat[p];
-            for (int i = p - 1; i >= 0; i--) mp = fmaf(mp, g, (float)A.mat[i]);
-            return mp * e;
-        }
-        case CF_ATOM_RQ_INT: {
-            float ib = cf_rcpf(fmaf(r2, (float)A.w, 1.0f));
-            float r = ib;
-            for (int i = 1; i < A.p; i++) r *= ib;
-            return r;
-        }
-        case CF_ATOM_RQ_REAL: {
-            float base = fmaf(r2, (float)A.w, 1.0f);
-            return cf_ex2f(-(float)A.alpha * cf_lg2f(base));
-        }
-        default: return dt + (float)A.sigma;
+    const int kind = (KIND >= 0) ? KIND : A.kind;
+    if (kind == CF_ATOM_EQ) return cf_ex2f(r2 * A.f_clog2e);
+    if (kind == CF_ATOM_MATERN) {
+        float g = r2 * cf_rsqrtf(fmaxf(r2, 1e-37f)); // sqrt(r2); 0 at r2 = 0
+        g = fminf(g, A.f_gmax);                       // far points: M(g) e^{cg} must underflow to 0
+        const float e = cf_ex2f(g * A.f_clog2e);
+        const int p = A.p;
+        if (p == 0) return e;
+        float mp = A.f_mat[p];
+        for (int i = p - 1; i >= 0; i--) mp = fmaf(mp, g, A.f_mat[i]);
+        return mp * e;
     }
+    if (kind == CF_ATOM_RQ_INT) {
+        const float ib = cf_rcpf(fmaf(r2, A.f_w, 1.0f));
+        float r = ib;
+        for (int i = 1; i < A.p; i++) r *= ib;
+        return r;
+    }
+    if (kind == CF_ATOM_RQ_REAL) return cf_ex2f(-A.f_alpha * cf_lg2f(fmaf(r2, A.f_w, 1.0f)));
+    return dt + A.f_sigma;
 }
 __device__ __forceinline__ float cf_sop_value_f32(float r2, float dt, const cf_program* __restrict__ P) {
     float val = 0.f;
@@ -253,7 +259,7 @@ __device__ __forceinline__ float cf_sop_value_f32(float r2, float dt, const cf_p
         const cf_term& T = P->terms[t];
         float prod = (float)T.coef;
         for (int f = 0; f < T.nfac; f++) {
-            float a = cf_atom_value_f32(r2, dt, P->atoms[T.fac[f].atom]);
+            float a = cf_atom_value_f32<-1>(r2, dt, P->atoms[T.fac[f].atom]);
             float r = a;
             for (int q = 1; q < T.fac[f].power; q++) r *= a;
             prod *= r;

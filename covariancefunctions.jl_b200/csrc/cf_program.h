@@ -10,7 +10,7 @@
 #define CF_MAX_MATERN_P 12
 #define CF_MAX_TERMS 16
 #define CF_MAX_FACTORS 6
-#define CF_EXP_POLY 5 /* degree of the exp polynomial after the 64-entry table reduction */
+#define CF_EXP_POLY 4 /* degree of the exp polynomial after the 256-entry table reduction */
 
 enum cf_atom_kind {
     CF_ATOM_EQ = 0,      // exp(c r2), c = -1/(2 l^2)                      reference src/stationary.jl:42
@@ -21,11 +21,11 @@ enum cf_atom_kind {
     CF_ATOM_SOP = 5      // (kernel-kind tag only) generic sum of products
 };
 
-// Constants for exp(c*v) = 2^k * T[j] * P(u):  t = fma(v, c1, MAGIC); kk = t - MAGIC = 64 k + j;
-// u = fma(kk, c2, v) (so c*u is the reduced argument, |c u| <= ln2/128); P(u) = 1 + u*(q0 + q1 u + ...)
+// Constants for exp(c*v) = 2^k * T[j] * P(u):  t = fma(v, c1, MAGIC); kk = t - MAGIC = 256 k + j;
+// u = fma(kk, c2, v) (so c*u is the reduced argument, |c u| <= ln2/512); P(u) = 1 + u*(q0 + q1 u + ...)
 struct cf_exp_consts {
-    double c1;             // c * 64 / ln2
-    double c2;             // -(ln2 / 64) / c
+    double c1;             // c * 256 / ln2
+    double c2;             // -(ln2 / 256) / c
     double q[CF_EXP_POLY]; // c^(i+1) / (i+1)!
     double c;              // the plain multiplier (fp32 path, derivative formulas)
     double vmax;           // clamp: c*vmax = -700 (result ~1e-304, i.e. 0)
@@ -52,6 +52,12 @@ struct cf_atom {
     double sigma;
     // plain r2 multiplier 1/l^2 (RQ, Taylor branch)
     double inv_l2;
+    // Float32 copies of the constants the fp32 kernels use (no fp64 instruction in the fp32 inner loop)
+    float f_clog2e;   // c * log2(e): exp(c v) = ex2(f_clog2e * v)
+    float f_gmax;     // clamp of g = sqrt(r2) so that M(g) exp(c g) underflows cleanly
+    float f_w, f_alpha, f_sigma, f_pad;
+    float f_mat[CF_MAX_MATERN_P + 1];
+    float f_pad2;
 };
 
 struct cf_factor {

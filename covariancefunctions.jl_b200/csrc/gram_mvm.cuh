@@ -38,7 +38,6 @@ struct cf_mvm_params {
 };
 
 // ---- mbarrier / TMA 1-D bulk copy wrappers (PTX ISA: cp.async.bulk, mbarrier) ------------------------------
-__device__ __forceinline__ uint32_t cf_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void cf_mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(cf_smem_u32(bar)), "r"(count));
 }
@@ -81,7 +80,7 @@ struct cf_mvm_smem {
 
 // pair evaluation -------------------------------------------------------------------------------------
 template <typename T, int D, int KIND>
-__device__ __forceinline__ T cf_pair_value(const T (&x)[D], const T* __restrict__ yj, const cf_mvm_params& P, const double* tbl_lane) {
+__device__ __forceinline__ T cf_pair_value(const T (&x)[D], const T* __restrict__ yj, const cf_mvm_params& P, cf_tbl_t tbl_lane) {
     T r2 = 0, dt = 0;
     if (KIND != CF_ATOM_LINE) {
 #pragma unroll
@@ -99,7 +98,7 @@ __device__ __forceinline__ T cf_pair_value(const T (&x)[D], const T* __restrict_
         return cf_atom_value<KIND>(r2, dt, P.atom, tbl_lane);
     } else {
         if (KIND == CF_ATOM_SOP) return cf_sop_value_f32(r2, dt, P.prog);
-        return cf_atom_value_f32(r2, dt, P.atom);
+        return cf_atom_value_f32<KIND>(r2, dt, P.atom);
     }
 }
 
@@ -112,7 +111,7 @@ __global__ void __launch_bounds__(NT, MINB) gram_mvm_kernel(const __grid_constan
     unsigned char* stages = smem + S::tbl_bytes + S::bar_bytes;
 
     const int tid = threadIdx.x;
-    const double* tbl_lane = tbl + (tid & 15);
+    const cf_tbl_t tbl_lane = cf_tbl_lane(tbl, tid);
     const T* __restrict__ Xg = static_cast<const T*>(P.X);
     const T* __restrict__ Yg = static_cast<const T*>(P.Y);
     const T* __restrict__ ag = static_cast<const T*>(P.a);

@@ -98,7 +98,6 @@ struct Shard {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     void* X = nullptr;  // n x D padded points (all rows, replicated)
     void* Y = nullptr;  // m x D (== X when symmetric)
-    cf_program* d_prog = nullptr;
     void* xn = nullptr;  // squared norms of the padded points (multi-RHS kernel)
     void* yn = nullptr;
     Buf a, y, partial, apad, ypad, at, cg[6];
@@ -114,6 +113,9 @@ struct cf_gramian_s {
     bool use_norms = false; // multi-RHS kernel may use r2 = |x|^2 + |y|^2 - 2 x.y (well-scaled data, d >= 8)
     int64_t row_begin = 0, row_end = 0;
     cf_program prog;
+    cf_sop_val sop_val;    // parameter-resident program for the value kernels
+    cf_sop_grad sop_grad;  // ... for the gradient kernel (valid when grad_ok)
+    bool grad_ok = false;
     int kind = CF_ATOM_SOP; // kernel kind used for the value MVM
     double coef = 1.0;      // leading constant when prog.single
     const cf_kernel_entry* entry = nullptr;
@@ -180,10 +182,10 @@ int launch_dense(cf_gramian_s* g, Shard& sh, void* d_M, int64_t ld, int64_t j0, 
     if (nrows <= 0 || nj <= 0) return CF_OK;
     const int blocks = (int)std::min<int64_t>((nrows * nj + 255) / 256, 148 * 16);
     if (g->dtype == CF_F64)
-        gram_dense_kernel<double><<<blocks, 256, 0, stream>>>((const double*)sh.X, (const double*)sh.Y, g->D, sh.d_prog,
+        gram_dense_kernel<double><<<blocks, 256, 0, stream>>>((const double*)sh.X, (const double*)sh.Y, g->D, g->sop_val,
                                                               sh.ctx->exp2_tbl, sh.r0, nrows, j0, nj, (double*)d_M, ld);
     else
-        gram_dense_kernel<float><<<blocks, 256, 0, stream>>>((const float*)sh.X, (const float*)sh.Y, g->D, sh.d_prog,
+        gram_dense_kernel<float><<<blocks, 256, 0, stream>>>((const float*)sh.X, (const float*)sh.Y, g->D, g->sop_val,
                                                              sh.ctx->exp2_tbl, sh.r0, nrows, j0, nj, (float*)d_M, ld);
     CF_CUDA(cudaGetLastError());
     return CF_OK;
@@ -204,7 +206,7 @@ int launch_mm(cf_gramian_s* g, Shard& sh, void* d_B, int64_t ldb, const void* d_
     cf_mm_params P;
     std::memset(&P, 0, sizeof(P));
     P.X = sh.X; P.Y = sh.Y; P.xn = sh.xn; P.yn = sh.yn; P.At = sh.at.p;
-    P.exp2_tbl = sh.ctx->exp2_tbl; P.prog = sh.d_prog;
+    P.exp2_tbl = sh.ctx->exp2_tbl; P.sop = g->sop_val;
     P.row0 = sh.r0; P.nrows = nrows; P.m = g->m; P.ldb = ldb;
     P.alpha = alpha; P.beta = beta;
     P.use_norms = g->use_norms ? 1 : 0;
@@ -378,13 +380,13 @@ int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const v
     std::memset(&P, 0, sizeof(P));
     P.X = sh.X; P.Y = sh.Y; P.a = d_a;
     P.exp2_tbl = sh.ctx->exp2_tbl;
-    P.prog = sh.d_prog;
+    P.sop = g->sop_val;
     P.row0 = sh.r0; P.nrows = nrows; P.m = g->m;
     P.cols_per_chunk = pl.cols_per_chunk;
     P.alpha = alpha * g->coef; P.beta = beta;
     P.coef = g->coef;
     P.use_tma = (((uintptr_t)d_a) % 16 == 0) ? 1 : 0;
-    if (g->prog.single) P.atom = g->prog.atoms[g->prog.terms[0].fac[0].atom];
+    if (g->prog.single) P.atom = g->prog.atoms[g->prog.terms[0].fac[0].atom].v;
     P.direct = (pl.chunks == 1) ? 1 : 0;
     if (P.direct) {
         P.out = d_y; P.yin = d_yin;
@@ -439,7 +441,7 @@ int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, co
     P.X = (const double*)sh.X; P.Y = (const double*)sh.Y; P.a = a_use;
     P.partial = (double*)sh.partial.p;
     P.exp2_tbl = sh.ctx->exp2_tbl;
-    P.prog = sh.d_prog;
+    P.sop = g->sop_grad;
     P.row0 = sh.r0; P.nrows = nrows; P.m = g->m; P.cols_per_chunk = pl.cols_per_chunk;
     P.single = g->prog.single;
     P.coef = g->coef;
@@ -474,7 +476,6 @@ int destroy_impl(cf_gramian_s* g) {
         if (sh.ctx) cudaSetDevice(sh.ctx->dev);
         if (sh.Y && sh.Y != sh.X) cudaFree(sh.Y);
         if (sh.X) cudaFree(sh.X);
-        if (sh.d_prog) cudaFree(sh.d_prog);
         if (sh.yn && sh.yn != sh.xn) cudaFree(sh.yn);
         if (sh.xn) cudaFree(sh.xn);
         sh.a.release(); sh.y.release(); sh.partial.release(); sh.apad.release(); sh.ypad.release(); sh.at.release();
@@ -525,8 +526,13 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
     if ((n > 0 && !X) || (Y == nullptr && m != n)) return fail(CF_ERR_BAD_ARGUMENT, "cf_gramian_create: X is NULL, or Y is NULL with m != n");
     if (ldx < d || (Y && ldy < d)) return fail(CF_ERR_DIMENSION, "cf_gramian_create: leading dimension smaller than d");
     cf_program lowered;
+    cf_sop_val sop_val;
+    cf_sop_grad sop_grad;
+    bool grad_ok = false;
     try {
         lowered = cf::lower(prog, nnodes);
+        cf::to_sop_val(lowered, sop_val);
+        grad_ok = cf::to_sop_grad(lowered, sop_grad);
     } catch (const cf::LowerError& e) {
         return fail(e.code, "cf_gramian_create: %s", e.msg.c_str());
     } catch (...) {
@@ -542,11 +548,12 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
     g->symmetric = (Y == nullptr);
     g->row_begin = 0; g->row_end = n;
     g->prog = lowered;
+    g->sop_val = sop_val; g->sop_grad = sop_grad; g->grad_ok = grad_ok;
     g->entry = entry;
     if (lowered.single) {
         const cf_atom& A = lowered.atoms[lowered.terms[0].fac[0].atom];
         g->coef = lowered.terms[0].coef;
-        g->kind = (A.kind == CF_ATOM_EQ || A.kind == CF_ATOM_MATERN || A.kind == CF_ATOM_RQ_INT) ? A.kind : CF_ATOM_SOP;
+        g->kind = (A.v.kind == CF_ATOM_EQ || A.v.kind == CF_ATOM_MATERN || A.v.kind == CF_ATOM_RQ_INT) ? A.v.kind : CF_ATOM_SOP;
         if (g->kind == CF_ATOM_SOP) g->coef = 1.0; // generic path applies the coefficient itself
     } else {
         g->kind = CF_ATOM_SOP;
@@ -611,8 +618,6 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
         } else {
             sh.Y = sh.X;
         }
-        CF_CREATE_CUDA(cudaMalloc(&sh.d_prog, sizeof(cf_program)));
-        CF_CREATE_CUDA(cudaMemcpy(sh.d_prog, &g->prog, sizeof(cf_program), cudaMemcpyHostToDevice));
         CF_CREATE_CUDA(cudaMalloc(&sh.xn, std::max<size_t>(16, (size_t)n * es)));
         if (Y) CF_CREATE_CUDA(cudaMalloc(&sh.yn, std::max<size_t>(16, (size_t)m * es)));
         else sh.yn = sh.xn;
@@ -674,6 +679,7 @@ static int mul_host_impl(cf_gramian_t g, void* y, int64_t ldy, const void* x, in
     if (gradient) {
         if (g->dtype != CF_F64) return fail(CF_ERR_UNSUPPORTED, "gradient operator: Float64 only");
         if (!g->prog.isotropic) return fail(CF_ERR_UNSUPPORTED, "gradient operator: kernel does not have the IsotropicInput trait");
+        if (!g->grad_ok) return fail(CF_ERR_UNSUPPORTED, "gradient operator: kernel too complex (more than 4 terms or 3 base kernels)");
     }
     if (nrhs == 1) { ldy = rows; ldx = cols; }
     std::lock_guard<std::mutex> lk(g->mu);
@@ -743,6 +749,7 @@ static int mul_device_impl(cf_gramian_t g, void* d_y, int64_t ldy, const void* d
     if (gradient) {
         if (g->dtype != CF_F64) return fail(CF_ERR_UNSUPPORTED, "gradient operator: Float64 only");
         if (!g->prog.isotropic) return fail(CF_ERR_UNSUPPORTED, "gradient operator: kernel does not have the IsotropicInput trait");
+        if (!g->grad_ok) return fail(CF_ERR_UNSUPPORTED, "gradient operator: kernel too complex (more than 4 terms or 3 base kernels)");
     }
     std::lock_guard<std::mutex> lk(g->mu);
     Shard& sh = g->shards[0];
@@ -837,7 +844,8 @@ int cf_cg_solve(cf_gramian_t g, double sigma2, void* x, const void* b, double re
     if (g->n != g->m) return fail(CF_ERR_DIMENSION, "cf_cg_solve: Gramian is %lld x %lld, not square", (long long)g->n, (long long)g->m);
     if (g->dtype != CF_F64) return fail(CF_ERR_UNSUPPORTED, "cf_cg_solve: Float64 only");
     if (g->row_begin != 0 || g->row_end != g->n) return fail(CF_ERR_UNSUPPORTED, "cf_cg_solve: handle is restricted to a row range");
-    if (gradient && !g->prog.isotropic) return fail(CF_ERR_UNSUPPORTED, "gradient operator: kernel does not have the IsotropicInput trait");
+    if (gradient && (!g->prog.isotropic || !g->grad_ok))
+        return fail(CF_ERR_UNSUPPORTED, "gradient operator: kernel does not have the IsotropicInput trait or is too complex");
     std::lock_guard<std::mutex> lk(g->mu);
     return cg_solve_impl(g, sigma2, (double*)x, (const double*)b, reltol, maxiter, gradient != 0, iters, resnorm);
 }

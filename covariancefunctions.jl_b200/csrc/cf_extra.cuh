@@ -13,7 +13,7 @@ __global__ void cf_scale_kernel(T* __restrict__ y, const T* __restrict__ yin, in
 // ---- Matrix!(M, G): M[(i - r0) + ld (j - j0)] = k(x_i, y_j)   (reference src/gramian.jl:107-114) ------------------
 // one thread per entry, generic sum-of-products evaluation; not a hot path.
 template <typename T>
-__global__ void gram_dense_kernel(const T* __restrict__ X, const T* __restrict__ Y, int D, const cf_program* __restrict__ prog,
+__global__ void gram_dense_kernel(const T* __restrict__ X, const T* __restrict__ Y, int D, const __grid_constant__ cf_sop_val prog,
                                   const double* __restrict__ exp2_tbl, int64_t r0, int64_t nrows, int64_t j0, int64_t ncols,
                                   T* __restrict__ M, int64_t ld) {
     __shared__ double tbl[CF_EXP_TBL_DOUBLES];
@@ -69,11 +69,12 @@ struct cf_mm_params {
     const void* X; const void* Y; const void* xn; const void* yn; // points and squared norms
     const void* At;   // transposed weights, m x PC (row j holds the PC columns of this pass, zero padded)
     void* B;
-    const double* exp2_tbl; const cf_program* prog;
+    const double* exp2_tbl;
     int64_t row0, nrows, m, ldb;
     int nrhs;         // columns in this pass (<= CF_MM_PC)
     int use_norms;
     double alpha, beta;
+    cf_sop_val sop;
 };
 
 // At[j][c] = c < nrhs ? A[j + lda c] : 0   (one pass of <= CF_MM_PC columns)
@@ -149,7 +150,7 @@ __global__ void __launch_bounds__(256, 1) gram_mm_kernel(const __grid_constant__
         for (int c = 0; c < D; c++) x[c] = Xg[i * D + c];
         xnorm = static_cast<const T*>(P.xn)[i];
     }
-    const int rg = tid & 15, cg = tid >> 4; // phase B tile: rows 8 rg .. 8 rg + 7, columns 4 cg .. 4 cg + 3
+    const int rg = tid & 15, cg = tid >> 4; // phase B tile: rows {32 a2 + 2 rg + b}, columns 4 cg .. 4 cg + 3
     T acc[8][4];
 #pragma unroll
     for (int a = 0; a < 8; a++)
@@ -157,61 +158,80 @@ __global__ void __launch_bounds__(256, 1) gram_mm_kernel(const __grid_constant__
         for (int b = 0; b < 4; b++) acc[a][b] = 0;
 
     auto tile_compute = [&](const T* __restrict__ ys, const T* __restrict__ yns, const T* __restrict__ As, int cnt) {
-        // phase A
-#pragma unroll 2
-        for (int q = 0; q < CF_MM_TJ / 2; q++) {
-            const int j = jh * (CF_MM_TJ / 2) + q;
-            T kv = 0;
-            if (j < cnt) {
-                T r2 = 0, dt = 0;
-                if (P.use_norms) {
+        // phase A: 4 entries at a time (independent FMA chains hide the FP64 latency with only 2 warps per scheduler)
+        for (int q0 = 0; q0 < CF_MM_TJ / 2; q0 += 4) {
+            const int jb = jh * (CF_MM_TJ / 2) + q0;
+            T r2[4], dt[4];
 #pragma unroll
-                    for (int c = 0; c < D; c++) dt = (c == 0) ? x[c] * ys[j * D + c] : fma(x[c], ys[j * D + c], dt);
-                    r2 = fma((T)-2, dt, xnorm + yns[j]);
-                    r2 = (r2 > (T)0) ? r2 : (T)0;
-                } else {
+            for (int u = 0; u < 4; u++) { r2[u] = 0; dt[u] = 0; }
+            if (P.use_norms) {
 #pragma unroll
-                    for (int c = 0; c < D; c++) {
-                        const T yv = ys[j * D + c];
+                for (int c = 0; c < D; c++) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) dt[u] = fma(x[c], ys[(jb + u) * D + c], dt[u]);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const T v = fma((T)-2, dt[u], xnorm + yns[jb + u]);
+                    r2[u] = (v > (T)0) ? v : (T)0;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < D; c++) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const T yv = ys[(jb + u) * D + c];
                         const T df = x[c] - yv;
-                        r2 = (c == 0) ? df * df : fma(df, df, r2);
-                        dt = (c == 0) ? x[c] * yv : fma(x[c], yv, dt);
+                        r2[u] = fma(df, df, r2[u]);
+                        dt[u] = fma(x[c], yv, dt[u]);
                     }
                 }
-                if constexpr (sizeof(T) == 8) kv = cf_sop_value(r2, dt, P.prog, tbl_lane);
-                else kv = cf_sop_value_f32(r2, dt, P.prog);
             }
-            Ks[j * CF_MM_TI + li] = kv;
+            T kv[4];
+            if constexpr (sizeof(T) == 8) cf_sop_value_n<4>(r2, dt, P.sop, tbl_lane, kv);
+            else cf_sop_value_f32_n<4>(r2, dt, P.sop, kv);
+#pragma unroll
+            for (int u = 0; u < 4; u++) Ks[(jb + u) * CF_MM_TI + li] = (jb + u < cnt) ? kv[u] : (T)0; // past the end: no contribution
         }
         __syncthreads();
-        // phase B
-#pragma unroll 2
-        for (int k = 0; k < CF_MM_TJ; k++) {
-            T kr[8], ac[4];
+        // phase B: this thread's rows are {32 a2 + 2 rg + b}: the 16 lanes of a half-warp read 256 contiguous bytes of Ks.
+        // Software pipelined: the operands of step k+1 are loaded while the 32 FMAs of step k issue.
+        T kr[2][8], ac[2][4];
+        auto loadk = [&](int k, T (&krr)[8], T (&acc_)[4]) {
             if constexpr (sizeof(T) == 8) {
 #pragma unroll
                 for (int h = 0; h < 4; h++) {
-                    const double2 v = *reinterpret_cast<const double2*>(&Ks[k * CF_MM_TI + 8 * rg + 2 * h]);
-                    kr[2 * h] = v.x; kr[2 * h + 1] = v.y;
+                    const double2 v = *reinterpret_cast<const double2*>(&Ks[k * CF_MM_TI + 32 * h + 2 * rg]);
+                    krr[2 * h] = v.x; krr[2 * h + 1] = v.y;
                 }
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                     const double2 v = *reinterpret_cast<const double2*>(&As[k * CF_MM_PC + 4 * cg + 2 * h]);
-                    ac[2 * h] = v.x; ac[2 * h + 1] = v.y;
+                    acc_[2 * h] = v.x; acc_[2 * h + 1] = v.y;
                 }
             } else {
 #pragma unroll
-                for (int h = 0; h < 2; h++) {
-                    const float4 v = *reinterpret_cast<const float4*>(&Ks[k * CF_MM_TI + 8 * rg + 4 * h]);
-                    kr[4 * h] = v.x; kr[4 * h + 1] = v.y; kr[4 * h + 2] = v.z; kr[4 * h + 3] = v.w;
+                for (int h = 0; h < 4; h++) {
+                    const float2 v = *reinterpret_cast<const float2*>(&Ks[k * CF_MM_TI + 32 * h + 2 * rg]);
+                    krr[2 * h] = v.x; krr[2 * h + 1] = v.y;
                 }
                 const float4 v = *reinterpret_cast<const float4*>(&As[k * CF_MM_PC + 4 * cg]);
-                ac[0] = v.x; ac[1] = v.y; ac[2] = v.z; ac[3] = v.w;
+                acc_[0] = v.x; acc_[1] = v.y; acc_[2] = v.z; acc_[3] = v.w;
             }
+        };
+        loadk(0, kr[0], ac[0]);
+#pragma unroll 1
+        for (int k = 0; k < CF_MM_TJ; k += 2) {
+            loadk(k + 1, kr[1], ac[1]);
 #pragma unroll
             for (int a = 0; a < 8; a++)
 #pragma unroll
-                for (int b = 0; b < 4; b++) acc[a][b] = fma(kr[a], ac[b], acc[a][b]);
+                for (int b = 0; b < 4; b++) acc[a][b] = fma(kr[0][a], ac[0][b], acc[a][b]);
+            if (k + 2 < CF_MM_TJ) loadk(k + 2, kr[0], ac[0]);
+#pragma unroll
+            for (int a = 0; a < 8; a++)
+#pragma unroll
+                for (int b = 0; b < 4; b++) acc[a][b] = fma(kr[1][a], ac[1][b], acc[a][b]);
         }
     };
 
@@ -231,8 +251,8 @@ __global__ void __launch_bounds__(256, 1) gram_mm_kernel(const __grid_constant__
         T* yns = reinterpret_cast<T*>(stages + S::y_bytes);
         T* As = reinterpret_cast<T*>(stages + S::y_bytes + S::n_bytes);
         __syncthreads();
-        for (int q = tid; q < cnt * D; q += 256) ys[q] = Yg[j0 * D + q];
-        for (int q = tid; q < cnt; q += 256) yns[q] = yng[j0 + q];
+        for (int q = tid; q < CF_MM_TJ * D; q += 256) ys[q] = (q < cnt * D) ? Yg[j0 * D + q] : (T)0;
+        for (int q = tid; q < CF_MM_TJ; q += 256) yns[q] = (q < cnt) ? yng[j0 + q] : (T)0;
         for (int q = tid; q < CF_MM_TJ * CF_MM_PC; q += 256) As[q] = (q < cnt * CF_MM_PC) ? Atg[j0 * CF_MM_PC + q] : (T)0;
         __syncthreads();
         tile_compute(ys, yns, As, cnt);
@@ -244,7 +264,7 @@ __global__ void __launch_bounds__(256, 1) gram_mm_kernel(const __grid_constant__
         if (c >= P.nrhs) continue;
 #pragma unroll
         for (int a = 0; a < 8; a++) {
-            const int64_t i = rbase + 8 * rg + a;
+            const int64_t i = rbase + 32 * (a >> 1) + 2 * rg + (a & 1);
             if (i >= rend) continue;
             T* o = Bg + (i - P.row0) + P.ldb * c;
             double v = P.alpha * (double)acc[a][b];

@@ -71,9 +71,9 @@ inline void fill_matern(cf_atom& A, int p, long double l) {
     const long double nu2 = 2 * p + 1;
     const long double kappa = sqrtl(nu2) / l;
     const long double norm = lfact(2 * p) / lfact(p);
-    A.kind = CF_ATOM_MATERN;
-    A.p = p;
-    fill_exp(A.e, -kappa);
+    A.v.kind = CF_ATOM_MATERN;
+    A.v.p = p;
+    fill_exp(A.v.e, -kappa);
     A.inv_l2 = (double)(1.0L / (l * l));
     // Laurent polynomials in s with exponents -3..p, index = exponent + 3
     const int OFF = 3, LEN = CF_MAX_MATERN_P + 1 + OFF;
@@ -100,7 +100,7 @@ inline void fill_matern(cf_atom& A, int p, long double l) {
     // convert: s = kappa g;  dk/dr2 = (nu2/l^2) dk/ds2 ;  store polynomials in g
     const long double j1 = nu2 / (l * l), j2 = j1 * j1;
     for (int i = 0; i <= CF_MAX_MATERN_P; i++) {
-        A.mat[i] = (i <= p) ? (double)(M[i + OFF] * powl(kappa, i)) : 0.0;
+        A.v.mat[i] = (i <= p) ? (double)(M[i + OFF] * powl(kappa, i)) : 0.0;
         A.matA[i] = (i <= p) ? (double)(j1 * Ad[i + OFF] * powl(kappa, i)) : 0.0;
         A.matB[i] = (i <= p) ? (double)(j2 * Bd[i + OFF] * powl(kappa, i)) : 0.0;
     }
@@ -167,8 +167,8 @@ inline cf_program lower(const cf_knode_t* prog, int nnodes) {
                 cf_atom A = zero_atom();
                 A.inv_l2 = (double)(1.0L / (l * l));
                 if (nd.op == CF_OP_EQ) {
-                    A.kind = CF_ATOM_EQ;
-                    fill_exp(A.e, -0.5L / (l * l));
+                    A.v.kind = CF_ATOM_EQ;
+                    fill_exp(A.v.e, -0.5L / (l * l));
                 } else if (nd.op == CF_OP_EXP) {
                     fill_matern(A, 0, l);
                 } else if (nd.op == CF_OP_MATERNP) {
@@ -179,10 +179,10 @@ inline cf_program lower(const cf_knode_t* prog, int nnodes) {
                     if (!(nd.fparam > 0) || !std::isfinite(nd.fparam))
                         throw LowerError{CF_ERR_DOMAIN, "RQ: alpha not positive"};  // stationary.jl:47
                     const bool is_int = nd.iparam != 0 && nd.fparam == std::floor(nd.fparam) && nd.fparam <= 64;
-                    A.kind = is_int ? CF_ATOM_RQ_INT : CF_ATOM_RQ_REAL;
-                    A.p = is_int ? (int)nd.fparam : 0;
-                    A.alpha = nd.fparam;
-                    A.w = (double)(1.0L / (2.0L * (long double)nd.fparam * l * l));
+                    A.v.kind = is_int ? CF_ATOM_RQ_INT : CF_ATOM_RQ_REAL;
+                    A.v.p = is_int ? (int)nd.fparam : 0;
+                    A.v.alpha = nd.fparam;
+                    A.v.w = (double)(1.0L / (2.0L * (long double)nd.fparam * l * l));
                 }
                 st.push_back(leaf_expr(add_atom(A), true));
                 t = u - 1;
@@ -192,8 +192,8 @@ inline cf_program lower(const cf_knode_t* prog, int nnodes) {
                 throw LowerError{CF_ERR_UNSUPPORTED, "Lengthscale must wrap an isotropic base kernel"};
             case CF_OP_DOT: {
                 cf_atom A = zero_atom();
-                A.kind = CF_ATOM_LINE;
-                A.sigma = 0.0;
+                A.v.kind = CF_ATOM_LINE;
+                A.v.sigma = 0.0;
                 HExpr e = leaf_expr(add_atom(A), false);
                 e.is_plain_dot = true;
                 st.push_back(e);
@@ -221,7 +221,7 @@ inline cf_program lower(const cf_knode_t* prog, int nnodes) {
                     if (k == 2 && ((args[0].is_plain_dot && args[1].is_const) || (args[1].is_plain_dot && args[0].is_const))) {
                         const HExpr& d = args[0].is_plain_dot ? args[0] : args[1];
                         const HExpr& c = args[0].is_plain_dot ? args[1] : args[0];
-                        atoms[d.atom].sigma = c.cval;
+                        atoms[d.atom].v.sigma = c.cval;
                         out = leaf_expr(d.atom, false);
                     } else {
                         for (auto& a : args) out.terms.insert(out.terms.end(), a.terms.begin(), a.terms.end());
@@ -301,10 +301,10 @@ inline cf_program lower(const cf_knode_t* prog, int nnodes) {
     P.natoms = (int)atoms.size();
     for (int a = 0; a < P.natoms; a++) {
         cf_atom& A = atoms[a];
-        A.f_clog2e = (float)(A.e.c * 1.44269504088896340736);
-        A.f_gmax = (A.e.c != 0.0) ? (float)(-87.0 / A.e.c) : 3.0e38f;  // exp(-87) ~ 1.6e-38
-        A.f_w = (float)A.w; A.f_alpha = (float)A.alpha; A.f_sigma = (float)A.sigma; A.f_pad = 0; A.f_pad2 = 0;
-        for (int i = 0; i <= CF_MAX_MATERN_P; i++) A.f_mat[i] = (float)A.mat[i];
+        A.v.f_clog2e = (float)(A.v.e.c * 1.44269504088896340736);
+        A.v.f_gmax = (A.v.e.c != 0.0) ? (float)(-87.0 / A.v.e.c) : 3.0e38f;  // exp(-87) ~ 1.6e-38
+        A.v.f_w = (float)A.v.w; A.v.f_alpha = (float)A.v.alpha; A.v.f_sigma = (float)A.v.sigma; A.v.f_pad = 0; A.v.f_pad2 = 0;
+        for (int i = 0; i <= CF_MAX_MATERN_P; i++) A.v.f_mat[i] = (float)A.v.mat[i];
         P.atoms[a] = A;
     }
     bool used[CF_MAX_TERMS] = {false};
@@ -318,11 +318,37 @@ inline cf_program lower(const cf_knode_t* prog, int nnodes) {
     P.isotropic = 1;
     for (int a = 0; a < P.natoms; a++) {
         if (!used[a]) continue;
-        if (P.atoms[a].kind == CF_ATOM_LINE) { P.needs_dot = 1; P.isotropic = 0; }
+        if (P.atoms[a].v.kind == CF_ATOM_LINE) { P.needs_dot = 1; P.isotropic = 0; }
         else P.needs_r2 = 1;
     }
     P.single = (P.nterms == 1 && P.terms[0].nfac == 1 && P.terms[0].fac[0].power == 1) ? 1 : 0;
     return P;
+}
+
+// device program builders (limits of the parameter-resident forms)
+inline void to_sop_val(const cf_program& P, cf_sop_val& out) {
+    if (P.nterms > CF_SOP_MAX_TERMS || P.natoms > CF_SOP_MAX_ATOMS)
+        throw LowerError{CF_ERR_UNSUPPORTED, "kernel is too complex for the device program (more than 8 terms or 6 base kernels)"};
+    std::memset(&out, 0, sizeof(out));
+    out.nterms = P.nterms; out.natoms = P.natoms;
+    for (int t = 0; t < P.nterms; t++) {
+        if (P.terms[t].nfac > CF_SOP_MAX_FACTORS) throw LowerError{CF_ERR_UNSUPPORTED, "more than 4 factors in one product"};
+        out.terms[t].coef = P.terms[t].coef; out.terms[t].nfac = P.terms[t].nfac;
+        for (int f = 0; f < P.terms[t].nfac; f++) { out.terms[t].atom[f] = P.terms[t].fac[f].atom; out.terms[t].power[f] = P.terms[t].fac[f].power; }
+    }
+    for (int a = 0; a < P.natoms; a++) out.atoms[a] = P.atoms[a].v;
+}
+inline bool to_sop_grad(const cf_program& P, cf_sop_grad& out) {
+    std::memset(&out, 0, sizeof(out));
+    if (P.nterms > CF_SOPG_MAX_TERMS || P.natoms > CF_SOPG_MAX_ATOMS) return false;
+    out.nterms = P.nterms; out.natoms = P.natoms;
+    for (int t = 0; t < P.nterms; t++) {
+        if (P.terms[t].nfac > CF_SOP_MAX_FACTORS) return false;
+        out.terms[t].coef = P.terms[t].coef; out.terms[t].nfac = P.terms[t].nfac;
+        for (int f = 0; f < P.terms[t].nfac; f++) { out.terms[t].atom[f] = P.terms[t].fac[f].atom; out.terms[t].power[f] = P.terms[t].fac[f].power; }
+    }
+    for (int a = 0; a < P.natoms; a++) out.atoms[a] = P.atoms[a];
+    return true;
 }
 
 }  // namespace cf

@@ -88,7 +88,7 @@ __device__ __forceinline__ double cf_powi(double b, int p) { // p >= 1, repeated
 }
 
 // ---- atom values (FP64) ------------------------------------------------------------------------
-__device__ __forceinline__ double cf_atom_eq(double r2, const cf_atom& A, cf_tbl_t tbl_lane) {
+__device__ __forceinline__ double cf_atom_eq(double r2, const cf_atom_val& A, cf_tbl_t tbl_lane) {
     return cf_exp_cv(r2, A.e, tbl_lane);
 }
 // M(g) exp(c g), g = sqrt(r2).  The reference's Taylor branch (src/stationary.jl:139-146) differs from this
@@ -96,7 +96,7 @@ __device__ __forceinline__ double cf_atom_eq(double r2, const cf_atom& A, cf_tbl
 __device__ __forceinline__ double cf_clamp_v(double v, const cf_exp_consts& E) {
     return __hiloint2double(min(__double2hiint(v), E.vmax_hi), __double2loint(v));
 }
-__device__ __forceinline__ double cf_atom_matern(double r2, const cf_atom& A, cf_tbl_t tbl_lane) {
+__device__ __forceinline__ double cf_atom_matern(double r2, const cf_atom_val& A, cf_tbl_t tbl_lane) {
     double g = cf_clamp_v(cf_sqrt_pos(r2), A.e); // clamp BEFORE the polynomial: M(g) e^{cg} with g ~ 1e150 must be 0, not M(g) * 1e-304
     double e = cf_exp_cv(g, A.e, tbl_lane);
     int p = A.p;
@@ -105,17 +105,19 @@ __device__ __forceinline__ double cf_atom_matern(double r2, const cf_atom& A, cf
     for (int i = p - 1; i >= 0; i--) mp = fma(mp, g, A.mat[i]);
     return mp * e;
 }
-__device__ __forceinline__ double cf_atom_rq_int(double r2, const cf_atom& A) {
+__device__ __forceinline__ double cf_atom_rq_int(double r2, const cf_atom_val& A) {
     double base = fma(r2, A.w, 1.0);
     return cf_powi(cf_rcp(base), A.p);
 }
-__device__ __forceinline__ double cf_atom_rq_real(double r2, const cf_atom& A) {
+// pow() is a large routine: keep one out-of-line copy per kernel instead of one per call site (instruction cache)
+static __device__ __noinline__ double cf_pow_outlined(double base, double e) { return pow(base, e); }
+__device__ __forceinline__ double cf_atom_rq_real(double r2, const cf_atom_val& A) {
     double base = fma(r2, A.w, 1.0);
-    return pow(base, -A.alpha);
+    return cf_pow_outlined(base, -A.alpha);
 }
 
 template <int KIND>
-__device__ __forceinline__ double cf_atom_value(double r2, double dt, const cf_atom& A, cf_tbl_t tbl_lane) {
+__device__ __forceinline__ double cf_atom_value(double r2, double dt, const cf_atom_val& A, cf_tbl_t tbl_lane) {
     if (KIND == CF_ATOM_EQ) return cf_atom_eq(r2, A, tbl_lane);
     if (KIND == CF_ATOM_MATERN) return cf_atom_matern(r2, A, tbl_lane);
     if (KIND == CF_ATOM_RQ_INT) return cf_atom_rq_int(r2, A);
@@ -123,7 +125,7 @@ __device__ __forceinline__ double cf_atom_value(double r2, double dt, const cf_a
     return dt + A.sigma; // LINE
 }
 
-__device__ __forceinline__ double cf_atom_value_dyn(double r2, double dt, const cf_atom& A, cf_tbl_t tbl_lane) {
+__device__ __forceinline__ double cf_atom_value_dyn(double r2, double dt, const cf_atom_val& A, cf_tbl_t tbl_lane) {
     switch (A.kind) {
         case CF_ATOM_EQ: return cf_atom_eq(r2, A, tbl_lane);
         case CF_ATOM_MATERN: return cf_atom_matern(r2, A, tbl_lane);
@@ -133,34 +135,78 @@ __device__ __forceinline__ double cf_atom_value_dyn(double r2, double dt, const 
     }
 }
 
-// generic sum of products (program in global memory, warp-uniform control flow)
-__device__ __forceinline__ double cf_sop_value(double r2, double dt, const cf_program* __restrict__ P, cf_tbl_t tbl_lane) {
-    double val = 0.0;
-    const int nt = P->nterms;
-    for (int t = 0; t < nt; t++) {
-        const cf_term& T = P->terms[t];
-        double prod = T.coef;
-        for (int f = 0; f < T.nfac; f++) {
-            double a = cf_atom_value_dyn(r2, dt, P->atoms[T.fac[f].atom], tbl_lane);
-            prod *= cf_powi(a, T.fac[f].power);
-        }
-        val += prod;
+// generic sum of products: the program lives in the kernel parameters (constant bank) and control flow is warp-uniform.
+// N pairs are evaluated together so that the interpreter's branches and loop counters are paid once per N values.
+template <int N>
+__device__ __forceinline__ void cf_atom_value_dyn_n(const double (&r2)[N], const double (&dt)[N], const cf_atom_val& A,
+                                                    cf_tbl_t tbl_lane, double (&out)[N]) {
+    switch (A.kind) {
+        case CF_ATOM_EQ:
+#pragma unroll
+            for (int u = 0; u < N; u++) out[u] = cf_atom_eq(r2[u], A, tbl_lane);
+            break;
+        case CF_ATOM_MATERN:
+#pragma unroll
+            for (int u = 0; u < N; u++) out[u] = cf_atom_matern(r2[u], A, tbl_lane);
+            break;
+        case CF_ATOM_RQ_INT:
+#pragma unroll
+            for (int u = 0; u < N; u++) out[u] = cf_atom_rq_int(r2[u], A);
+            break;
+        case CF_ATOM_RQ_REAL:
+#pragma unroll
+            for (int u = 0; u < N; u++) out[u] = cf_atom_rq_real(r2[u], A);
+            break;
+        default:
+#pragma unroll
+            for (int u = 0; u < N; u++) out[u] = dt[u] + A.sigma;
     }
-    return val;
+}
+template <int N>
+__device__ __forceinline__ void cf_sop_value_n(const double (&r2)[N], const double (&dt)[N], const cf_sop_val& P,
+                                               cf_tbl_t tbl_lane, double (&val)[N]) {
+#pragma unroll
+    for (int u = 0; u < N; u++) val[u] = 0.0;
+    const int nt = P.nterms;
+    for (int t = 0; t < nt; t++) {
+        const cf_sop_term& T = P.terms[t];
+        double prod[N];
+#pragma unroll
+        for (int u = 0; u < N; u++) prod[u] = T.coef;
+        for (int f = 0; f < T.nfac; f++) {
+            double a[N], r[N];
+            cf_atom_value_dyn_n<N>(r2, dt, P.atoms[T.atom[f]], tbl_lane, a);
+#pragma unroll
+            for (int u = 0; u < N; u++) r[u] = a[u];
+            for (int q = 1; q < T.power[f]; q++) {
+#pragma unroll
+                for (int u = 0; u < N; u++) r[u] *= a[u];
+            }
+#pragma unroll
+            for (int u = 0; u < N; u++) prod[u] *= r[u];
+        }
+#pragma unroll
+        for (int u = 0; u < N; u++) val[u] += prod[u];
+    }
+}
+__device__ __forceinline__ double cf_sop_value(double r2, double dt, const cf_sop_val& P, cf_tbl_t tbl_lane) {
+    double a[1] = {r2}, b[1] = {dt}, v[1];
+    cf_sop_value_n<1>(a, b, P, tbl_lane, v);
+    return v[0];
 }
 
 // ---- derivatives with respect to r2 (gradient kernel; reference src/gradient.jl:589-600) -------------
 // returns k, k1 = dk/dr2, k2 = d2k/dr2^2 of one isotropic atom
 __device__ __forceinline__ void cf_atom_jet(double r2, const cf_atom& A, cf_tbl_t tbl_lane, double& k, double& k1, double& k2) {
-    switch (A.kind) {
+    switch (A.v.kind) {
         case CF_ATOM_EQ: {
-            k = cf_exp_cv(r2, A.e, tbl_lane);
-            k1 = A.e.c * k;
-            k2 = A.e.c * k1;
+            k = cf_exp_cv(r2, A.v.e, tbl_lane);
+            k1 = A.v.e.c * k;
+            k2 = A.v.e.c * k1;
             return;
         }
         case CF_ATOM_MATERN: {
-            const int p = A.p;
+            const int p = A.v.p;
             const double s = r2 * A.inv_l2; // the inner kernel sees r2 / l^2 (reference src/transformation.jl:19)
             if (s < A.taylor_bound) { // reference src/stationary.jl:139-146 (differentiated through by ForwardDiff)
                 double v = 0, d1 = 0, d2 = 0;
@@ -172,10 +218,10 @@ __device__ __forceinline__ void cf_atom_jet(double r2, const cf_atom& A, cf_tbl_
                 k = v; k1 = d1 * A.inv_l2; k2 = d2 * A.inv_l2 * A.inv_l2;
                 return;
             }
-            double g = cf_clamp_v(cf_sqrt_pos(r2), A.e);
-            double e = cf_exp_cv(g, A.e, tbl_lane);
-            double m = A.mat[p], a = (p >= 1) ? A.matA[p - 1] : 0.0, b = (p >= 2) ? A.matB[p - 2] : 0.0;
-            for (int i = p - 1; i >= 0; i--) m = fma(m, g, A.mat[i]);
+            double g = cf_clamp_v(cf_sqrt_pos(r2), A.v.e);
+            double e = cf_exp_cv(g, A.v.e, tbl_lane);
+            double m = A.v.mat[p], a = (p >= 1) ? A.matA[p - 1] : 0.0, b = (p >= 2) ? A.matB[p - 2] : 0.0;
+            for (int i = p - 1; i >= 0; i--) m = fma(m, g, A.v.mat[i]);
             for (int i = p - 2; i >= 0; i--) a = fma(a, g, A.matA[i]);
             for (int i = p - 3; i >= 0; i--) b = fma(b, g, A.matB[i]);
             if (A.am1 != 0.0 || A.bm[0] != 0.0 || A.bm[1] != 0.0 || A.bm[2] != 0.0) { // p <= 1: singular terms
@@ -188,11 +234,11 @@ __device__ __forceinline__ void cf_atom_jet(double r2, const cf_atom& A, cf_tbl_
         }
         case CF_ATOM_RQ_INT:
         case CF_ATOM_RQ_REAL: {
-            double base = fma(r2, A.w, 1.0);
+            double base = fma(r2, A.v.w, 1.0);
             double ib = 1.0 / base;
-            k = (A.kind == CF_ATOM_RQ_INT) ? cf_powi(ib, A.p) : pow(base, -A.alpha);
-            k1 = -A.alpha * A.w * k * ib;
-            k2 = -(A.alpha + 1.0) * A.w * k1 * ib;
+            k = (A.v.kind == CF_ATOM_RQ_INT) ? cf_powi(ib, A.v.p) : cf_pow_outlined(base, -A.v.alpha);
+            k1 = -A.v.alpha * A.v.w * k * ib;
+            k2 = -(A.v.alpha + 1.0) * A.v.w * k1 * ib;
             return;
         }
         default: k = k1 = k2 = 0.0 / 0.0; return; // LINE is not isotropic
@@ -200,16 +246,15 @@ __device__ __forceinline__ void cf_atom_jet(double r2, const cf_atom& A, cf_tbl_
 }
 
 // jets of the generic isotropic sum of products: product rule over factors, powers by repeated multiplication
-__device__ __forceinline__ void cf_sop_jet(double r2, const cf_program* __restrict__ P, cf_tbl_t tbl_lane, double& k,
-                                           double& k1, double& k2) {
+__device__ __forceinline__ void cf_sop_jet(double r2, const cf_sop_grad& P, cf_tbl_t tbl_lane, double& k, double& k1, double& k2) {
     double sv = 0, s1 = 0, s2 = 0;
-    for (int t = 0; t < P->nterms; t++) {
-        const cf_term& T = P->terms[t];
+    for (int t = 0; t < P.nterms; t++) {
+        const cf_sop_term& T = P.terms[t];
         double pv = T.coef, p1 = 0, p2 = 0;
         for (int f = 0; f < T.nfac; f++) {
             double av, a1, a2;
-            cf_atom_jet(r2, P->atoms[T.fac[f].atom], tbl_lane, av, a1, a2);
-            for (int q = 0; q < T.fac[f].power; q++) {
+            cf_atom_jet(r2, P.atoms[T.atom[f]], tbl_lane, av, a1, a2);
+            for (int q = 0; q < T.power[f]; q++) {
                 double nv = pv * av;
                 double n1 = fma(p1, av, pv * a1);
                 double n2 = fma(p2, av, fma(2.0 * p1, a1, pv * a2));
@@ -231,7 +276,7 @@ __device__ __forceinline__ float cf_lg2f(float x) { float y; asm("lg2.approx.ftz
 
 // KIND < 0: dispatch on A.kind at run time (generic sum of products)
 template <int KIND>
-__device__ __forceinline__ float cf_atom_value_f32(float r2, float dt, const cf_atom& A) {
+__device__ __forceinline__ float cf_atom_value_f32(float r2, float dt, const cf_atom_val& A) {
     const int kind = (KIND >= 0) ? KIND : A.kind;
     if (kind == CF_ATOM_EQ) return cf_ex2f(r2 * A.f_clog2e);
     if (kind == CF_ATOM_MATERN) {
@@ -253,18 +298,33 @@ __device__ __forceinline__ float cf_atom_value_f32(float r2, float dt, const cf_
     if (kind == CF_ATOM_RQ_REAL) return cf_ex2f(-A.f_alpha * cf_lg2f(fmaf(r2, A.f_w, 1.0f)));
     return dt + A.f_sigma;
 }
-__device__ __forceinline__ float cf_sop_value_f32(float r2, float dt, const cf_program* __restrict__ P) {
-    float val = 0.f;
-    for (int t = 0; t < P->nterms; t++) {
-        const cf_term& T = P->terms[t];
-        float prod = (float)T.coef;
+template <int N>
+__device__ __forceinline__ void cf_sop_value_f32_n(const float (&r2)[N], const float (&dt)[N], const cf_sop_val& P, float (&val)[N]) {
+#pragma unroll
+    for (int u = 0; u < N; u++) val[u] = 0.f;
+    for (int t = 0; t < P.nterms; t++) {
+        const cf_sop_term& T = P.terms[t];
+        float prod[N];
+#pragma unroll
+        for (int u = 0; u < N; u++) prod[u] = (float)T.coef;
         for (int f = 0; f < T.nfac; f++) {
-            float a = cf_atom_value_f32<-1>(r2, dt, P->atoms[T.fac[f].atom]);
-            float r = a;
-            for (int q = 1; q < T.fac[f].power; q++) r *= a;
-            prod *= r;
+            const cf_atom_val& A = P.atoms[T.atom[f]];
+            float a[N], r[N];
+#pragma unroll
+            for (int u = 0; u < N; u++) { a[u] = cf_atom_value_f32<-1>(r2[u], dt[u], A); r[u] = a[u]; }
+            for (int q = 1; q < T.power[f]; q++) {
+#pragma unroll
+                for (int u = 0; u < N; u++) r[u] *= a[u];
+            }
+#pragma unroll
+            for (int u = 0; u < N; u++) prod[u] *= r[u];
         }
-        val += prod;
+#pragma unroll
+        for (int u = 0; u < N; u++) val[u] += prod[u];
     }
-    return val;
+}
+__device__ __forceinline__ float cf_sop_value_f32(float r2, float dt, const cf_sop_val& P) {
+    float a[1] = {r2}, b[1] = {dt}, v[1];
+    cf_sop_value_f32_n<1>(a, b, P, v);
+    return v[0];
 }

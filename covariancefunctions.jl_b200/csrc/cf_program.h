@@ -33,31 +33,35 @@ struct cf_exp_consts {
     int32_t pad_;
 };
 
-struct cf_atom {
+// value-path constants of one atom (kept small: programs travel in kernel parameters = constant bank, so that every
+// coefficient is an instruction operand instead of a dependent global/shared load)
+struct cf_atom_val {
     int32_t kind;
     int32_t p;       // Matern p / integer alpha / unused
     cf_exp_consts e; // EQ, MATERN
     // MATERN value polynomial in g: M(g) = sum_i mat[i] g^i (degree p), already divided by (2p)!/p!
     double mat[CF_MAX_MATERN_P + 1];
-    // MATERN derivative polynomials (gradient kernel): k1 = (A(g) + am1/g) e, k2 = (B(g) + bm[0]/g + bm[1]/g^2 + bm[2]/g^3) e
-    double matA[CF_MAX_MATERN_P + 1];
-    double matB[CF_MAX_MATERN_P + 1];
-    double am1, bm[3];
-    // MATERN Taylor branch (r2 < taylor_bound): derivatives at zero d_i / i!  (reference src/stationary.jl:139-146)
-    double taylor_bound;
-    double tay[CF_MAX_MATERN_P + 1]; // tay[0] = 1
-    // RQ: w = 1 / (2 alpha l^2), alpha
-    double w, alpha;
-    // LINE
-    double sigma;
-    // plain r2 multiplier 1/l^2 (RQ, Taylor branch)
-    double inv_l2;
-    // Float32 copies of the constants the fp32 kernels use (no fp64 instruction in the fp32 inner loop)
-    float f_clog2e;   // c * log2(e): exp(c v) = ex2(f_clog2e * v)
-    float f_gmax;     // clamp of g = sqrt(r2) so that M(g) exp(c g) underflows cleanly
+    double w, alpha; // RQ: w = 1 / (2 alpha l^2)
+    double sigma;    // LINE
+    // Float32 copies (no fp64 instruction in the fp32 inner loop)
+    float f_clog2e;  // c * log2(e): exp(c v) = ex2(f_clog2e * v)
+    float f_gmax;    // clamp of g = sqrt(r2) so that M(g) exp(c g) underflows cleanly
     float f_w, f_alpha, f_sigma, f_pad;
     float f_mat[CF_MAX_MATERN_P + 1];
     float f_pad2;
+};
+
+// full atom: value constants + derivative data for the gradient kernel
+struct cf_atom {
+    cf_atom_val v;
+    // MATERN derivative polynomials: k1 = (A(g) + am1/g) e, k2 = (B(g) + bm[0]/g + bm[1]/g^2 + bm[2]/g^3) e
+    double matA[CF_MAX_MATERN_P + 1];
+    double matB[CF_MAX_MATERN_P + 1];
+    double am1, bm[3];
+    // MATERN Taylor branch (r2 / l^2 < taylor_bound): derivatives at zero d_i / i!  (reference src/stationary.jl:139-146)
+    double taylor_bound;
+    double tay[CF_MAX_MATERN_P + 1]; // tay[0] = 1
+    double inv_l2;                   // plain r2 multiplier 1/l^2
 };
 
 struct cf_factor {
@@ -72,6 +76,7 @@ struct cf_term {
     cf_factor fac[CF_MAX_FACTORS];
 };
 
+// host-side lowered program (generous limits)
 struct cf_program {
     int32_t nterms;
     int32_t natoms;
@@ -79,5 +84,29 @@ struct cf_program {
     int32_t isotropic; // every atom is a function of r2 (IsotropicInput trait, reference src/properties.jl:39-63)
     int32_t single;    // 1 if the program is coef * one atom ^ 1 -> specialised kernels
     cf_term terms[CF_MAX_TERMS];
-    cf_atom atoms[CF_MAX_TERMS]; // at most one new atom per term in practice; capped
+    cf_atom atoms[CF_MAX_TERMS];
+};
+
+// device-side programs, passed BY VALUE in kernel parameters
+#define CF_SOP_MAX_TERMS 8
+#define CF_SOP_MAX_FACTORS 4
+#define CF_SOP_MAX_ATOMS 6
+#define CF_SOPG_MAX_TERMS 4
+#define CF_SOPG_MAX_ATOMS 3
+struct cf_sop_term {
+    double coef;
+    int32_t nfac;
+    int32_t atom[CF_SOP_MAX_FACTORS];
+    int32_t power[CF_SOP_MAX_FACTORS];
+    int32_t pad_;
+};
+struct cf_sop_val { // value kernels (MVM, multi-RHS, dense)
+    int32_t nterms, natoms;
+    cf_sop_term terms[CF_SOP_MAX_TERMS];
+    cf_atom_val atoms[CF_SOP_MAX_ATOMS];
+};
+struct cf_sop_grad { // gradient kernel (needs the derivative data)
+    int32_t nterms, natoms;
+    cf_sop_term terms[CF_SOPG_MAX_TERMS];
+    cf_atom atoms[CF_SOPG_MAX_ATOMS];
 };

@@ -19,10 +19,10 @@ struct cf_grad_params {
     const double* a;   // padded, m x D
     double* partial;   // [chunks][nrows * D]
     const double* exp2_tbl;
-    const cf_program* prog; // used when !single
     int64_t row0, nrows, m, cols_per_chunk;
     int single;
-    cf_atom atom;
+    cf_atom atom;      // single atom
+    cf_sop_grad sop;   // composite isotropic kernels (!single)
     double coef;       // leading constant of a single-atom program
 };
 
@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(NT, MINB) grad_mvm_kernel(const __grid_constan
                 }
                 double k, k1, k2;
                 if (P.single) cf_atom_jet(r2, P.atom, tbl_lane, k, k1, k2);
-                else cf_sop_jet(r2, P.prog, tbl_lane, k, k1, k2);
+                else cf_sop_jet(r2, P.sop, tbl_lane, k, k1, k2);
                 const double ca = -2.0 * k1, cr = -4.0 * k2 * dra;
 #pragma unroll
                 for (int c = 0; c < D; c++) b[r][c] = fma(cr, rr[c], fma(ca, aj[c], b[r][c]));

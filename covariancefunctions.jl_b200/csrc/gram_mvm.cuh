@@ -26,7 +26,6 @@ struct cf_mvm_params {
     void* out;            // y (direct) or partial sums [chunks][nrows]
     const void* yin;      // y for the beta term (direct mode)
     const double* exp2_tbl;
-    const cf_program* prog; // generic sum-of-products program (global memory), KIND == CF_ATOM_SOP only
     int64_t row0, nrows;  // rows [row0, row0 + nrows) are computed; out index = i - row0
     int64_t m;            // number of columns
     int64_t cols_per_chunk; // multiple of TJ
@@ -34,7 +33,8 @@ struct cf_mvm_params {
     double coef;          // leading constant of a single-atom program (folded into alpha by the host when direct)
     int direct;           // 1: write alpha*sum + beta*y, 0: write the raw partial sum
     int use_tma;          // 0: a is not 16-byte aligned -> cooperative loads
-    cf_atom atom;         // the single atom (specialised kinds)
+    cf_atom_val atom;     // the single atom (specialised kinds)
+    cf_sop_val sop;       // generic sum of products (KIND == CF_ATOM_SOP)
 };
 
 // ---- mbarrier / TMA 1-D bulk copy wrappers (PTX ISA: cp.async.bulk, mbarrier) ------------------------------
@@ -78,27 +78,37 @@ struct cf_mvm_smem {
     static constexpr int total = tbl_bytes + bar_bytes + NS * stage_bytes;
 };
 
-// pair evaluation -------------------------------------------------------------------------------------
-template <typename T, int D, int KIND>
-__device__ __forceinline__ T cf_pair_value(const T (&x)[D], const T* __restrict__ yj, const cf_mvm_params& P, cf_tbl_t tbl_lane) {
-    T r2 = 0, dt = 0;
-    if (KIND != CF_ATOM_LINE) {
+// k(x_r, y_j) for the R rows of a thread ----------------------------------------------------------------------
+template <typename T, int D, int KIND, int R>
+__device__ __forceinline__ void cf_rows_value(const T (&x)[R][D], const T (&yj)[D], const cf_mvm_params& P, cf_tbl_t tbl_lane, T (&kv)[R]) {
+    T r2[R], dt[R];
 #pragma unroll
-        for (int c = 0; c < D; c++) {
-            T df = x[c] - yj[c];
-            r2 = (c == 0) ? df * df : fma(df, df, r2);
+    for (int r = 0; r < R; r++) {
+        r2[r] = 0; dt[r] = 0;
+        if (KIND != CF_ATOM_LINE) {
+#pragma unroll
+            for (int c = 0; c < D; c++) {
+                T df = x[r][c] - yj[c];
+                r2[r] = (c == 0) ? df * df : fma(df, df, r2[r]);
+            }
+        }
+        if (KIND == CF_ATOM_LINE || KIND == CF_ATOM_SOP) {
+#pragma unroll
+            for (int c = 0; c < D; c++) dt[r] = (c == 0) ? x[r][c] * yj[c] : fma(x[r][c], yj[c], dt[r]);
         }
     }
-    if (KIND == CF_ATOM_LINE || KIND == CF_ATOM_SOP) {
-#pragma unroll
-        for (int c = 0; c < D; c++) dt = (c == 0) ? x[c] * yj[c] : fma(x[c], yj[c], dt);
-    }
     if constexpr (sizeof(T) == 8) {
-        if (KIND == CF_ATOM_SOP) return cf_sop_value(r2, dt, P.prog, tbl_lane);
-        return cf_atom_value<KIND>(r2, dt, P.atom, tbl_lane);
+        if constexpr (KIND == CF_ATOM_SOP) cf_sop_value_n<R>(r2, dt, P.sop, tbl_lane, kv);
+        else {
+#pragma unroll
+            for (int r = 0; r < R; r++) kv[r] = cf_atom_value<KIND>(r2[r], dt[r], P.atom, tbl_lane);
+        }
     } else {
-        if (KIND == CF_ATOM_SOP) return cf_sop_value_f32(r2, dt, P.prog);
-        return cf_atom_value_f32<KIND>(r2, dt, P.atom);
+        if constexpr (KIND == CF_ATOM_SOP) cf_sop_value_f32_n<R>(r2, dt, P.sop, kv);
+        else {
+#pragma unroll
+            for (int r = 0; r < R; r++) kv[r] = cf_atom_value_f32<KIND>(r2[r], dt[r], P.atom);
+        }
     }
 }
 
@@ -167,11 +177,10 @@ __global__ void __launch_bounds__(NT, MINB) gram_mvm_kernel(const __grid_constan
 #pragma unroll
             for (int c = 0; c < D; c++) yj[c] = ys[j * D + c];
             const T aj = as[j];
+            T kv[R];
+            cf_rows_value<T, D, KIND, R>(x, yj, P, tbl_lane, kv);
 #pragma unroll
-            for (int r = 0; r < R; r++) {
-                T kv = cf_pair_value<T, D, KIND>(x[r], yj, P, tbl_lane);
-                acc[r] = fma(kv, aj, acc[r]);
-            }
+            for (int r = 0; r < R; r++) acc[r] = fma(kv[r], aj, acc[r]);
         }
 #pragma unroll
         for (int r = 0; r < R; r++) tot[r] += (double)acc[r];

@@ -117,8 +117,7 @@ def cpu_port_rate(w, X, a, target_s=12.0, threads=None):
     from oracle import oracle as O
 
     O.build()
-    if threads:
-        O.set_num_threads(threads)
+    O.set_num_threads(threads or os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
     prog = w["kernel"].program()
     n = w["n"]
 
@@ -279,7 +278,7 @@ def main():
     b_pin = torch.empty_like(b_loc, device="cpu").pin_memory()
     a_np = a_pin.numpy().T if nrhs > 1 else a_pin.numpy()
     b_np = b_pin.numpy().T if nrhs > 1 else b_pin.numpy()
-    XT = np.ascontiguousarray(X.T)
+    XT = X.T  # d x n, column-major (columns are points): the layout of a Julia Matrix passed to gramian(k, X)
 
     def step_e2e():
         Ge = cf.gramian(k, XT).set_row_range(r0, r1)  # create: packs + uploads X (reference: gramian(k, x) is O(1) lazy)

@@ -455,19 +455,28 @@ int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, co
     return CF_OK;
 }
 
-template <typename T>
-int pack_points(const T* X, int64_t ldx, int64_t n, int d, int D, std::vector<T>& out, double* max_sqnorm) {
-    out.assign((size_t)n * D, (T)0);
-    for (int64_t i = 0; i < n; i++) {
-        double s = 0;
-        for (int c = 0; c < d; c++) {
-            T v = X[i * ldx + c];
-            if (!std::isfinite((double)v)) return fail(CF_ERR_NONFINITE, "point %lld coordinate %d is not finite", (long long)i, c);
-            out[(size_t)i * D + c] = v;
-            s += (double)v * (double)v;
-        }
-        if (s > *max_sqnorm) *max_sqnorm = s;
+// upload one point set: raw d x n (leading dimension ld) -> padded AoS on the device, squared norms, finiteness check.
+// No host-side packing: one 2-D copy, one pad kernel (only when D != d) and one validation/norm kernel.
+int upload_points(int dtype, const void* H, int64_t ld, int64_t n, int d, int D, void** dX, void** dN, Buf& scratch,
+                  double* flags_dev, cudaStream_t st) {
+    const size_t es = esize(dtype);
+    CF_CUDA(cudaMalloc(dX, std::max<size_t>(16, (size_t)n * D * es)));
+    CF_CUDA(cudaMalloc(dN, std::max<size_t>(16, (size_t)n * es)));
+    if (n == 0) return CF_OK;
+    if (D == d) {
+        CF_CUDA(cudaMemcpy2DAsync(*dX, (size_t)d * es, H, (size_t)ld * es, (size_t)d * es, n, cudaMemcpyHostToDevice, st));
+    } else {
+        if (int rc = scratch.ensure((size_t)n * d * es)) return rc;
+        CF_CUDA(cudaMemcpy2DAsync(scratch.p, (size_t)d * es, H, (size_t)ld * es, (size_t)d * es, n, cudaMemcpyHostToDevice, st));
+        const int blocks = (int)std::min<int64_t>((n * D + 255) / 256, 8192);
+        if (dtype == CF_F64) cf_pad_points<double><<<blocks, 256, 0, st>>>((const double*)scratch.p, d, d, (double*)*dX, D, n);
+        else cf_pad_points<float><<<blocks, 256, 0, st>>>((const float*)scratch.p, d, d, (float*)*dX, D, n);
+        CF_CUDA(cudaGetLastError());
     }
+    const int nb = (int)std::min<int64_t>((n + 255) / 256, 4096);
+    if (dtype == CF_F64) cf_sqnorm_validate_kernel<double><<<nb, 256, 0, st>>>((const double*)*dX, D, n, (double*)*dN, flags_dev);
+    else cf_sqnorm_validate_kernel<float><<<nb, 256, 0, st>>>((const float*)*dX, D, n, (float*)*dN, flags_dev);
+    CF_CUDA(cudaGetLastError());
     return CF_OK;
 }
 
@@ -570,28 +579,9 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
         if (cudaGetDevice(&cur) != cudaSuccess) { delete g; return fail(CF_ERR_CUDA, "cudaGetDevice failed"); }
         devs.push_back(cur);
     }
-    // host packing (+ finiteness validation)
-    std::vector<double> xd, yd;
-    std::vector<float> xf, yf;
-    int rc = CF_OK;
-    double max_sq = 0;
-    if (dtype == CF_F64) {
-        rc = pack_points<double>((const double*)X, ldx, n, d, g->D, xd, &max_sq);
-        if (!rc && Y) rc = pack_points<double>((const double*)Y, ldy, m, d, g->D, yd, &max_sq);
-    } else {
-        rc = pack_points<float>((const float*)X, ldx, n, d, g->D, xf, &max_sq);
-        if (!rc && Y) rc = pack_points<float>((const float*)Y, ldy, m, d, g->D, yf, &max_sq);
-    }
-    if (rc) { delete g; return rc; }
-    // r2 from norms only for larger d and well-scaled data: |delta r2| <= (d + 2) eps (|x|^2 + |y|^2) must stay below 1e-13
-    {
-        const double eps = dtype == CF_F64 ? 2.220446049250313e-16 : 1.1920928955078125e-07;
-        const double bound = dtype == CF_F64 ? 1e-13 : 1e-5;
-        g->use_norms = (d >= 8) && ((d + 2) * eps * 2.0 * max_sq < bound);
-    }
-    const void* hx = dtype == CF_F64 ? (const void*)xd.data() : (const void*)xf.data();
-    const void* hy = dtype == CF_F64 ? (const void*)yd.data() : (const void*)yf.data();
     const size_t es = esize(dtype);
+    double max_sq = 0;
+    int rc = CF_OK;
 
     g->shards.resize(devs.size());
     for (size_t s = 0; s < devs.size(); s++) {
@@ -610,31 +600,36 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
         CF_CREATE_CUDA(cudaStreamCreateWithFlags(&sh.stream, cudaStreamNonBlocking));
         CF_CREATE_CUDA(cudaEventCreate(&sh.ev0));
         CF_CREATE_CUDA(cudaEventCreate(&sh.ev1));
-        CF_CREATE_CUDA(cudaMalloc(&sh.X, std::max<size_t>(16, (size_t)n * g->D * es)));
-        if (n) CF_CREATE_CUDA(cudaMemcpy(sh.X, hx, (size_t)n * g->D * es, cudaMemcpyHostToDevice));
-        if (Y) {
-            CF_CREATE_CUDA(cudaMalloc(&sh.Y, std::max<size_t>(16, (size_t)m * g->D * es)));
-            if (m) CF_CREATE_CUDA(cudaMemcpy(sh.Y, hy, (size_t)m * g->D * es, cudaMemcpyHostToDevice));
-        } else {
-            sh.Y = sh.X;
-        }
-        CF_CREATE_CUDA(cudaMalloc(&sh.xn, std::max<size_t>(16, (size_t)n * es)));
-        if (Y) CF_CREATE_CUDA(cudaMalloc(&sh.yn, std::max<size_t>(16, (size_t)m * es)));
-        else sh.yn = sh.xn;
         {
-            const int nb = (int)std::min<int64_t>((std::max<int64_t>(n, m) + 255) / 256 + 1, 4096);
-            if (dtype == CF_F64) {
-                if (n) cf_sqnorm_kernel<double><<<nb, 256>>>((const double*)sh.X, g->D, n, (double*)sh.xn);
-                if (Y && m) cf_sqnorm_kernel<double><<<nb, 256>>>((const double*)sh.Y, g->D, m, (double*)sh.yn);
-            } else {
-                if (n) cf_sqnorm_kernel<float><<<nb, 256>>>((const float*)sh.X, g->D, n, (float*)sh.xn);
-                if (Y && m) cf_sqnorm_kernel<float><<<nb, 256>>>((const float*)sh.Y, g->D, m, (float*)sh.yn);
+            // flags[0] = number of non-finite coordinates, flags[1] = max squared norm (as ordered bits)
+            double* flags = nullptr;
+            CF_CREATE_CUDA(cudaMalloc(&flags, 16));
+            CF_CREATE_CUDA(cudaMemsetAsync(flags, 0, 16, sh.stream));
+            rc = upload_points(dtype, X, ldx, n, d, g->D, &sh.X, &sh.xn, sh.apad, flags, sh.stream);
+            if (!rc) {
+                if (Y) rc = upload_points(dtype, Y, ldy, m, d, g->D, &sh.Y, &sh.yn, sh.apad, flags, sh.stream);
+                else { sh.Y = sh.X; sh.yn = sh.xn; }
             }
-            CF_CREATE_CUDA(cudaGetLastError());
-            CF_CREATE_CUDA(cudaDeviceSynchronize());
+            unsigned long long hflags[2] = {0, 0};
+            if (!rc && cudaMemcpyAsync(hflags, flags, 16, cudaMemcpyDeviceToHost, sh.stream) != cudaSuccess) rc = fail(CF_ERR_CUDA, "flag copy failed");
+            if (!rc && cudaStreamSynchronize(sh.stream) != cudaSuccess) rc = fail(CF_ERR_CUDA, "upload failed: %s", cudaGetErrorString(cudaGetLastError()));
+            cudaFree(flags);
+            if (!rc && hflags[0] != 0) rc = fail(CF_ERR_NONFINITE, "%llu point coordinates are not finite (NaN or Inf)", hflags[0]);
+            if (rc) { destroy_impl(g); return rc; }
+            double ms;
+            std::memcpy(&ms, &hflags[1], 8);
+            max_sq = std::max(max_sq, ms);
         }
 #undef CF_CREATE_CUDA
     }
+    // r2 from norms (multi-RHS kernel) only for larger d and well-scaled data:
+    // |delta r2| <= (d + 2) eps (|x|^2 + |y|^2) must stay below 1e-13 (Float64) / 1e-5 (Float32)
+    {
+        const double eps = dtype == CF_F64 ? 2.220446049250313e-16 : 1.1920928955078125e-07;
+        const double bound = dtype == CF_F64 ? 1e-13 : 1e-5;
+        g->use_norms = (d >= 8) && ((d + 2) * eps * 2.0 * max_sq < bound);
+    }
+    (void)es;
     split_rows(g);
     *out = g;
     return CF_OK;

@@ -96,14 +96,25 @@ __global__ void cf_transpose_rhs(const T* __restrict__ A, int64_t lda, int64_t m
     }
 }
 
-// squared norms of padded points
+// squared norms of padded points + validation: flags[0] += number of non-finite coordinates,
+// flags[1] = max squared norm (bit pattern of a non-negative double: integer order == floating-point order)
 template <typename T>
-__global__ void cf_sqnorm_kernel(const T* __restrict__ X, int D, int64_t n, T* __restrict__ out) {
+__global__ void cf_sqnorm_validate_kernel(const T* __restrict__ X, int D, int64_t n, T* __restrict__ out, double* flags) {
+    unsigned long long bad = 0;
+    double mx = 0.0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         T s = 0;
-        for (int c = 0; c < D; c++) s = fma(X[i * D + c], X[i * D + c], s);
+        for (int c = 0; c < D; c++) {
+            const T v = X[i * D + c];
+            if (!isfinite(v)) bad++;
+            s = fma(v, v, s);
+        }
         out[i] = s;
+        if ((double)s > mx) mx = (double)s;
     }
+    unsigned long long* f = reinterpret_cast<unsigned long long*>(flags);
+    if (bad) atomicAdd(&f[0], bad);
+    if (mx > 0.0 && isfinite(mx)) atomicMax(&f[1], (unsigned long long)__double_as_longlong(mx));
 }
 
 template <typename T, int D>

@@ -463,11 +463,17 @@ int upload_points(int dtype, const void* H, int64_t ld, int64_t n, int d, int D,
     CF_CUDA(cudaMalloc(dX, std::max<size_t>(16, (size_t)n * D * es)));
     CF_CUDA(cudaMalloc(dN, std::max<size_t>(16, (size_t)n * es)));
     if (n == 0) return CF_OK;
+    // a 2-D copy of n rows of d*es bytes is processed row by row by the driver (150 ms for 2^20 points): use the 1-D form
+    // whenever the host buffer is dense (ld == d), which is the layout of a Julia Matrix / vecofvec column views
+    auto h2d = [&](void* dst) -> cudaError_t {
+        if (ld == d) return cudaMemcpyAsync(dst, H, (size_t)n * d * es, cudaMemcpyHostToDevice, st);
+        return cudaMemcpy2DAsync(dst, (size_t)d * es, H, (size_t)ld * es, (size_t)d * es, n, cudaMemcpyHostToDevice, st);
+    };
     if (D == d) {
-        CF_CUDA(cudaMemcpy2DAsync(*dX, (size_t)d * es, H, (size_t)ld * es, (size_t)d * es, n, cudaMemcpyHostToDevice, st));
+        CF_CUDA(h2d(*dX));
     } else {
         if (int rc = scratch.ensure((size_t)n * d * es)) return rc;
-        CF_CUDA(cudaMemcpy2DAsync(scratch.p, (size_t)d * es, H, (size_t)ld * es, (size_t)d * es, n, cudaMemcpyHostToDevice, st));
+        CF_CUDA(h2d(scratch.p));
         const int blocks = (int)std::min<int64_t>((n * D + 255) / 256, 8192);
         if (dtype == CF_F64) cf_pad_points<double><<<blocks, 256, 0, st>>>((const double*)scratch.p, d, d, (double*)*dX, D, n);
         else cf_pad_points<float><<<blocks, 256, 0, st>>>((const float*)scratch.p, d, d, (float*)*dX, D, n);

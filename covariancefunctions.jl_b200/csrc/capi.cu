@@ -278,6 +278,7 @@ int cg_solve_impl(cf_gramian_s* g, double sigma2, double* x, const double* b, do
             // gather this row block next to the sigma2 term (scratch: cg[4] is b, so use shard-0 partial-free buffer)
         }
         // gather: copy every block into a scratch vector on device 0 and add
+        CF_CUDA(cudaSetDevice(s0.ctx->dev));
         if (int rc = s0.ypad.ensure((size_t)N * 8)) return rc;
         for (size_t q = 0; q < g->shards.size(); q++) {
             Shard& sh = g->shards[q];
@@ -713,10 +714,17 @@ static int mul_host_impl(cf_gramian_t g, void* y, int64_t ldy, const void* x, in
             }
         }
         CF_CUDA(cudaEventRecord(sh.ev1, sh.stream));
+    }
+    // stage 2: results back (a device-to-host copy into pageable memory blocks the host, so it must not sit between
+    // the launches of different shards), then wait
+    for (auto& sh : g->shards) {
+        const int64_t srows = (sh.r1 - sh.r0) * blk;
+        if (srows == 0) continue;
+        const int64_t off = (sh.r0 - g->row_begin) * blk;
+        CF_CUDA(cudaSetDevice(sh.ctx->dev));
         CF_CUDA(cudaMemcpy2DAsync((char*)y + off * es, ldy * es, sh.y.p, srows * es, srows * es, nrhs, cudaMemcpyDeviceToHost,
                                   sh.stream));
     }
-    // stage 2: wait
     float worst = 0;
     for (auto& sh : g->shards) {
         CF_CUDA(cudaSetDevice(sh.ctx->dev));

@@ -1,0 +1,53 @@
+"""Single-process multi-GPU mode (cf_init): one host thread drives several devices, rows sharded inside the library --
+the form the Julia ccall shim uses.  Needs >= 2 GPUs (gpurun --gpus 2); skipped otherwise."""
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture()
+def two_gpus(cf):
+    if cf.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    cf.init([0, 1])
+    yield
+    cf.init([0])
+
+
+def test_rows_sharded_over_two_devices(cf, O, two_gpus):
+    rng = np.random.default_rng(41)
+    n, m, d = 3001, 2000, 3  # ragged split
+    X, Y = rng.standard_normal((n, d)), rng.standard_normal((m, d))
+    a = rng.standard_normal(m)
+    for k in (cf.EQ(), cf.MaternP(2), 0.5 * cf.RQ(2) + cf.Dot() ** 2):
+        G = cf.gramian(k, X.T, Y.T)
+        assert relerr(G @ a, O.mul_vec(k.program(), X, a, Y=Y)) < 1e-12
+        y0 = rng.standard_normal(n)
+        y = y0.copy()
+        cf.mul_(y, G, a, 0.5, -2.0)
+        assert relerr(y, O.mul_vec(k.program(), X, a, Y=Y, alpha=0.5, beta=-2.0, y0=y0)) < 1e-12
+    A = rng.standard_normal((m, 5))
+    G = cf.gramian(cf.EQ(), X.T, Y.T)
+    assert relerr(G @ A, O.mul_mat(cf.EQ().program(), X, A, Y=Y)) < 1e-12
+    Xg = rng.standard_normal((301, 4)) / 2
+    ag = rng.standard_normal(301 * 4)
+    Gg = cf.gramian(cf.GradientKernel(cf.MaternP(2)), Xg.T)
+    assert relerr(Gg @ ag, O.gradient_mul(cf.MaternP(2).program(), Xg, ag)) < 1e-12
+    M = cf.gramian(cf.EQ(), X[:100].T, Y[:70].T).Matrix()
+    assert relerr(M, O.matrix(cf.EQ().program(), X[:100], Y[:70])) < 1e-13
+
+
+def test_cg_over_two_devices(cf, O, two_gpus):
+    rng = np.random.default_rng(42)
+    n, d = 1201, 8
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    y = rng.standard_normal(n)
+    k = cf.MaternP(2)
+    A = 1e-2 * cf.I(n) + cf.gramian(k, X.T)
+    x, iters, res = A.solve(y)
+    xo, ito, reso, _ = O.cg_solve(k.program(), X, y, 1e-2)
+    assert abs(iters - ito) <= max(3, 0.05 * ito)
+    assert relerr(x, xo) < 1e-6

@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -447,7 +448,8 @@ int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, co
     P.single = g->prog.single;
     P.coef = g->coef;
     if (g->prog.single) P.atom = g->prog.atoms[g->prog.terms[0].fac[0].atom];
-    CF_CUDA(g->entry->grad(P, dim3(pl.row_tiles, pl.chunks), stream));
+    const int gslot = (g->prog.single && P.atom.v.kind == CF_ATOM_EQ) ? 0 : 1;
+    CF_CUDA(g->entry->grad[gslot](P, dim3(pl.row_tiles, pl.chunks), stream));
     g->last_launches++;
     const int blocks = (int)std::min<int64_t>((nrows * d + 255) / 256, 8192);
     grad_reduce_partials<<<blocks, 256, 0, stream>>>((const double*)sh.partial.p, pl.chunks, nrows, D, d, d_y, d_yin, 0, alpha, beta);

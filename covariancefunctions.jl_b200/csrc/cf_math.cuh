@@ -105,9 +105,47 @@ __device__ __forceinline__ double cf_atom_matern(double r2, const cf_atom_val& A
     for (int i = p - 1; i >= 0; i--) mp = fma(mp, g, A.mat[i]);
     return mp * e;
 }
+// N pairs at once: every stage (sqrt, exp, Horner step) is issued for all N values before the next one, so the N
+// dependent chains interleave and the runtime loop over p costs one branch per N values
+template <int N>
+__device__ __forceinline__ void cf_atom_matern_n(const double (&r2)[N], const cf_atom_val& A, cf_tbl_t tbl_lane, double (&out)[N]) {
+    double g[N], e[N];
+#pragma unroll
+    for (int u = 0; u < N; u++) g[u] = cf_clamp_v(cf_sqrt_pos(r2[u]), A.e);
+#pragma unroll
+    for (int u = 0; u < N; u++) e[u] = cf_exp_cv(g[u], A.e, tbl_lane);
+    const int p = A.p;
+    if (p == 0) {
+#pragma unroll
+        for (int u = 0; u < N; u++) out[u] = e[u];
+        return;
+    }
+    double mp[N];
+#pragma unroll
+    for (int u = 0; u < N; u++) mp[u] = A.mat[p];
+    for (int i = p - 1; i >= 0; i--) {
+        const double ci = A.mat[i];
+#pragma unroll
+        for (int u = 0; u < N; u++) mp[u] = fma(mp[u], g[u], ci);
+    }
+#pragma unroll
+    for (int u = 0; u < N; u++) out[u] = mp[u] * e[u];
+}
 __device__ __forceinline__ double cf_atom_rq_int(double r2, const cf_atom_val& A) {
     double base = fma(r2, A.w, 1.0);
     return cf_powi(cf_rcp(base), A.p);
+}
+template <int N>
+__device__ __forceinline__ void cf_atom_rq_int_n(const double (&r2)[N], const cf_atom_val& A, double (&out)[N]) {
+    double ib[N];
+#pragma unroll
+    for (int u = 0; u < N; u++) ib[u] = cf_rcp(fma(r2[u], A.w, 1.0));
+#pragma unroll
+    for (int u = 0; u < N; u++) out[u] = ib[u];
+    for (int i = 1; i < A.p; i++) {
+#pragma unroll
+        for (int u = 0; u < N; u++) out[u] *= ib[u];
+    }
 }
 // pow() is a large routine: keep one out-of-line copy per kernel instead of one per call site (instruction cache)
 static __device__ __noinline__ double cf_pow_outlined(double base, double e) { return pow(base, e); }
@@ -146,12 +184,10 @@ __device__ __forceinline__ void cf_atom_value_dyn_n(const double (&r2)[N], const
             for (int u = 0; u < N; u++) out[u] = cf_atom_eq(r2[u], A, tbl_lane);
             break;
         case CF_ATOM_MATERN:
-#pragma unroll
-            for (int u = 0; u < N; u++) out[u] = cf_atom_matern(r2[u], A, tbl_lane);
+            cf_atom_matern_n<N>(r2, A, tbl_lane, out);
             break;
         case CF_ATOM_RQ_INT:
-#pragma unroll
-            for (int u = 0; u < N; u++) out[u] = cf_atom_rq_int(r2[u], A);
+            cf_atom_rq_int_n<N>(r2, A, out);
             break;
         case CF_ATOM_RQ_REAL:
 #pragma unroll
@@ -242,6 +278,18 @@ __device__ __forceinline__ void cf_atom_jet(double r2, const cf_atom& A, cf_tbl_
             return;
         }
         default: k = k1 = k2 = 0.0 / 0.0; return; // LINE is not isotropic
+    }
+}
+
+// compile-time specialised jets for the common single-atom gradient kernels (no switch, no inlined dead paths)
+template <int KIND>
+__device__ __forceinline__ void cf_atom_jet_t(double r2, const cf_atom& A, cf_tbl_t tbl_lane, double& k, double& k1, double& k2) {
+    if constexpr (KIND == CF_ATOM_EQ) {
+        k = cf_exp_cv(r2, A.v.e, tbl_lane);
+        k1 = A.v.e.c * k;
+        k2 = A.v.e.c * k1;
+    } else {
+        cf_atom_jet(r2, A, tbl_lane, k, k1, k2);
     }
 }
 

@@ -18,7 +18,7 @@ struct cf_kernel_entry {
     int D;
     cf_mvm_launch_fn mvm[2][CF_NKINDS]; // [dtype][kind slot]
     cf_mvm_config mvm_cfg[2];
-    cf_grad_launch_fn grad;
+    cf_grad_launch_fn grad[2];  // [0]: EQ specialised, [1]: generic isotropic (single atom or sum of products)
     cf_mvm_config grad_cfg;
     cf_mm_launch_fn mm[2]; // [dtype]
 };
@@ -32,7 +32,7 @@ template <int D> struct cf_tune {
     static constexpr int MINB = (D <= 8) ? 2 : 1;
     // gradient kernel
     static constexpr int GR = (D <= 4) ? 2 : 1;
-    static constexpr int GNT = (D <= 16) ? 256 : 128;
+    static constexpr int GNT = (D <= 8) ? 256 : 128;
     static constexpr int GTJ = (D <= 8) ? 128 : (D <= 16 ? 64 : 32);
     static constexpr int GMINB = (D <= 6) ? 2 : 1;
 };

@@ -35,7 +35,7 @@ struct cf_grad_smem {
     static constexpr int total = tbl_bytes + bar_bytes + NS * stage_bytes;
 };
 
-template <int D, int R, int NT, int TJ, int NS, int MINB>
+template <int D, int KIND, int R, int NT, int TJ, int NS, int MINB>
 __global__ void __launch_bounds__(NT, MINB) grad_mvm_kernel(const __grid_constant__ cf_grad_params P) {
     using S = cf_grad_smem<D, TJ, NS>;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -80,24 +80,35 @@ __global__ void __launch_bounds__(NT, MINB) grad_mvm_kernel(const __grid_constan
 
     auto compute = [&](const double* __restrict__ ys, const double* __restrict__ as, int cnt) {
         for (int j = 0; j < cnt; j++) {
-            double yj[D], aj[D];
-#pragma unroll
-            for (int c = 0; c < D; c++) { yj[c] = ys[j * D + c]; aj[c] = as[j * D + c]; }
+            const double* __restrict__ yj = ys + j * D;
+            const double* __restrict__ aj = as + j * D;
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                double rr[D], r2 = 0, dra = 0;
+                // r2 and r.a with NP independent partial sums each (FP64 latency would otherwise serialise 2 D FMAs)
+                constexpr int NP = (D >= 8) ? 4 : ((D >= 2) ? 2 : 1);
+                double r2p[NP], drp[NP];
+#pragma unroll
+                for (int q = 0; q < NP; q++) { r2p[q] = 0.0; drp[q] = 0.0; }
+                double rr[D];
 #pragma unroll
                 for (int c = 0; c < D; c++) {
-                    rr[c] = x[r][c] - yj[c];
-                    r2 = (c == 0) ? rr[c] * rr[c] : fma(rr[c], rr[c], r2);
-                    dra = (c == 0) ? rr[c] * aj[c] : fma(rr[c], aj[c], dra);
+                    const double df = x[r][c] - yj[c];
+                    rr[c] = df;
+                    r2p[c % NP] = fma(df, df, r2p[c % NP]);
+                    drp[c % NP] = fma(df, aj[c], drp[c % NP]);
                 }
+                double r2 = r2p[0], dra = drp[0];
+#pragma unroll
+                for (int q = 1; q < NP; q++) { r2 += r2p[q]; dra += drp[q]; }
                 double k, k1, k2;
-                if (P.single) cf_atom_jet(r2, P.atom, tbl_lane, k, k1, k2);
+                if constexpr (KIND == CF_ATOM_EQ) cf_atom_jet_t<CF_ATOM_EQ>(r2, P.atom, tbl_lane, k, k1, k2);
+                else if (P.single) cf_atom_jet(r2, P.atom, tbl_lane, k, k1, k2);
                 else cf_sop_jet(r2, P.sop, tbl_lane, k, k1, k2);
                 const double ca = -2.0 * k1, cr = -4.0 * k2 * dra;
 #pragma unroll
-                for (int c = 0; c < D; c++) b[r][c] = fma(cr, rr[c], fma(ca, aj[c], b[r][c]));
+                for (int c = 0; c < D; c++) {
+                    b[r][c] = fma(cr, rr[c], fma(ca, aj[c], b[r][c]));
+                }
             }
         }
     };
@@ -160,10 +171,10 @@ __global__ void cf_pad_points(const T* __restrict__ src, int64_t lds, int d, T* 
 
 typedef cudaError_t (*cf_grad_launch_fn)(const cf_grad_params& P, dim3 grid, cudaStream_t stream);
 
-template <int D, int R, int NT, int TJ, int NS, int MINB>
+template <int D, int KIND, int R, int NT, int TJ, int NS, int MINB>
 cudaError_t cf_grad_launch(const cf_grad_params& P, dim3 grid, cudaStream_t stream) {
     using S = cf_grad_smem<D, TJ, NS>;
-    auto kern = grad_mvm_kernel<D, R, NT, TJ, NS, MINB>;
+    auto kern = grad_mvm_kernel<D, KIND, R, NT, TJ, NS, MINB>;
     static bool configured[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);

@@ -99,6 +99,8 @@ __device__ __forceinline__ void cf_rows_value(const T (&x)[R][D], const T (&yj)[
     }
     if constexpr (sizeof(T) == 8) {
         if constexpr (KIND == CF_ATOM_SOP) cf_sop_value_n<R>(r2, dt, P.sop, tbl_lane, kv);
+        else if constexpr (KIND == CF_ATOM_MATERN) cf_atom_matern_n<R>(r2, P.atom, tbl_lane, kv);
+        else if constexpr (KIND == CF_ATOM_RQ_INT) cf_atom_rq_int_n<R>(r2, P.atom, kv);
         else {
 #pragma unroll
             for (int r = 0; r < R; r++) kv[r] = cf_atom_value<KIND>(r2[r], dt[r], P.atom, tbl_lane);

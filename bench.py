@@ -321,7 +321,10 @@ def main():
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     roofline = {
         "bound": "fp64_fma_pipe", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
-        "frac": achieved_tflops / peak_tflops, "traffic": None,
+        "frac": achieved_tflops / peak_tflops,
+        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture at this workload
+        # (profiles/r1_ncu_mvm_eq_c2_n1048576.md): 33.90 MB + 0.76 MB per launch; only known for the 1-GPU c2 shape
+        "traffic": 34653184 if (args.config == "c2" and world == 1) else None,
         "kernel_ms": kernel_ms, "flops_per_pair": 2 * slots,
         "peak_source": "cf_peak_probe DFMA microbenchmark in this run (MEASURED_PEAKS.json has no FP64 entry); "
                        "nominal 64 DFMA/clk/SM x 148 SMs x 1.965 GHz = 37.2 TFLOP/s",

@@ -70,6 +70,8 @@ SYMBOLS = {
     "cf_gramian_getindex": (_int, [_vp, _i64, _i64, C.POINTER(_dbl)]),
     "cf_gradient_mul": (_int, [_vp, _vp, _i64, _vp, _i64, _i64, _dbl, _dbl]),
     "cf_gradient_mul_device": (_int, [_vp, _vp, _i64, _vp, _i64, _i64, _dbl, _dbl, _vp]),
+    "cf_value_gradient_mul": (_int, [_vp, _vp, _i64, _vp, _i64, _i64, _dbl, _dbl]),
+    "cf_value_gradient_mul_device": (_int, [_vp, _vp, _i64, _vp, _i64, _i64, _dbl, _dbl, _vp]),
     "cf_cg_solve": (_int, [_vp, _dbl, _vp, _vp, _dbl, _int, _int, C.POINTER(_int), C.POINTER(_dbl)]),
     "cf_last_timing": (_int, [_vp, C.POINTER(C.c_float), C.POINTER(_int)]),
     "cf_peak_probe": (_int, [_int, _int, C.POINTER(_dbl), C.POINTER(C.c_float)]),

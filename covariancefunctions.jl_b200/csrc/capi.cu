@@ -118,7 +118,8 @@ struct cf_gramian_s {
     cf_sop_grad sop_grad;  // ... for the gradient kernel (valid when grad_ok)
     bool grad_ok = false;
     int kind = CF_ATOM_SOP; // kernel kind used for the value MVM
-    double coef = 1.0;      // leading constant when prog.single
+    double coef = 1.0;      // leading constant when prog.single (value kernels fold it into alpha)
+    double coef_grad = 1.0; // the same constant for the derivative kernels (always the term's coefficient)
     const cf_kernel_entry* entry = nullptr;
     std::vector<Shard> shards;
     std::mutex mu;
@@ -230,15 +231,17 @@ int launch_mm(cf_gramian_s* g, Shard& sh, void* d_B, int64_t ldb, const void* d_
 int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const void* d_a, double alpha, double beta,
                cudaStream_t stream);
 int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, const double* d_a, double alpha, double beta,
-                cudaStream_t stream);
+                cudaStream_t stream, int vg);
 
 // conjugate gradients on (sigma2 I + K) x = b; restates IterativeSolvers.cg! 0.9.2 [upstream] behind
 // ldiv!(x, ::LazyMatrixSum, b) (reference src/lazy_linear_algebra.jl:126-144).  State lives on shard 0; with several shards
 // the search direction is broadcast to every device and the row blocks of K u are gathered back once per iteration
 // (peer copies over NVLink).
-int cg_solve_impl(cf_gramian_s* g, double sigma2, double* x, const double* b, double reltol, int maxiter, bool gradient,
+int cg_solve_impl(cf_gramian_s* g, double sigma2, double* x, const double* b, double reltol, int maxiter, int deriv,
                   int* iters, double* resnorm) {
-    const int64_t blk = gradient ? g->d : 1;
+    const bool gradient = deriv != 0;
+    const int vg = deriv == 2 ? 1 : 0;
+    const int64_t blk = deriv == 0 ? 1 : g->d + vg;
     const int64_t N = g->n * blk;
     if (reltol <= 0) reltol = std::sqrt(2.220446049250313e-16);
     if (maxiter <= 0) maxiter = (int)std::min<int64_t>(N, 2147483647);
@@ -262,7 +265,7 @@ int cg_solve_impl(cf_gramian_s* g, double sigma2, double* x, const double* b, do
         cf_axpby_kernel<<<vb, 256, 0, st>>>(out, sigma2, v, 0.0, v, N);
         CF_CUDA(cudaGetLastError());
         if (g->shards.size() == 1) {
-            return gradient ? launch_grad(g, s0, out, out, v, 1.0, 1.0, st) : launch_mvm(g, s0, out, out, v, 1.0, 1.0, st);
+            return gradient ? launch_grad(g, s0, out, out, v, 1.0, 1.0, st, vg) : launch_mvm(g, s0, out, out, v, 1.0, 1.0, st);
         }
         CF_CUDA(cudaStreamSynchronize(st));
         for (size_t q = 0; q < g->shards.size(); q++) {
@@ -273,7 +276,7 @@ int cg_solve_impl(cf_gramian_s* g, double sigma2, double* x, const double* b, do
             if (int rc = sh.y.ensure(std::max<size_t>(16, (size_t)srows * 8))) return rc;
             CF_CUDA(cudaMemcpyPeerAsync(sh.a.p, sh.ctx->dev, v, s0.ctx->dev, N * 8, sh.stream));
             if (srows == 0) continue;
-            int rc = gradient ? launch_grad(g, sh, (double*)sh.y.p, nullptr, (const double*)sh.a.p, 1.0, 0.0, sh.stream)
+            int rc = gradient ? launch_grad(g, sh, (double*)sh.y.p, nullptr, (const double*)sh.a.p, 1.0, 0.0, sh.stream, vg)
                               : launch_mvm(g, sh, sh.y.p, nullptr, sh.a.p, 1.0, 0.0, sh.stream);
             if (rc) return rc;
             // gather this row block next to the sigma2 term (scratch: cg[4] is b, so use shard-0 partial-free buffer)
@@ -414,45 +417,56 @@ int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const v
     return CF_OK;
 }
 
-// gradient operator, one right-hand side, device pointers (unpadded flat vectors)
+// derivative operators, one right-hand side, device pointers (unpadded flat vectors with blocks of d + vg entries):
+// vg = 0 GradientKernel, vg = 1 ValueGradientKernel (entry 0 of every block is the value part)
 int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, const double* d_a, double alpha, double beta,
-                cudaStream_t stream) {
+                cudaStream_t stream, int vg) {
     const int64_t nrows = sh.r1 - sh.r0;
     if (nrows <= 0) return CF_OK;
-    const int d = g->d, D = g->D;
+    const int d = g->d, D = g->D, bs = d + vg;
     if (g->m == 0) {
-        launch_scale(CF_F64, d_y, d_yin, nrows * d, beta, stream);
+        launch_scale(CF_F64, d_y, d_yin, nrows * bs, beta, stream);
         return CF_OK;
     }
-    const cf_mvm_config& cfg = g->entry->grad_cfg;
+    const cf_mvm_config& cfg = g->entry->grad_cfg[vg];
     Plan pl = make_plan(nrows, g->m, cfg, sh.ctx->sms);
     const double* a_use = d_a;
-    if (D != d || (((uintptr_t)d_a) % 16) != 0) {
-        int rc = sh.apad.ensure((size_t)g->m * D * sizeof(double));
+    const double* a0_use = nullptr;
+    if (vg || D != d || (((uintptr_t)d_a) % 16) != 0) {
+        int rc = sh.apad.ensure((size_t)g->m * (D + 1) * sizeof(double));
         if (rc) return rc;
         const int blocks = (int)std::min<int64_t>((g->m * D + 255) / 256, 8192);
-        cf_pad_points<double><<<blocks, 256, 0, stream>>>(d_a, d, d, (double*)sh.apad.p, D, g->m);
+        cf_pad_points<double><<<blocks, 256, 0, stream>>>(d_a + vg, bs, d, (double*)sh.apad.p, D, g->m);
         CF_CUDA(cudaGetLastError());
         g->last_launches++;
         a_use = (const double*)sh.apad.p;
+        if (vg) {
+            double* a0 = (double*)sh.apad.p + (size_t)g->m * D;
+            cf_pad_points<double><<<(int)std::min<int64_t>((g->m + 255) / 256, 8192), 256, 0, stream>>>(d_a, bs, 1, a0, 1, g->m);
+            CF_CUDA(cudaGetLastError());
+            g->last_launches++;
+            a0_use = a0;
+        }
     }
-    int rc = sh.partial.ensure((size_t)pl.chunks * nrows * D * sizeof(double));
+    int rc = sh.partial.ensure((size_t)pl.chunks * nrows * (D + 1) * sizeof(double));
     if (rc) return rc;
     cf_grad_params P;
     std::memset(&P, 0, sizeof(P));
-    P.X = (const double*)sh.X; P.Y = (const double*)sh.Y; P.a = a_use;
+    P.X = (const double*)sh.X; P.Y = (const double*)sh.Y; P.a = a_use; P.a0 = a0_use;
     P.partial = (double*)sh.partial.p;
+    P.partial0 = (double*)sh.partial.p + (size_t)pl.chunks * nrows * D;
     P.exp2_tbl = sh.ctx->exp2_tbl;
     P.sop = g->sop_grad;
     P.row0 = sh.r0; P.nrows = nrows; P.m = g->m; P.cols_per_chunk = pl.cols_per_chunk;
     P.single = g->prog.single;
-    P.coef = g->coef;
+    P.coef = g->coef_grad;
     if (g->prog.single) P.atom = g->prog.atoms[g->prog.terms[0].fac[0].atom];
-    const int gslot = (g->prog.single && P.atom.v.kind == CF_ATOM_EQ) ? 0 : 1;
-    CF_CUDA(g->entry->grad[gslot](P, dim3(pl.row_tiles, pl.chunks), stream));
+    const int variant = g->prog.dotproduct ? 2 : ((g->prog.single && P.atom.v.kind == CF_ATOM_EQ) ? 0 : 1);
+    CF_CUDA(g->entry->grad[vg][variant](P, dim3(pl.row_tiles, pl.chunks), stream));
     g->last_launches++;
-    const int blocks = (int)std::min<int64_t>((nrows * d + 255) / 256, 8192);
-    grad_reduce_partials<<<blocks, 256, 0, stream>>>((const double*)sh.partial.p, pl.chunks, nrows, D, d, d_y, d_yin, 0, alpha, beta);
+    const int blocks = (int)std::min<int64_t>((nrows * bs + 255) / 256, 8192);
+    grad_reduce_partials<<<blocks, 256, 0, stream>>>((const double*)sh.partial.p, P.partial0, pl.chunks, nrows, D, d, vg, d_y, d_yin,
+                                                     alpha, beta);
     CF_CUDA(cudaGetLastError());
     g->last_launches++;
     return CF_OK;
@@ -571,6 +585,7 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
     if (lowered.single) {
         const cf_atom& A = lowered.atoms[lowered.terms[0].fac[0].atom];
         g->coef = lowered.terms[0].coef;
+        g->coef_grad = lowered.terms[0].coef;
         g->kind = (A.v.kind == CF_ATOM_EQ || A.v.kind == CF_ATOM_MATERN || A.v.kind == CF_ATOM_RQ_INT) ? A.v.kind : CF_ATOM_SOP;
         if (g->kind == CF_ATOM_SOP) g->coef = 1.0; // generic path applies the coefficient itself
     } else {
@@ -669,22 +684,29 @@ int cf_gramian_set_row_range(cf_gramian_t g, int64_t row_begin, int64_t row_end)
     return CF_OK;
 }
 
+static int check_derivative(cf_gramian_s* g) {
+    if (g->dtype != CF_F64) return fail(CF_ERR_UNSUPPORTED, "derivative operators: Float64 only");
+    if (!g->prog.isotropic && !g->prog.dotproduct)
+        return fail(CF_ERR_UNSUPPORTED, "derivative operators: kernel has neither the IsotropicInput nor the DotProductInput trait");
+    if (!g->grad_ok) return fail(CF_ERR_UNSUPPORTED, "derivative operators: kernel too complex (more than 4 terms or 3 base kernels)");
+    return CF_OK;
+}
+
 static int mul_host_impl(cf_gramian_t g, void* y, int64_t ldy, const void* x, int64_t ldx, int64_t nrhs, double alpha,
-                         double beta, bool gradient) {
+                         double beta, int deriv) {
+    const bool gradient = deriv != 0;
+    const int vg = deriv == 2 ? 1 : 0;
     if (int rc = check_handle(g)) return rc;
     if (nrhs < 0) return fail(CF_ERR_BAD_ARGUMENT, "nrhs is negative");
-    const int64_t blk = gradient ? g->d : 1;
+    const int64_t blk = deriv == 0 ? 1 : g->d + vg;
     const int64_t rows = (g->row_end - g->row_begin) * blk, cols = g->m * blk;
     if (nrhs == 0 || rows == 0) return CF_OK;
     if (!y || (!x && cols > 0)) return fail(CF_ERR_BAD_ARGUMENT, "NULL vector pointer");
     if (nrhs > 1 && (ldy < rows || ldx < cols))
         return fail(CF_ERR_DIMENSION, "leading dimension too small: ldy = %lld (rows %lld), ldx = %lld (cols %lld)", (long long)ldy,
                     (long long)rows, (long long)ldx, (long long)cols);
-    if (gradient) {
-        if (g->dtype != CF_F64) return fail(CF_ERR_UNSUPPORTED, "gradient operator: Float64 only");
-        if (!g->prog.isotropic) return fail(CF_ERR_UNSUPPORTED, "gradient operator: kernel does not have the IsotropicInput trait");
-        if (!g->grad_ok) return fail(CF_ERR_UNSUPPORTED, "gradient operator: kernel too complex (more than 4 terms or 3 base kernels)");
-    }
+    if (gradient)
+        if (int rc = check_derivative(g)) return rc;
     if (nrhs == 1) { ldy = rows; ldx = cols; }
     std::lock_guard<std::mutex> lk(g->mu);
     const size_t es = esize(g->dtype);
@@ -710,7 +732,7 @@ static int mul_host_impl(cf_gramian_t g, void* y, int64_t ldy, const void* x, in
             for (int64_t c = 0; c < nrhs; c++) {
                 void* yc = (char*)sh.y.p + (size_t)c * srows * es;
                 const void* ac = (const char*)sh.a.p + (size_t)c * cols * es;
-                int rc = gradient ? launch_grad(g, sh, (double*)yc, (const double*)yc, (const double*)ac, alpha, beta, sh.stream)
+                int rc = gradient ? launch_grad(g, sh, (double*)yc, (const double*)yc, (const double*)ac, alpha, beta, sh.stream, vg)
                                   : launch_mvm(g, sh, yc, yc, ac, alpha, beta, sh.stream);
                 if (rc) return rc;
             }
@@ -741,27 +763,29 @@ static int mul_host_impl(cf_gramian_t g, void* y, int64_t ldy, const void* x, in
 }
 
 int cf_gramian_mul(cf_gramian_t g, void* y, int64_t ldy, const void* x, int64_t ldx, int64_t nrhs, double alpha, double beta) {
-    return mul_host_impl(g, y, ldy, x, ldx, nrhs, alpha, beta, false);
+    return mul_host_impl(g, y, ldy, x, ldx, nrhs, alpha, beta, 0);
 }
 int cf_gradient_mul(cf_gramian_t g, void* y, int64_t ldy, const void* x, int64_t ldx, int64_t nrhs, double alpha, double beta) {
-    return mul_host_impl(g, y, ldy, x, ldx, nrhs, alpha, beta, true);
+    return mul_host_impl(g, y, ldy, x, ldx, nrhs, alpha, beta, 1);
+}
+int cf_value_gradient_mul(cf_gramian_t g, void* y, int64_t ldy, const void* x, int64_t ldx, int64_t nrhs, double alpha, double beta) {
+    return mul_host_impl(g, y, ldy, x, ldx, nrhs, alpha, beta, 2);
 }
 
 static int mul_device_impl(cf_gramian_t g, void* d_y, int64_t ldy, const void* d_x, int64_t ldx, int64_t nrhs, double alpha,
-                           double beta, void* stream, bool gradient) {
+                           double beta, void* stream, int deriv) {
+    const bool gradient = deriv != 0;
+    const int vg = deriv == 2 ? 1 : 0;
     if (int rc = check_handle(g)) return rc;
     if (g->shards.size() != 1) return fail(CF_ERR_UNSUPPORTED, "device-pointer multiply needs a single-device handle");
-    const int64_t blk = gradient ? g->d : 1;
+    const int64_t blk = deriv == 0 ? 1 : g->d + vg;
     const int64_t rows = (g->row_end - g->row_begin) * blk, cols = g->m * blk;
     if (nrhs <= 0 || rows == 0) return CF_OK;
     if (!d_y || (!d_x && cols > 0)) return fail(CF_ERR_BAD_ARGUMENT, "NULL device pointer");
     if (nrhs == 1) { ldy = rows; ldx = cols; }
     if (ldy < rows || ldx < cols) return fail(CF_ERR_DIMENSION, "leading dimension too small");
-    if (gradient) {
-        if (g->dtype != CF_F64) return fail(CF_ERR_UNSUPPORTED, "gradient operator: Float64 only");
-        if (!g->prog.isotropic) return fail(CF_ERR_UNSUPPORTED, "gradient operator: kernel does not have the IsotropicInput trait");
-        if (!g->grad_ok) return fail(CF_ERR_UNSUPPORTED, "gradient operator: kernel too complex (more than 4 terms or 3 base kernels)");
-    }
+    if (gradient)
+        if (int rc = check_derivative(g)) return rc;
     std::lock_guard<std::mutex> lk(g->mu);
     Shard& sh = g->shards[0];
     CF_CUDA(cudaSetDevice(sh.ctx->dev));
@@ -776,7 +800,7 @@ static int mul_device_impl(cf_gramian_t g, void* d_y, int64_t ldy, const void* d
         for (int64_t c = 0; c < nrhs; c++) {
             void* yc = (char*)d_y + (size_t)c * ldy * es;
             const void* ac = (const char*)d_x + (size_t)c * ldx * es;
-            int rc = gradient ? launch_grad(g, sh, (double*)yc, (const double*)yc, (const double*)ac, alpha, beta, st)
+            int rc = gradient ? launch_grad(g, sh, (double*)yc, (const double*)yc, (const double*)ac, alpha, beta, st, vg)
                               : launch_mvm(g, sh, yc, yc, ac, alpha, beta, st);
             if (rc) return rc;
         }
@@ -792,11 +816,15 @@ static int mul_device_impl(cf_gramian_t g, void* d_y, int64_t ldy, const void* d
 
 int cf_gramian_mul_device(cf_gramian_t g, void* d_y, int64_t ldy, const void* d_x, int64_t ldx, int64_t nrhs, double alpha,
                           double beta, void* stream) {
-    return mul_device_impl(g, d_y, ldy, d_x, ldx, nrhs, alpha, beta, stream, false);
+    return mul_device_impl(g, d_y, ldy, d_x, ldx, nrhs, alpha, beta, stream, 0);
 }
 int cf_gradient_mul_device(cf_gramian_t g, void* d_y, int64_t ldy, const void* d_x, int64_t ldx, int64_t nrhs, double alpha,
                            double beta, void* stream) {
-    return mul_device_impl(g, d_y, ldy, d_x, ldx, nrhs, alpha, beta, stream, true);
+    return mul_device_impl(g, d_y, ldy, d_x, ldx, nrhs, alpha, beta, stream, 1);
+}
+int cf_value_gradient_mul_device(cf_gramian_t g, void* d_y, int64_t ldy, const void* d_x, int64_t ldx, int64_t nrhs, double alpha,
+                                 double beta, void* stream) {
+    return mul_device_impl(g, d_y, ldy, d_x, ldx, nrhs, alpha, beta, stream, 2);
 }
 
 int cf_gramian_matrix(cf_gramian_t g, void* M, int64_t ldm) {
@@ -855,10 +883,11 @@ int cf_cg_solve(cf_gramian_t g, double sigma2, void* x, const void* b, double re
     if (g->n != g->m) return fail(CF_ERR_DIMENSION, "cf_cg_solve: Gramian is %lld x %lld, not square", (long long)g->n, (long long)g->m);
     if (g->dtype != CF_F64) return fail(CF_ERR_UNSUPPORTED, "cf_cg_solve: Float64 only");
     if (g->row_begin != 0 || g->row_end != g->n) return fail(CF_ERR_UNSUPPORTED, "cf_cg_solve: handle is restricted to a row range");
-    if (gradient && (!g->prog.isotropic || !g->grad_ok))
-        return fail(CF_ERR_UNSUPPORTED, "gradient operator: kernel does not have the IsotropicInput trait or is too complex");
+    if (gradient < 0 || gradient > 2) return fail(CF_ERR_BAD_ARGUMENT, "cf_cg_solve: gradient must be 0, 1 or 2");
+    if (gradient)
+        if (int rc = check_derivative(g)) return rc;
     std::lock_guard<std::mutex> lk(g->mu);
-    return cg_solve_impl(g, sigma2, (double*)x, (const double*)b, reltol, maxiter, gradient != 0, iters, resnorm);
+    return cg_solve_impl(g, sigma2, (double*)x, (const double*)b, reltol, maxiter, gradient, iters, resnorm);
 }
 
 int cf_last_timing(cf_gramian_t g, float* kernel_ms, int* launches) {

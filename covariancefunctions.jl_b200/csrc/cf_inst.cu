@@ -22,9 +22,14 @@ const cf_kernel_entry entry = {
      {mvm_fn<double, CF_ATOM_EQ>(), mvm_fn<double, CF_ATOM_MATERN>(), mvm_fn<double, CF_ATOM_RQ_INT>(), mvm_fn<double, CF_ATOM_SOP>()}},
     {{TU::NT * TU::R, TU::TJ, cf_mvm_smem<float, D, TU::TJ, TU::NS>::total, TU::MINB},
      {TU::NT * TU::R, TU::TJ, cf_mvm_smem<double, D, TU::TJ, TU::NS>::total, TU::MINB}},
-    {&cf_grad_launch<D, CF_ATOM_EQ, TU::GR, TU::GNT, TU::GTJ, TU::NS, TU::GMINB>,
-     &cf_grad_launch<D, CF_ATOM_SOP, TU::GR, TU::GNT, TU::GTJ, TU::NS, TU::GMINB>},
-    {TU::GNT * TU::GR, TU::GTJ, cf_grad_smem<D, TU::GTJ, TU::NS>::total, TU::GMINB},
+    {{&cf_grad_launch<D, CF_ATOM_EQ, CF_GRAD_ISO, false, TU::GR, TU::GNT, TU::GTJ, TU::NS, TU::GMINB>,
+      &cf_grad_launch<D, CF_ATOM_SOP, CF_GRAD_ISO, false, TU::GR, TU::GNT, TU::GTJ, TU::NS, TU::GMINB>,
+      &cf_grad_launch<D, CF_ATOM_SOP, CF_GRAD_DOT, false, TU::GR, TU::GNT, TU::GTJ, TU::NS, TU::GMINB>},
+     {&cf_grad_launch<D, CF_ATOM_EQ, CF_GRAD_ISO, true, TU::GR, TU::GNT, TU::GTJ, TU::NS, TU::GMINB>,
+      &cf_grad_launch<D, CF_ATOM_SOP, CF_GRAD_ISO, true, TU::GR, TU::GNT, TU::GTJ, TU::NS, TU::GMINB>,
+      &cf_grad_launch<D, CF_ATOM_SOP, CF_GRAD_DOT, true, TU::GR, TU::GNT, TU::GTJ, TU::NS, TU::GMINB>}},
+    {{TU::GNT * TU::GR, TU::GTJ, cf_grad_smem<D, TU::GTJ, TU::NS, false>::total, TU::GMINB},
+     {TU::GNT * TU::GR, TU::GTJ, cf_grad_smem<D, TU::GTJ, TU::NS, true>::total, TU::GMINB}},
     {&cf_mm_launch<float, D>, &cf_mm_launch<double, D>},
 };
 }  // namespace

@@ -316,11 +316,15 @@ inline cf_program lower(const cf_knode_t* prog, int nnodes) {
         for (size_t f = 0; f < ht.fac.size(); f++) { P.terms[t].fac[f] = ht.fac[f]; used[ht.fac[f].atom] = true; }
     }
     P.isotropic = 1;
+    P.dotproduct = 1;
+    bool any = false;
     for (int a = 0; a < P.natoms; a++) {
         if (!used[a]) continue;
+        any = true;
         if (P.atoms[a].v.kind == CF_ATOM_LINE) { P.needs_dot = 1; P.isotropic = 0; }
-        else P.needs_r2 = 1;
+        else { P.needs_r2 = 1; P.dotproduct = 0; }
     }
+    if (!any) P.dotproduct = 0; // all-constant programs count as isotropic (reference src/properties.jl:49-50)
     P.single = (P.nterms == 1 && P.terms[0].nfac == 1 && P.terms[0].fac[0].power == 1) ? 1 : 0;
     return P;
 }

@@ -277,7 +277,7 @@ __device__ __forceinline__ void cf_atom_jet(double r2, const cf_atom& A, cf_tbl_
             k2 = -(A.v.alpha + 1.0) * A.v.w * k1 * ib;
             return;
         }
-        default: k = k1 = k2 = 0.0 / 0.0; return; // LINE is not isotropic
+        default: k = r2 + A.v.sigma; k1 = 1.0; k2 = 0.0; return; // LINE: the variable is t = x.y (DotProductInput programs)
     }
 }
 

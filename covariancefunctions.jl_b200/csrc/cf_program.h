@@ -82,6 +82,7 @@ struct cf_program {
     int32_t natoms;
     int32_t needs_r2, needs_dot;
     int32_t isotropic; // every atom is a function of r2 (IsotropicInput trait, reference src/properties.jl:39-63)
+    int32_t dotproduct; // every atom is a function of x.y (DotProductInput trait)
     int32_t single;    // 1 if the program is coef * one atom ^ 1 -> specialised kernels
     cf_term terms[CF_MAX_TERMS];
     cf_atom atoms[CF_MAX_TERMS];

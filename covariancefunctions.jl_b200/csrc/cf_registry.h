@@ -18,8 +18,9 @@ struct cf_kernel_entry {
     int D;
     cf_mvm_launch_fn mvm[2][CF_NKINDS]; // [dtype][kind slot]
     cf_mvm_config mvm_cfg[2];
-    cf_grad_launch_fn grad[2];  // [0]: EQ specialised, [1]: generic isotropic (single atom or sum of products)
-    cf_mvm_config grad_cfg;
+    // gradient kernels: [value_gradient][variant]; variants: 0 = isotropic EQ specialised, 1 = isotropic generic, 2 = dot product
+    cf_grad_launch_fn grad[2][3];
+    cf_mvm_config grad_cfg[2];
     cf_mm_launch_fn mm[2]; // [dtype]
 };
 

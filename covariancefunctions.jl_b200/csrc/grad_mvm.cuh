@@ -16,28 +16,40 @@
 struct cf_grad_params {
     const double* X;   // padded AoS, stride D
     const double* Y;
-    const double* a;   // padded, m x D
+    const double* a;   // gradient weights, padded, m x D
+    const double* a0;  // value weights, m (ValueGradientKernel only)
     double* partial;   // [chunks][nrows * D]
+    double* partial0;  // [chunks][nrows]       (ValueGradientKernel only)
     const double* exp2_tbl;
     int64_t row0, nrows, m, cols_per_chunk;
     int single;
     cf_atom atom;      // single atom
-    cf_sop_grad sop;   // composite isotropic kernels (!single)
+    cf_sop_grad sop;   // composite kernels (!single)
     double coef;       // leading constant of a single-atom program
 };
 
-template <int D, int TJ, int NS>
+// MODE: which scalar the kernel is a function of (reference src/properties.jl:31-45)
+#define CF_GRAD_ISO 0  /* IsotropicInput:  t = |x - y|^2, block = -2 (k1 I + 2 k2 r r^T)      src/gradient.jl:86-92   */
+#define CF_GRAD_DOT 1  /* DotProductInput: t = x . y,     block = k1 I + k2 y x^T             src/gradient.jl:109-115 */
+
+template <int D, int TJ, int NS, bool VG>
 struct cf_grad_smem {
     static constexpr int tbl_bytes = CF_EXP_TBL_DOUBLES * 8;
     static constexpr int bar_bytes = 128;
     static constexpr int y_bytes = TJ * D * 8;
-    static constexpr int stage_bytes = 2 * y_bytes;
+    static constexpr int a0_bytes = VG ? TJ * 8 : 0;
+    static constexpr int stage_bytes = ((2 * y_bytes + a0_bytes + 127) / 128) * 128;
     static constexpr int total = tbl_bytes + bar_bytes + NS * stage_bytes;
 };
 
-template <int D, int KIND, int R, int NT, int TJ, int NS, int MINB>
+// VG = false: GradientKernel (blocks d x d);  VG = true: ValueGradientKernel (blocks (d+1) x (d+1), entry 0 = value):
+//   isotropic   [k0, (-2 k1 r)^T; 2 k1 r, GG]      dot product   [k0, (k1 x)^T; k1 y, GG]     (src/gradient.jl:442-463)
+// Both modes reduce to   b_g += ca a_g + cw w,   b_0 += k0 a_0 + cs s   with
+//   ISO: w = r = x - y, s = r.a_g, ca = -2 k1, cw = -4 k2 s + 2 k1 a_0, cs = -2 k1
+//   DOT: w = y,         s = x.a_g, ca = k1,    cw = k2 s + k1 a_0,      cs = k1
+template <int D, int KIND, int MODE, bool VG, int R, int NT, int TJ, int NS, int MINB>
 __global__ void __launch_bounds__(NT, MINB) grad_mvm_kernel(const __grid_constant__ cf_grad_params P) {
-    using S = cf_grad_smem<D, TJ, NS>;
+    using S = cf_grad_smem<D, TJ, NS, VG>;
     extern __shared__ __align__(128) unsigned char smem[];
     double* tbl = reinterpret_cast<double*>(smem);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::tbl_bytes);
@@ -60,55 +72,65 @@ __global__ void __launch_bounds__(NT, MINB) grad_mvm_kernel(const __grid_constan
         const int s = tile % NS;
         unsigned char* st = stages + (size_t)s * S::stage_bytes;
         const int64_t j0 = c0 + (int64_t)tile * TJ;
-        cf_mbar_expect_tx(&bars[s], (uint32_t)(2 * S::y_bytes));
+        cf_mbar_expect_tx(&bars[s], (uint32_t)(2 * S::y_bytes + S::a0_bytes));
         cf_tma_load_1d(st, P.Y + j0 * D, (uint32_t)S::y_bytes, &bars[s]);
         cf_tma_load_1d(st + S::y_bytes, P.a + j0 * D, (uint32_t)S::y_bytes, &bars[s]);
+        if (VG) cf_tma_load_1d(st + 2 * S::y_bytes, P.a0 + j0, (uint32_t)S::a0_bytes, &bars[s]);
     };
     if (tid == 0)
         for (int t = 0; t < NS && t < nfull; t++) issue(t);
 
-    double x[R][D], b[R][D];
+    double x[R][D], b[R][D], b0[R];
     const int64_t rbase = P.row0 + (int64_t)blockIdx.x * (NT * R);
     const int64_t rend = P.row0 + P.nrows;
 #pragma unroll
     for (int r = 0; r < R; r++) {
         int64_t i = rbase + (int64_t)r * NT + tid;
         if (i >= rend) i = rend - 1;
+        b0[r] = 0.0;
 #pragma unroll
         for (int c = 0; c < D; c++) { x[r][c] = P.X[i * D + c]; b[r][c] = 0.0; }
     }
 
-    auto compute = [&](const double* __restrict__ ys, const double* __restrict__ as, int cnt) {
+    auto compute = [&](const double* __restrict__ ys, const double* __restrict__ as, const double* __restrict__ a0s, int cnt) {
         for (int j = 0; j < cnt; j++) {
             const double* __restrict__ yj = ys + j * D;
             const double* __restrict__ aj = as + j * D;
+            const double a0 = VG ? a0s[j] : 0.0;
 #pragma unroll
             for (int r = 0; r < R; r++) {
-                // r2 and r.a with NP independent partial sums each (FP64 latency would otherwise serialise 2 D FMAs)
+                // t and s with NP independent partial sums each (FP64 latency would otherwise serialise 2 D FMAs)
                 constexpr int NP = (D >= 8) ? 4 : ((D >= 2) ? 2 : 1);
-                double r2p[NP], drp[NP];
+                double tp[NP], sp[NP];
 #pragma unroll
-                for (int q = 0; q < NP; q++) { r2p[q] = 0.0; drp[q] = 0.0; }
-                double rr[D];
+                for (int q = 0; q < NP; q++) { tp[q] = 0.0; sp[q] = 0.0; }
+                double w[D];
 #pragma unroll
                 for (int c = 0; c < D; c++) {
-                    const double df = x[r][c] - yj[c];
-                    rr[c] = df;
-                    r2p[c % NP] = fma(df, df, r2p[c % NP]);
-                    drp[c % NP] = fma(df, aj[c], drp[c % NP]);
+                    if (MODE == CF_GRAD_ISO) {
+                        const double df = x[r][c] - yj[c];
+                        w[c] = df;
+                        tp[c % NP] = fma(df, df, tp[c % NP]);
+                        sp[c % NP] = fma(df, aj[c], sp[c % NP]);
+                    } else {
+                        w[c] = yj[c];
+                        tp[c % NP] = fma(x[r][c], yj[c], tp[c % NP]);
+                        sp[c % NP] = fma(x[r][c], aj[c], sp[c % NP]);
+                    }
                 }
-                double r2 = r2p[0], dra = drp[0];
+                double t = tp[0], sdot = sp[0];
 #pragma unroll
-                for (int q = 1; q < NP; q++) { r2 += r2p[q]; dra += drp[q]; }
+                for (int q = 1; q < NP; q++) { t += tp[q]; sdot += sp[q]; }
                 double k, k1, k2;
-                if constexpr (KIND == CF_ATOM_EQ) cf_atom_jet_t<CF_ATOM_EQ>(r2, P.atom, tbl_lane, k, k1, k2);
-                else if (P.single) cf_atom_jet(r2, P.atom, tbl_lane, k, k1, k2);
-                else cf_sop_jet(r2, P.sop, tbl_lane, k, k1, k2);
-                const double ca = -2.0 * k1, cr = -4.0 * k2 * dra;
+                if constexpr (KIND == CF_ATOM_EQ) cf_atom_jet_t<CF_ATOM_EQ>(t, P.atom, tbl_lane, k, k1, k2);
+                else if (P.single) cf_atom_jet(t, P.atom, tbl_lane, k, k1, k2);
+                else cf_sop_jet(t, P.sop, tbl_lane, k, k1, k2);
+                double ca, cw, cs;
+                if (MODE == CF_GRAD_ISO) { ca = -2.0 * k1; cs = ca; cw = fma(-4.0 * k2, sdot, VG ? 2.0 * k1 * a0 : 0.0); }
+                else { ca = k1; cs = k1; cw = fma(k2, sdot, VG ? k1 * a0 : 0.0); }
 #pragma unroll
-                for (int c = 0; c < D; c++) {
-                    b[r][c] = fma(cr, rr[c], fma(ca, aj[c], b[r][c]));
-                }
+                for (int c = 0; c < D; c++) b[r][c] = fma(cw, w[c], fma(ca, aj[c], b[r][c]));
+                if (VG) b0[r] = fma(k, a0, fma(cs, sdot, b0[r]));
             }
         }
     };
@@ -117,7 +139,8 @@ __global__ void __launch_bounds__(NT, MINB) grad_mvm_kernel(const __grid_constan
         const int s = t % NS;
         cf_mbar_wait(&bars[s], (uint32_t)((t / NS) & 1));
         const unsigned char* st = stages + (size_t)s * S::stage_bytes;
-        compute(reinterpret_cast<const double*>(st), reinterpret_cast<const double*>(st + S::y_bytes), TJ);
+        compute(reinterpret_cast<const double*>(st), reinterpret_cast<const double*>(st + S::y_bytes),
+                reinterpret_cast<const double*>(st + 2 * S::y_bytes), TJ);
         __syncthreads();
         if (tid == 0 && t + NS < nfull) issue(t + NS);
     }
@@ -125,10 +148,12 @@ __global__ void __launch_bounds__(NT, MINB) grad_mvm_kernel(const __grid_constan
         const int cnt = (int)((c1 - j0 < TJ) ? c1 - j0 : TJ);
         double* ys = reinterpret_cast<double*>(stages);
         double* as = reinterpret_cast<double*>(stages + S::y_bytes);
+        double* a0s = reinterpret_cast<double*>(stages + 2 * S::y_bytes);
         __syncthreads();
         for (int q = tid; q < cnt * D; q += NT) { ys[q] = P.Y[j0 * D + q]; as[q] = P.a[j0 * D + q]; }
+        if (VG) for (int q = tid; q < cnt; q += NT) a0s[q] = P.a0[j0 + q];
         __syncthreads();
-        compute(ys, as, cnt);
+        compute(ys, as, a0s, cnt);
     }
 
     const double coef = P.single ? P.coef : 1.0;
@@ -139,19 +164,27 @@ __global__ void __launch_bounds__(NT, MINB) grad_mvm_kernel(const __grid_constan
             double* o = P.partial + ((int64_t)blockIdx.y * P.nrows + (i - P.row0)) * D;
 #pragma unroll
             for (int c = 0; c < D; c++) o[c] = coef * b[r][c];
+            if (VG) P.partial0[(int64_t)blockIdx.y * P.nrows + (i - P.row0)] = coef * b0[r];
         }
     }
 }
 
-// y[i*d + c] = alpha * sum_s partial[s][i*D + c] + beta * y[i*d + c]   (reference src/gramian.jl:245)
-static __global__ void grad_reduce_partials(const double* __restrict__ partial, int chunks, int64_t nrows, int D, int d,
-                                     double* __restrict__ y, const double* __restrict__ yin, int64_t ldy_unused, double alpha, double beta) {
-    const int64_t total = nrows * d;
+// y[i*bs + e] = alpha * sum_s partial[...] + beta * y[i*bs + e], bs = d + vg; entry 0 of a ValueGradient block is the
+// value part (reference src/gramian.jl:245 for the beta handling)
+static __global__ void grad_reduce_partials(const double* __restrict__ partial, const double* __restrict__ partial0, int chunks,
+                                            int64_t nrows, int D, int d, int vg, double* __restrict__ y,
+                                            const double* __restrict__ yin, double alpha, double beta) {
+    const int bs = d + vg;
+    const int64_t total = nrows * bs;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t i = q / d;
-        const int c = (int)(q - i * d);
+        const int64_t i = q / bs;
+        const int e = (int)(q - i * bs);
         double s = 0.0;
-        for (int ch = 0; ch < chunks; ch++) s += partial[((int64_t)ch * nrows + i) * D + c];
+        if (vg && e == 0) {
+            for (int ch = 0; ch < chunks; ch++) s += partial0[(int64_t)ch * nrows + i];
+        } else {
+            for (int ch = 0; ch < chunks; ch++) s += partial[((int64_t)ch * nrows + i) * D + (e - vg)];
+        }
         double v = alpha * s;
         if (beta != 0.0) v += beta * yin[q];
         y[q] = v;
@@ -171,10 +204,10 @@ __global__ void cf_pad_points(const T* __restrict__ src, int64_t lds, int d, T* 
 
 typedef cudaError_t (*cf_grad_launch_fn)(const cf_grad_params& P, dim3 grid, cudaStream_t stream);
 
-template <int D, int KIND, int R, int NT, int TJ, int NS, int MINB>
+template <int D, int KIND, int MODE, bool VG, int R, int NT, int TJ, int NS, int MINB>
 cudaError_t cf_grad_launch(const cf_grad_params& P, dim3 grid, cudaStream_t stream) {
-    using S = cf_grad_smem<D, TJ, NS>;
-    auto kern = grad_mvm_kernel<D, KIND, R, NT, TJ, NS, MINB>;
+    using S = cf_grad_smem<D, TJ, NS, VG>;
+    auto kern = grad_mvm_kernel<D, KIND, MODE, VG, R, NT, TJ, NS, MINB>;
     static bool configured[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);

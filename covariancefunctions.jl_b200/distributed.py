@@ -95,7 +95,7 @@ def cg(op: ShardedOperator, b: torch.Tensor, x0: torch.Tensor | None = None, rel
 def gpu_local_mul(G):
     """local_mul for a covfn_b200 Gramian restricted to this rank's row block (device tensors, current stream)."""
     r0, r1 = G.row_range
-    blk = G.d if G.is_gradient else 1
+    blk = G.block
 
     def f(u: torch.Tensor) -> torch.Tensor:
         out = torch.empty((r1 - r0) * blk, dtype=u.dtype, device=u.device)

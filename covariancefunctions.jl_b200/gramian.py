@@ -14,7 +14,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import CF_F32, CF_F64, DimensionMismatch, KNode, UnsupportedKernel, check, lib
-from .kernels import AbstractKernel, Dot, GradientKernel, IsotropicInput
+from .kernels import AbstractKernel, Dot, DotProductInput, GradientKernel, IsotropicInput
 
 
 def _points(x, dtype=None):
@@ -57,6 +57,7 @@ class Gramian:
                 f"inputs have to have the same length: {self.x.shape[1]}, {self.y.shape[1]}")  # src/util.jl:41
         self.dtype = self.x.dtype  # gramian_eltype: promote(eltype(k), coordinate types) (src/gramian.jl:30-33)
         self.is_gradient = isinstance(k, GradientKernel)
+        self.block = (self.x.shape[1] + k.block_extra) if self.is_gradient else 1  # BlockFactorization block size
         self._handle = None
         self._rows = None
 
@@ -67,7 +68,7 @@ class Gramian:
 
     @property
     def shape(self):
-        b = self.d if self.is_gradient else 1  # BlockFactorization size (d n) x (d m) (test/gradient.jl:35)
+        b = self.block  # BlockFactorization size (d n) x (d m) (test/gradient.jl:35), (d+1) for ValueGradientKernel
         return (self.x.shape[0] * b, self.y.shape[0] * b)
 
     def size(self, i=None):
@@ -156,7 +157,7 @@ class Gramian:
     def __matmul__(self, a):  # *(G, a) / *(G, A) (src/gramian.jl:66-75)
         a = np.asarray(a)
         r0, r1 = self.row_range
-        rows = (r1 - r0) * (self.d if self.is_gradient else 1)
+        rows = (r1 - r0) * self.block
         dt = np.promote_types(self.dtype, a.dtype) if a.dtype.kind == "f" else self.dtype
         if a.ndim == 1:
             b = np.zeros(rows, dtype=dt)
@@ -180,7 +181,9 @@ class Gramian:
 
     # ---- device-resident multiply (torch tensors or raw pointers) ------------------------------------------------
     def mul_device(self, y_ptr: int, x_ptr: int, nrhs: int = 1, ldy: int = 0, ldx: int = 0, alpha=1.0, beta=0.0, stream: int = 0):
-        fn = lib().cf_gradient_mul_device if self.is_gradient else lib().cf_gramian_mul_device
+        fn = lib().cf_gramian_mul_device
+        if self.is_gradient:
+            fn = lib().cf_value_gradient_mul_device if self.k.block_extra else lib().cf_gradient_mul_device
         check(fn(self.handle(), C.c_void_p(y_ptr), ldy, C.c_void_p(x_ptr), ldx, nrhs, float(alpha), float(beta),
                  C.c_void_p(stream) if stream else None))
 
@@ -214,7 +217,7 @@ def mul_(y, G, x, alpha=1, beta=0):
     if y.ndim != x.ndim or y.ndim not in (1, 2):
         raise DimensionMismatch("y and x must both be vectors or both be matrices")
     r0, r1 = G.row_range
-    blk = G.d if G.is_gradient else 1
+    blk = G.block
     rows, cols = (r1 - r0) * blk, G.shape[1]
     if y.shape[0] != rows or x.shape[0] != cols:
         raise DimensionMismatch(
@@ -234,9 +237,12 @@ def mul_(y, G, x, alpha=1, beta=0):
         xc = np.asfortranarray(xc)
         ywork = y if y.flags.f_contiguous else np.asfortranarray(y)
         ldy, ldx = max(rows, 1), max(cols, 1)
-    fn = lib().cf_gradient_mul if G.is_gradient else lib().cf_gramian_mul
-    if G.is_gradient and G.k.input_trait() != IsotropicInput():
-        raise UnsupportedKernel("GradientKernel MVM is lowered for IsotropicInput kernels only (src/gradient.jl:83-92)")
+    fn = lib().cf_gramian_mul
+    if G.is_gradient:
+        fn = lib().cf_value_gradient_mul if G.k.block_extra else lib().cf_gradient_mul
+        if G.k.input_trait() not in (IsotropicInput(), DotProductInput()):
+            raise UnsupportedKernel("derivative-kernel MVMs are lowered for IsotropicInput and DotProductInput kernels only "
+                                    "(src/gradient.jl:83-115); GenericInput kernels use the reference's dense fallback")
     check(fn(G.handle(), ywork.ctypes.data_as(C.c_void_p), ldy, xc.ctypes.data_as(C.c_void_p), ldx, nrhs,
              float(alpha), float(beta)))
     if ywork is not y:
@@ -306,7 +312,7 @@ class LazyMatrixSum:
         x = np.zeros(N) if x0 is None else np.array(x0, dtype=np.float64, copy=True)
         iters, res = C.c_int(), C.c_double()
         check(lib().cf_cg_solve(G.handle(), self.D.sigma2, x.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
-                                float(reltol), int(maxiter), int(G.is_gradient), C.byref(iters), C.byref(res)))
+                                float(reltol), int(maxiter), (1 + G.k.block_extra) if G.is_gradient else 0, C.byref(iters), C.byref(res)))
         return x, iters.value, res.value
 
 

@@ -400,11 +400,14 @@ class Power(AbstractKernel):
 
 class GradientKernel:
     """GradientKernel(k) (gradient.jl:7-24): the d x d matrix-valued kernel of gradient observations.  Captures
-    input_trait(k) at construction; only IsotropicInput is lowered to the device (gradient.jl:83-92)."""
+    input_trait(k) at construction; the IsotropicInput and DotProductInput elements are lowered to the device
+    (gradient.jl:83-92, 107-115); GenericInput kernels are not (dense ForwardDiff fallback in the reference)."""
+
+    block_extra = 0  # block size is d + block_extra
 
     def __init__(self, k):
         if not isinstance(k, AbstractKernel):
-            raise TypeError("GradientKernel(k::AbstractKernel)")
+            raise TypeError(f"{type(self).__name__}(k::AbstractKernel)")
         self.k = k
         self._trait = input_trait(k)
 
@@ -416,3 +419,13 @@ class GradientKernel:
 
     def __repr__(self):
         return f"GradientKernel({self.k!r})"
+
+
+class ValueGradientKernel(GradientKernel):
+    """ValueGradientKernel(k) (gradient.jl:400-474): (d+1) x (d+1) blocks covering the value and its gradient;
+    entry 0 of every block is the value observation (DerivativeKernelElement, gradient.jl:217-239)."""
+
+    block_extra = 1
+
+    def __repr__(self):
+        return f"ValueGradientKernel({self.k!r})"

@@ -133,20 +133,30 @@ int cf_gramian_matrix(cf_gramian_t g, void* M, int64_t ldm);
 /* single entry, replaces getindex(G, i, j) (reference src/gramian.jl:37-40); 0-based i, j */
 int cf_gramian_getindex(cf_gramian_t g, int64_t i, int64_t j, double* out);
 
-/* ---- isotropic GradientKernel ----------------------------------------------------------- */
+/* ---- derivative kernels: GradientKernel and ValueGradientKernel -------------------------------------- */
 /*
- * y <- alpha * G * x + beta * y for G = gramian(GradientKernel(k), X[, Y]), the (n d) x (m d) operator
- * whose d x d block (i, j) is  -2 (k' I + 2 k'' r r^T),  r = x_i - y_j, k', k'' derivatives of k
- * with respect to r^2.  Replaces blockmul!(y, G::Gramian, x, alpha, beta) (reference
- * src/gramian.jl:241-253) with the IsotropicGradientKernelElement mul! (reference
- * src/gradient.jl:86-92) and derivative_laplacian (src/gradient.jl:589-600).
- * The handle's program must have the IsotropicInput trait (reference src/properties.jl:39-63).
- * x: (m d) x nrhs, y: (n d) x nrhs, flat index i*d + c.  HOST pointers.
+ * y <- alpha * G * x + beta * y for G = gramian(GradientKernel(k), X[, Y]), the (n d) x (m d) operator whose d x d
+ * block (i, j) is
+ *     -2 (k' I + 2 k'' r r^T),  r = x_i - y_j,  k', k'' derivatives of k in r^2   (IsotropicInput kernels)
+ *     k' I + k'' y_j x_i^T,     k', k'' derivatives of k in t = x_i . y_j         (DotProductInput kernels)
+ * Replaces blockmul!(y, G::Gramian, x, alpha, beta) (reference src/gramian.jl:241-253) with the lazy
+ * IsotropicGradientKernelElement / DotProductGradientKernelElement mul! (reference src/gradient.jl:86-92, 109-115) and
+ * derivative_laplacian (src/gradient.jl:589-600).  The handle's program must have the IsotropicInput or the
+ * DotProductInput trait (reference src/properties.jl:39-63).
+ * x: (m d) x nrhs, y: (n d) x nrhs, flat index i*d + c.  HOST pointers.  Float64 only.
  */
 int cf_gradient_mul(cf_gramian_t g, void* y, int64_t ldy, const void* x, int64_t ldx, int64_t nrhs,
                     double alpha, double beta);
 int cf_gradient_mul_device(cf_gramian_t g, void* d_y, int64_t ldy, const void* d_x, int64_t ldx,
                            int64_t nrhs, double alpha, double beta, void* stream);
+/*
+ * The same for G = gramian(ValueGradientKernel(k), X[, Y]): (d+1) x (d+1) blocks [vv vg; gv gg] with entry 0 the value
+ * observation (reference src/gradient.jl:400-474, DerivativeKernelElement :217-239): flat index i*(d+1) + e.
+ */
+int cf_value_gradient_mul(cf_gramian_t g, void* y, int64_t ldy, const void* x, int64_t ldx, int64_t nrhs,
+                          double alpha, double beta);
+int cf_value_gradient_mul_device(cf_gramian_t g, void* d_y, int64_t ldy, const void* d_x, int64_t ldx,
+                                 int64_t nrhs, double alpha, double beta, void* stream);
 
 /* ---- chained MVMs: conjugate gradients on (K + sigma2 I) x = b -------------------------- */
 /*
@@ -155,7 +165,8 @@ int cf_gradient_mul_device(cf_gramian_t g, void* d_y, int64_t ldy, const void* d
  * on entry (an initial residual MVM is always done, as cg! does) and the solution on exit.
  * reltol <= 0 selects sqrt(eps(T)); maxiter <= 0 selects n.  Iterates stay on the device(s); with
  * several devices each owns a row block and the search direction is re-assembled once per iteration.
- * gradient != 0 solves with the GradientKernel operator instead (reference src/gramian.jl:229-238).
+ * gradient = 1 solves with the GradientKernel operator instead, gradient = 2 with the ValueGradientKernel operator
+ * (reference src/gramian.jl:229-238).
  */
 int cf_cg_solve(cf_gramian_t g, double sigma2, void* x, const void* b, double reltol, int maxiter,
                 int gradient, int* iters, double* resnorm);

@@ -464,6 +464,8 @@ static jet kernel_jet(const orc_knode_t* prog, int nnodes, double r2v) {
             for (int w = t + nls; w > t; w--) r2 = j_scale(r2, 1.0 / (prog[w].fparam * prog[w].fparam));
             st[sp++] = jet_iso_leaf(nd, r2);
             t += nls;
+        } else if (nd->op == OP_DOT) {
+            st[sp++] = j_var(r2v); /* DotProductInput programs: the variable is x.y, (k::Dot)(d) = d (mercer.jl:9) */
         } else if (nd->op == OP_CONST) {
             st[sp++] = j_const(nd->fparam);
         } else if (nd->op == OP_SUM || nd->op == OP_PROD) {
@@ -475,7 +477,7 @@ static jet kernel_jet(const orc_knode_t* prog, int nnodes, double r2v) {
         } else if (nd->op == OP_POW) {
             st[sp - 1] = j_powi(st[sp - 1], nd->iparam);
         } else {
-            return j_const(NAN); /* DOT: not isotropic */
+            return j_const(NAN);
         }
     }
     return st[0];
@@ -517,6 +519,90 @@ void orc_gradient_mul(const orc_knode_t* prog, int nnodes, int d, int64_t n, con
             for (int c = 0; c < d; c++) b[c] = alpha * (-2 * (k1 * a[c] + 2 * k2 * r[c] * dot_r_a)) + 1.0 * b[c];
         }
     }
+}
+
+/*
+ * Generalised block multiply for the derivative kernels on the path:
+ *   trait 0 = IsotropicInput  (variable r2 = |x - y|^2):  gradient element  src/gradient.jl:86-92
+ *   trait 1 = DotProductInput (variable t = x . y):       gradient element  src/gradient.jl:109-115
+ *                                                          b = alpha (k1 a + k2 y (x . a)) + beta b
+ *   vg = 0: GradientKernel, blocks d x d;  vg = 1: ValueGradientKernel, blocks (d+1) x (d+1), entry 0 = value
+ *           (DerivativeKernelElement [vv vg; gv gg], src/gradient.jl:217-239; value_gradient_kernel! :442-463:
+ *            isotropic: vv = k0, vg = -2 k1 r, gv = 2 k1 r;  dot product: vv = k0, vg = k1 x, gv = k1 y)
+ * blockmul! loop structure as in src/gramian.jl:241-253.  Float64.
+ */
+void orc_derivative_mul(const orc_knode_t* prog, int nnodes, int d, int trait, int vg, int64_t n, const double* X, int64_t ldx,
+                        int64_t m, const double* Y, int64_t ldy, int64_t i0, int64_t i1, double* y, const double* x,
+                        double alpha, double beta) {
+    (void)n;
+    const int bs = d + (vg ? 1 : 0);
+#pragma omp parallel for schedule(static)
+    for (int64_t i = i0; i < i1; i++) {
+        const double* xi = X + ldx * i;
+        double* b = y + (i - i0) * bs;
+        double r[d > 0 ? d : 1], t[bs > 0 ? bs : 1];
+        for (int c = 0; c < bs; c++) b[c] = (beta == 0) ? 0.0 : beta * b[c];
+        for (int64_t j = 0; j < m; j++) {
+            const double* yj = Y + ldy * j;
+            const double* a = x + j * bs;
+            const double* ag = a + (vg ? 1 : 0);
+            double var = 0;
+            if (trait == 0) { for (int c = 0; c < d; c++) { r[c] = xi[c] - yj[c]; var += r[c] * r[c]; } }
+            else { for (int c = 0; c < d; c++) var += xi[c] * yj[c]; }
+            jet kj = kernel_jet(prog, nnodes, var);
+            const double k0 = kj.v, k1 = kj.d1, k2 = kj.d2;
+            /* t = block * a */
+            if (trait == 0) {
+                double dra = 0;
+                for (int c = 0; c < d; c++) dra += r[c] * ag[c];
+                for (int c = 0; c < d; c++) t[c + (vg ? 1 : 0)] = -2 * (k1 * ag[c] + 2 * k2 * r[c] * dra);
+                if (vg) {
+                    double vgdot = 0;
+                    for (int c = 0; c < d; c++) vgdot += (-2 * k1 * r[c]) * ag[c];
+                    t[0] = k0 * a[0] + vgdot;
+                    for (int c = 0; c < d; c++) t[c + 1] += (2 * k1 * r[c]) * a[0];
+                }
+            } else {
+                double dxa = 0;
+                for (int c = 0; c < d; c++) dxa += xi[c] * ag[c];
+                for (int c = 0; c < d; c++) t[c + (vg ? 1 : 0)] = k1 * ag[c] + k2 * yj[c] * dxa;
+                if (vg) {
+                    double vgdot = 0;
+                    for (int c = 0; c < d; c++) vgdot += (k1 * xi[c]) * ag[c];
+                    t[0] = k0 * a[0] + vgdot;
+                    for (int c = 0; c < d; c++) t[c + 1] += (k1 * yj[c]) * a[0];
+                }
+            }
+            for (int c = 0; c < bs; c++) b[c] = alpha * t[c] + 1.0 * b[c];
+        }
+    }
+}
+
+/* dense instantiation of the same operators, column-major, ldm >= n*bs */
+void orc_derivative_matrix(const orc_knode_t* prog, int nnodes, int d, int trait, int vg, int64_t n, const double* X, int64_t ldx,
+                           int64_t m, const double* Y, int64_t ldy, double* M, int64_t ldm) {
+    const int bs = d + (vg ? 1 : 0), o = vg ? 1 : 0;
+    for (int64_t i = 0; i < n; i++)
+        for (int64_t j = 0; j < m; j++) {
+            const double* xi = X + ldx * i;
+            const double* yj = Y + ldy * j;
+            double r[d > 0 ? d : 1], var = 0;
+            if (trait == 0) { for (int c = 0; c < d; c++) { r[c] = xi[c] - yj[c]; var += r[c] * r[c]; } }
+            else { for (int c = 0; c < d; c++) var += xi[c] * yj[c]; }
+            jet kj = kernel_jet(prog, nnodes, var);
+            double* B = M + (i * bs) + ldm * (j * bs);
+            for (int c = 0; c < d; c++)
+                for (int e = 0; e < d; e++)
+                    B[(c + o) + ldm * (e + o)] = (trait == 0) ? -2 * (kj.d1 * (c == e) + 2 * kj.d2 * r[c] * r[e])
+                                                              : kj.d1 * (c == e) + kj.d2 * yj[c] * xi[e];
+            if (vg) {
+                B[0] = kj.v;
+                for (int c = 0; c < d; c++) {
+                    B[0 + ldm * (c + 1)] = (trait == 0) ? -2 * kj.d1 * r[c] : kj.d1 * xi[c]; /* value_gradient (row) */
+                    B[(c + 1) + 0] = (trait == 0) ? 2 * kj.d1 * r[c] : kj.d1 * yj[c];         /* gradient_value (column) */
+                }
+            }
+        }
 }
 
 /* dense (n d) x (m d) instantiation of the gradient Gramian: block (i,j) = -2 (k1 I + 2 k2 r r^T)

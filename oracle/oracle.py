@@ -198,3 +198,33 @@ def truth_getindex(program, x, y) -> float:
     y = np.ascontiguousarray(y, dtype=np.float64).ravel()
     pa, nn = _prog(program)
     return lib().orc_truth_getindex(pa, nn, C.c_int(x.size), _p(x), _p(y))
+
+
+def derivative_mul(program, X, a, Y=None, trait="isotropic", value_gradient=False, alpha=1.0, beta=0.0, y0=None, rows=None):
+    """blockmul! for GradientKernel / ValueGradientKernel with the isotropic or dot-product element
+    (reference src/gramian.jl:241-253, src/gradient.jl:86-92, 109-115, 442-463).  Flat vectors, blocks of d (+1)."""
+    X = _pts(X, np.float64)
+    Y = X if Y is None else _pts(Y, np.float64)
+    n, m, d = X.shape[0], Y.shape[0], X.shape[1]
+    bs = d + (1 if value_gradient else 0)
+    i0, i1 = (0, n) if rows is None else rows
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    assert a.shape == (m * bs,)
+    y = np.zeros((i1 - i0) * bs) if y0 is None else np.array(y0, dtype=np.float64, copy=True)
+    pa, nn = _prog(program)
+    lib().orc_derivative_mul(pa, nn, C.c_int(d), C.c_int(0 if trait == "isotropic" else 1), C.c_int(int(value_gradient)),
+                             _i64(n), _p(X), _i64(d), _i64(m), _p(Y), _i64(d), _i64(i0), _i64(i1), _p(y), _p(a),
+                             C.c_double(alpha), C.c_double(beta))
+    return y
+
+
+def derivative_matrix(program, X, Y=None, trait="isotropic", value_gradient=False):
+    X = _pts(X, np.float64)
+    Y = X if Y is None else _pts(Y, np.float64)
+    n, m, d = X.shape[0], Y.shape[0], X.shape[1]
+    bs = d + (1 if value_gradient else 0)
+    M = np.zeros((m * bs, n * bs))  # column-major (n bs) x (m bs)
+    pa, nn = _prog(program)
+    lib().orc_derivative_matrix(pa, nn, C.c_int(d), C.c_int(0 if trait == "isotropic" else 1), C.c_int(int(value_gradient)),
+                                _i64(n), _p(X), _i64(d), _i64(m), _p(Y), _i64(d), _p(M), _i64(n * bs))
+    return M.T

@@ -74,11 +74,80 @@ def test_gradient_config4_shape(cf, O):
     assert relerr(b[rows[0] * d:rows[1] * d], ref) < 1e-12
 
 
-def test_gradient_rejects_dot(cf):
+def test_gradient_rejects_generic_input(cf):
+    # EQ + Dot has the GenericInput trait (src/properties.jl:57-58): the reference uses a dense ForwardDiff fallback
     X = np.random.default_rng(0).standard_normal((3, 10))
-    G = cf.gramian(cf.GradientKernel(cf.Dot() ** 3), X)
+    G = cf.gramian(cf.GradientKernel(cf.EQ() + cf.Dot()), X)
     with pytest.raises(cf.UnsupportedKernel):
         G @ np.ones(30)
+
+
+DOT_KERNELS = ["Dot^3", "Dot", "Poly(3,0.5)", "Dot^2+2*Dot^3"]
+
+
+def _dot_kernel(cf, name):
+    return {"Dot^3": cf.Dot() ** 3, "Dot": cf.Dot(), "Poly(3,0.5)": cf.Poly(3, 0.5),
+            "Dot^2+2*Dot^3": cf.Dot() ** 2 + 2 * cf.Dot() ** 3}[name]
+
+
+@pytest.mark.parametrize("name", DOT_KERNELS)
+@pytest.mark.parametrize("d", [1, 5, 16])
+def test_dot_product_gradient_mvm(cf, O, name, d):
+    # DotProductGradientKernelElement (src/gradient.jl:107-115), kernels of test/gradient.jl:21
+    k = _dot_kernel(cf, name)
+    rng = np.random.default_rng(zlib.crc32(f"dot-{name}-{d}".encode()))
+    n, m = 40, 67
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    Y = rng.standard_normal((m, d)) / np.sqrt(d)
+    a = rng.standard_normal(m * d)
+    G = cf.gramian(cf.GradientKernel(k), X.T.copy(), Y.T.copy())
+    assert relerr(G @ a, O.derivative_mul(k.program(), X, a, Y=Y, trait="dot")) < 1e-12
+    alpha, beta = rng.standard_normal(2)
+    y0 = rng.standard_normal(n * d)
+    y = y0.copy()
+    cf.mul_(y, G, a, alpha, beta)
+    M = O.derivative_matrix(k.program(), X, Y, trait="dot")
+    assert relerr(y, alpha * (M @ a) + beta * y0) < 1e-12  # test/gradient.jl:47-52
+
+
+@pytest.mark.parametrize("name", ["MaternP(3)", "EQ", "RQ(1.0)", "Dot^3", "0.5*EQ+MaternP(2)"])
+@pytest.mark.parametrize("d", [2, 5, 16])
+def test_value_gradient_kernel_mvm(cf, O, name, d):
+    # ValueGradientKernel (src/gradient.jl:400-474; test/gradient.jl:87-137): (d+1) x (d+1) blocks
+    k = {"MaternP(3)": cf.MaternP(3), "EQ": cf.EQ(), "RQ(1.0)": cf.RQ(1.0), "Dot^3": cf.Dot() ** 3,
+         "0.5*EQ+MaternP(2)": 0.5 * cf.EQ() + cf.MaternP(2)}[name]
+    trait = "dot" if name.startswith("Dot") else "isotropic"
+    rng = np.random.default_rng(zlib.crc32(f"vg-{name}-{d}".encode()))
+    n = 37
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    a, b = rng.standard_normal((d + 1) * n), rng.standard_normal((d + 1) * n)
+    G = cf.gramian(cf.ValueGradientKernel(k), X.T.copy())
+    assert G.shape == ((d + 1) * n, (d + 1) * n)  # test/gradient.jl:103
+    MK = O.derivative_matrix(k.program(), X, trait=trait, value_gradient=True)
+    assert np.abs(MK - MK.T).max() < 1e4 * np.finfo(float).eps  # test/gradient.jl:96
+    alpha, beta = rng.standard_normal(2)
+    Kab = b.copy()
+    cf.mul_(Kab, G, a, alpha, beta)
+    assert relerr(Kab, alpha * (MK @ a) + beta * b) < 1e-12  # test/gradient.jl:119-123
+    assert relerr(G @ a, O.derivative_mul(k.program(), X, a, trait=trait, value_gradient=True)) < 1e-12
+    # rectangular
+    Y = rng.standard_normal((53, d)) / np.sqrt(d)
+    a2 = rng.standard_normal(53 * (d + 1))
+    G2 = cf.gramian(cf.ValueGradientKernel(k), X.T.copy(), Y.T.copy())
+    assert relerr(G2 @ a2, O.derivative_mul(k.program(), X, a2, Y=Y, trait=trait, value_gradient=True)) < 1e-12
+
+
+def test_value_gradient_solve(cf, O):
+    # test/gradient.jl:127-136: K \ (K a) residual < 1e-6 for EQ and RQ(1.)
+    rng = np.random.default_rng(77)
+    n, d = 12, 3
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    for k in (cf.EQ(), cf.RQ(1.0)):
+        G = cf.gramian(cf.ValueGradientKernel(k), X.T.copy())
+        a = rng.standard_normal(n * (d + 1))
+        Ka = G @ a
+        x, iters, res = (1e-10 * cf.I(n * (d + 1)) + G).solve(Ka, reltol=1e-10, maxiter=5000)
+        assert np.linalg.norm((G @ x) - Ka) / np.linalg.norm(Ka) < 1e-6
 
 
 def test_cg_solve(cf, O):

@@ -9,7 +9,7 @@ Public surface (mirrors the reference, /root/reference/src/CovarianceFunctions.j
 """
 from ._lib import (CovFnError, CudaError, DimensionMismatch, DomainError, UnsupportedKernel, device_count, init, lib,
                    LIB_PATH, SYMBOLS)
-from .kernels import (EQ, RQ, AbstractKernel, Constant, Dot, DotProductInput, Exp, Exponential, ExponentiatedQuadratic,
+from .kernels import (ARD, EQ, RQ, AbstractKernel, Constant, Dot, DotProductInput, Exp, Exponential, ExponentiatedQuadratic,
                       GenericInput, GradientKernel, IsotropicInput, IsotropicKernel, Lengthscale, Line, Matern, MaternP,
                       Poly, Polynomial, Power, Product, RationalQuadratic, Sum, ValueGradientKernel, input_trait)
 from .gramian import Diagonal, Gramian, I, LazyMatrixSum, gramian, mul_, peak_probe

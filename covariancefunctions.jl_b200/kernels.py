@@ -429,3 +429,34 @@ class ValueGradientKernel(GradientKernel):
 
     def __repr__(self):
         return f"ValueGradientKernel({self.k!r})"
+
+
+class ARD:
+    """ARD(k, l::AbstractVector) (transformation.jl:42-45): Normed(k, tau -> sum(tau_c^2 / l_c)).  Lowered by pre-scaling
+    the points with 1/sqrt(l_c) when the Gramian is built -- the reference itself pre-transforms the data for its
+    input-scaling kernels (transformation.jl:83-95) -- after which the isotropic kernel k runs unchanged.
+    ARD(k, l::Real) is Lengthscale(k, l) (transformation.jl:46)."""
+
+    def __new__(cls, k, l):
+        if np.ndim(l) == 0:
+            return Lengthscale(k, l)
+        return super().__new__(cls)
+
+    def __init__(self, k, l):
+        if not isinstance(k, IsotropicKernel):
+            raise TypeError("ARD(k::IsotropicKernel, l)")
+        l = np.asarray(l, dtype=np.float64)
+        if not np.all(l > 0):
+            raise DomainError(f"l = {l} is non-positive")
+        self.k, self.l = k, l
+
+    def __call__(self, x, y):
+        x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+        tau = x - y
+        return self.k._of_scalar(float(np.sum(tau * tau / self.l)))
+
+    def scale(self):
+        return 1.0 / np.sqrt(self.l)
+
+    def __repr__(self):
+        return f"ARD({self.k!r}, {self.l.tolist()})"

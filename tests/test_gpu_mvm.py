@@ -206,3 +206,19 @@ def test_row_range(cf, O):
         G = cf.gramian(k, X.T.copy()).set_row_range(n * r // 3, n * (r + 1) // 3)
         parts.append(G @ a)
     assert np.array_equal(np.concatenate(parts), full)  # sharding does not change a single bit
+
+
+def test_ard_lengthscales(cf):
+    # ARD(k, l) = Normed(k, tau -> sum(tau^2 / l)) (src/transformation.jl:42-45, test/stationary.jl:132-154)
+    rng = np.random.default_rng(17)
+    n, m, d = 60, 45, 3
+    X, Y = rng.standard_normal((n, d)), rng.standard_normal((m, d))
+    a = rng.standard_normal(m)
+    l = np.exp(rng.standard_normal(d))
+    for k in (cf.EQ(), cf.MaternP(2), cf.RQ(2)):
+        kard = cf.ARD(k, l)
+        G = cf.gramian(kard, X.T.copy(), Y.T.copy())
+        M = np.array([[kard(X[i], Y[j]) for j in range(m)] for i in range(n)])
+        assert relerr(G @ a, M @ a) < 1e-12
+        assert relerr(G.Matrix(), M) < 1e-13
+    assert isinstance(cf.ARD(cf.EQ(), 2.0), cf.Lengthscale)  # ARD(k, l::Real) = Lengthscale(k, l)

@@ -64,6 +64,7 @@ SYMBOLS = {
     "cf_gramian_destroy": (_int, [_vp]),
     "cf_gramian_size": (_int, [_vp, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_int), C.POINTER(_int)]),
     "cf_gramian_set_row_range": (_int, [_vp, _i64, _i64]),
+    "cf_gramian_set_option": (_int, [_vp, _int, _int]),
     "cf_gramian_mul": (_int, [_vp, _vp, _i64, _vp, _i64, _i64, _dbl, _dbl]),
     "cf_gramian_mul_device": (_int, [_vp, _vp, _i64, _vp, _i64, _i64, _dbl, _dbl, _vp]),
     "cf_gramian_matrix": (_int, [_vp, _vp, _i64]),

@@ -101,7 +101,8 @@ struct Shard {
     void* Y = nullptr;  // m x D (== X when symmetric)
     void* xn = nullptr;  // squared norms of the padded points (multi-RHS kernel)
     void* yn = nullptr;
-    Buf a, y, partial, apad, ypad, at, cg[6];
+    Buf a, y, partial, apad, ypad, at, cg[6], sym_items, bsym;
+    int sym_nitems = 0;
     int64_t r0 = 0, r1 = 0; // rows owned
 };
 
@@ -123,6 +124,7 @@ struct cf_gramian_s {
     const cf_kernel_entry* entry = nullptr;
     std::vector<Shard> shards;
     std::mutex mu;
+    bool opt_symmetric = false; // use the symmetric variant (each unordered pair evaluated once) when applicable
     float last_ms = 0;
     int last_launches = 0;
 };
@@ -369,6 +371,59 @@ int peak_probe_impl(int kind, int iters, double* lane_ops_per_s, float* ms_out) 
     return CF_OK;
 }
 
+// symmetric variant (gram_mvm_sym.cuh): diagonal row blocks with the plain kernel, everything beyond them once
+int launch_mvm_sym(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, const double* d_a, double alpha, double beta,
+                   cudaStream_t stream) {
+    const int64_t n = g->n;
+    const cf_mvm_config& cfg = g->entry->mvm_cfg[CF_F64];
+    const int64_t TR = cfg.rows_per_cta, TJ = cfg.tj;
+    const int64_t T = (n + TR - 1) / TR;
+    if (sh.sym_nitems == 0) { // build the (row tile, column chunk) list once per handle
+        int64_t ch = ((T * n / 2 / 8192) / TJ) * TJ;
+        if (ch < TJ) ch = TJ;
+        std::vector<cf_sym_item> items;
+        for (int64_t I = 0; I < T; I++)
+            for (int64_t c0 = (I + 1) * TR; c0 < n; c0 += ch) {
+                cf_sym_item it;
+                it.col0 = c0; it.col1 = std::min(n, c0 + ch); it.row_tile = (int32_t)I; it.pad_ = 0;
+                items.push_back(it);
+            }
+        if (int rc = sh.sym_items.ensure(std::max<size_t>(16, items.size() * sizeof(cf_sym_item)))) return rc;
+        if (!items.empty())
+            CF_CUDA(cudaMemcpyAsync(sh.sym_items.p, items.data(), items.size() * sizeof(cf_sym_item), cudaMemcpyHostToDevice, stream));
+        CF_CUDA(cudaStreamSynchronize(stream)); // items is a host temporary
+        sh.sym_nitems = (int)items.size();
+    }
+    if (int rc = sh.bsym.ensure((size_t)n * 8)) return rc;
+    if (int rc = sh.partial.ensure((size_t)n * 8)) return rc;
+    CF_CUDA(cudaMemsetAsync(sh.bsym.p, 0, (size_t)n * 8, stream));
+    // 1. diagonal blocks: plain kernel, each CTA sweeps only its own row block, raw sums into partial[0][*]
+    cf_mvm_params P;
+    std::memset(&P, 0, sizeof(P));
+    P.X = sh.X; P.Y = sh.X; P.a = d_a; P.out = sh.partial.p;
+    P.exp2_tbl = sh.ctx->exp2_tbl; P.sop = g->sop_val;
+    P.row0 = 0; P.nrows = n; P.m = n; P.cols_per_chunk = ((n + TJ - 1) / TJ) * TJ;
+    P.alpha = 1.0; P.beta = 0.0; P.direct = 0; P.use_tma = 1; P.diag_block = TR;
+    if (g->prog.single) P.atom = g->prog.atoms[g->prog.terms[0].fac[0].atom].v;
+    CF_CUDA(g->entry->mvm[CF_F64][cf_kind_slot(g->kind)](P, dim3((unsigned)T, 1), stream));
+    // 2. everything beyond the diagonal blocks, each unordered pair once
+    if (sh.sym_nitems > 0) {
+        cf_sym_params S;
+        std::memset(&S, 0, sizeof(S));
+        S.X = (const double*)sh.X; S.a = d_a; S.bsym = (double*)sh.bsym.p; S.exp2_tbl = sh.ctx->exp2_tbl;
+        S.items = (const cf_sym_item*)sh.sym_items.p; S.n = n; S.use_tma = 1;
+        S.atom = P.atom; S.sop = g->sop_val;
+        CF_CUDA(g->entry->sym[cf_kind_slot(g->kind)](S, sh.sym_nitems, stream));
+    }
+    // 3. y = alpha (diag + sym) + beta y
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, 4096);
+    gram_sym_combine<<<blocks, 256, 0, stream>>>((const double*)sh.partial.p, (const double*)sh.bsym.p, n, d_y, d_yin,
+                                                 alpha * g->coef, beta);
+    CF_CUDA(cudaGetLastError());
+    g->last_launches += 3;
+    return CF_OK;
+}
+
 // one column of  y <- alpha K a + beta y  on one shard; device pointers; asynchronous on sh.stream
 int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const void* d_a, double alpha, double beta,
                cudaStream_t stream) {
@@ -380,6 +435,9 @@ int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const v
         return CF_OK;
     }
     const cf_mvm_config& cfg = g->entry->mvm_cfg[dt];
+    if (g->opt_symmetric && g->symmetric && dt == CF_F64 && sh.r0 == 0 && sh.r1 == g->n && g->n >= 65536 &&
+        (((uintptr_t)d_a) % 16) == 0)
+        return launch_mvm_sym(g, sh, (double*)d_y, (const double*)d_yin, (const double*)d_a, alpha, beta, stream);
     Plan pl = make_plan(nrows, g->m, cfg, sh.ctx->sms);
     cf_mvm_params P;
     std::memset(&P, 0, sizeof(P));
@@ -510,7 +568,7 @@ int destroy_impl(cf_gramian_s* g) {
         if (sh.X) cudaFree(sh.X);
         if (sh.yn && sh.yn != sh.xn) cudaFree(sh.yn);
         if (sh.xn) cudaFree(sh.xn);
-        sh.a.release(); sh.y.release(); sh.partial.release(); sh.apad.release(); sh.ypad.release(); sh.at.release();
+        sh.a.release(); sh.y.release(); sh.partial.release(); sh.apad.release(); sh.ypad.release(); sh.at.release(); sh.sym_items.release(); sh.bsym.release();
         for (auto& b : sh.cg) b.release();
         if (sh.ev0) cudaEventDestroy(sh.ev0);
         if (sh.ev1) cudaEventDestroy(sh.ev1);
@@ -581,6 +639,7 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
     g->row_begin = 0; g->row_end = n;
     g->prog = lowered;
     g->sop_val = sop_val; g->sop_grad = sop_grad; g->grad_ok = grad_ok;
+    if (const char* e = std::getenv("COVFN_SYMMETRIC")) g->opt_symmetric = std::atoi(e) != 0;
     g->entry = entry;
     if (lowered.single) {
         const cf_atom& A = lowered.atoms[lowered.terms[0].fac[0].atom];
@@ -671,6 +730,13 @@ int cf_gramian_size(cf_gramian_t g, int64_t* n, int64_t* m, int* d, int* dtype) 
     if (d) *d = g->d;
     if (dtype) *dtype = g->dtype;
     return CF_OK;
+}
+
+int cf_gramian_set_option(cf_gramian_t g, int option, int value) {
+    if (int rc = check_handle(g)) return rc;
+    std::lock_guard<std::mutex> lk(g->mu);
+    if (option == CF_OPT_SYMMETRIC) { g->opt_symmetric = value != 0; return CF_OK; }
+    return fail(CF_ERR_BAD_ARGUMENT, "cf_gramian_set_option: unknown option %d", option);
 }
 
 int cf_gramian_set_row_range(cf_gramian_t g, int64_t row_begin, int64_t row_end) {

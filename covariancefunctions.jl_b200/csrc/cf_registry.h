@@ -3,6 +3,7 @@
 #include "gram_mvm.cuh"
 #include "grad_mvm.cuh"
 #include "cf_extra.cuh"
+#include "gram_mvm_sym.cuh"
 
 #define CF_NKINDS 4 /* EQ, MATERN, RQ_INT, SOP */
 inline int cf_kind_slot(int kind) {
@@ -22,6 +23,7 @@ struct cf_kernel_entry {
     cf_grad_launch_fn grad[2][3];
     cf_mvm_config grad_cfg[2];
     cf_mm_launch_fn mm[2]; // [dtype]
+    cf_sym_launch_fn sym[CF_NKINDS]; // Float64 symmetric variant, [kind slot]
 };
 
 // tuning per D: rows per thread R, threads NT, tile TJ, stages NS, min CTAs/SM

@@ -33,6 +33,7 @@ struct cf_mvm_params {
     double coef;          // leading constant of a single-atom program (folded into alpha by the host when direct)
     int direct;           // 1: write alpha*sum + beta*y, 0: write the raw partial sum
     int use_tma;          // 0: a is not 16-byte aligned -> cooperative loads
+    int64_t diag_block;   // > 0: each CTA sweeps only the columns of its own row block of this size (symmetric variant)
     cf_atom_val atom;     // the single atom (specialised kinds)
     cf_sop_val sop;       // generic sum of products (KIND == CF_ATOM_SOP)
 };
@@ -80,7 +81,8 @@ struct cf_mvm_smem {
 
 // k(x_r, y_j) for the R rows of a thread ----------------------------------------------------------------------
 template <typename T, int D, int KIND, int R>
-__device__ __forceinline__ void cf_rows_value(const T (&x)[R][D], const T (&yj)[D], const cf_mvm_params& P, cf_tbl_t tbl_lane, T (&kv)[R]) {
+__device__ __forceinline__ void cf_rows_value(const T (&x)[R][D], const T (&yj)[D], const cf_atom_val& atom, const cf_sop_val& sop,
+                                              cf_tbl_t tbl_lane, T (&kv)[R]) {
     T r2[R], dt[R];
 #pragma unroll
     for (int r = 0; r < R; r++) {
@@ -98,18 +100,18 @@ __device__ __forceinline__ void cf_rows_value(const T (&x)[R][D], const T (&yj)[
         }
     }
     if constexpr (sizeof(T) == 8) {
-        if constexpr (KIND == CF_ATOM_SOP) cf_sop_value_n<R>(r2, dt, P.sop, tbl_lane, kv);
-        else if constexpr (KIND == CF_ATOM_MATERN) cf_atom_matern_n<R>(r2, P.atom, tbl_lane, kv);
-        else if constexpr (KIND == CF_ATOM_RQ_INT) cf_atom_rq_int_n<R>(r2, P.atom, kv);
+        if constexpr (KIND == CF_ATOM_SOP) cf_sop_value_n<R>(r2, dt, sop, tbl_lane, kv);
+        else if constexpr (KIND == CF_ATOM_MATERN) cf_atom_matern_n<R>(r2, atom, tbl_lane, kv);
+        else if constexpr (KIND == CF_ATOM_RQ_INT) cf_atom_rq_int_n<R>(r2, atom, kv);
         else {
 #pragma unroll
-            for (int r = 0; r < R; r++) kv[r] = cf_atom_value<KIND>(r2[r], dt[r], P.atom, tbl_lane);
+            for (int r = 0; r < R; r++) kv[r] = cf_atom_value<KIND>(r2[r], dt[r], atom, tbl_lane);
         }
     } else {
-        if constexpr (KIND == CF_ATOM_SOP) cf_sop_value_f32_n<R>(r2, dt, P.sop, kv);
+        if constexpr (KIND == CF_ATOM_SOP) cf_sop_value_f32_n<R>(r2, dt, sop, kv);
         else {
 #pragma unroll
-            for (int r = 0; r < R; r++) kv[r] = cf_atom_value_f32<KIND>(r2[r], dt[r], P.atom);
+            for (int r = 0; r < R; r++) kv[r] = cf_atom_value_f32<KIND>(r2[r], dt[r], atom);
         }
     }
 }
@@ -128,8 +130,12 @@ __global__ void __launch_bounds__(NT, MINB) gram_mvm_kernel(const __grid_constan
     const T* __restrict__ Yg = static_cast<const T*>(P.Y);
     const T* __restrict__ ag = static_cast<const T*>(P.a);
 
-    const int64_t c0 = (int64_t)blockIdx.y * P.cols_per_chunk;
-    const int64_t c1 = (c0 + P.cols_per_chunk < P.m) ? c0 + P.cols_per_chunk : P.m;
+    int64_t c0 = (int64_t)blockIdx.y * P.cols_per_chunk;
+    int64_t c1 = (c0 + P.cols_per_chunk < P.m) ? c0 + P.cols_per_chunk : P.m;
+    if (P.diag_block > 0) { // columns of this CTA's own row block only
+        c0 = ((P.row0 + (int64_t)blockIdx.x * (NT * R)) / P.diag_block) * P.diag_block;
+        c1 = (c0 + P.diag_block < P.m) ? c0 + P.diag_block : P.m;
+    }
     const int64_t ncols = c1 - c0;
     const int nfull = P.use_tma ? (int)(ncols / TJ) : 0;  // tiles streamed by TMA
     const int64_t rem0 = c0 + (int64_t)nfull * TJ;          // first column handled by cooperative loads
@@ -180,7 +186,7 @@ __global__ void __launch_bounds__(NT, MINB) gram_mvm_kernel(const __grid_constan
             for (int c = 0; c < D; c++) yj[c] = ys[j * D + c];
             const T aj = as[j];
             T kv[R];
-            cf_rows_value<T, D, KIND, R>(x, yj, P, tbl_lane, kv);
+            cf_rows_value<T, D, KIND, R>(x, yj, P.atom, P.sop, tbl_lane, kv);
 #pragma unroll
             for (int r = 0; r < R; r++) acc[r] = fma(kv[r], aj, acc[r]);
         }

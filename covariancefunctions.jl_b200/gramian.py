@@ -114,6 +114,11 @@ class Gramian:
             check(lib().cf_gramian_set_row_range(self._handle, *self._rows))
         return self
 
+    def set_symmetric(self, on: bool = True):
+        """opt in to the symmetric variant (CF_OPT_SYMMETRIC): each unordered pair evaluated once; see include/covfn_b200.h"""
+        check(lib().cf_gramian_set_option(self.handle(), 1, int(bool(on))))
+        return self
+
     @property
     def row_range(self):
         return self._rows if self._rows is not None else (0, self.x.shape[0])

@@ -111,6 +111,16 @@ int cf_gramian_size(cf_gramian_t g, int64_t* n, int64_t* m, int* d, int* dtype);
 int cf_gramian_set_row_range(cf_gramian_t g, int64_t row_begin, int64_t row_end);
 
 /*
+ * Options.  CF_OPT_SYMMETRIC (default 0, or the environment variable COVFN_SYMMETRIC at create time): for y === x,
+ * Float64, nrhs == 1, n >= 65536 and the full row range, evaluate every unordered pair {i, j} once and use it for
+ * both b_i and b_j.  Halves the kernel evaluations of a symmetric Gramian MVM; the column half is accumulated with
+ * floating-point atomics, so results match the default path to rounding but are not bit-reproducible run to run.
+ * The reference always evaluates all n*m entries (src/gramian.jl:78-87).
+ */
+#define CF_OPT_SYMMETRIC 1
+int cf_gramian_set_option(cf_gramian_t g, int option, int value);
+
+/*
  * y <- alpha * K * x + beta * y, beta == 0 overwrites y (NaN-safe).
  * nrhs == 1 replaces mul!(y::AbstractVector, G::Gramian, x::AbstractVector, alpha, beta)
  *   (reference src/gramian.jl:78-87);

@@ -107,3 +107,28 @@ def test_config5_cg_d8_n2pow19_bounded_iterations(cf, O):
     Av = A @ v
     rows = (12345, 12345 + 512)
     assert relerr(Av[rows[0]:rows[1]], sigma2 * v[rows[0]:rows[1]] + O.mul_vec(k.program(), X, v, rows=rows)) < 1e-12
+
+
+def test_symmetric_variant_matches_default(cf, O):
+    # CF_OPT_SYMMETRIC: every unordered pair once (gram_mvm_sym.cuh); equal to the default path to rounding
+    n, d = 1 << 17, 3
+    rng = _philox(0xC0F00012)
+    X = rng.standard_normal((n, d))
+    a = rng.standard_normal(n)
+    for k in (cf.EQ(), cf.MaternP(2), 0.5 * cf.RQ(2) + cf.EQ()):
+        G = cf.gramian(k, X.T)
+        b0 = G @ a
+        G.set_symmetric(True)
+        b1 = G @ a
+        assert relerr(b1, b0) < 1e-13, repr(k)
+        rows = (n - 300, n)  # the last rows: their result is almost entirely column sums
+        assert relerr(b1[rows[0]:rows[1]], O.mul_vec(k.program(), X, a, rows=rows)) < 1e-12
+        y0 = rng.standard_normal(n)
+        y = y0.copy()
+        cf.mul_(y, G, a, -0.5, 2.0)
+        assert relerr(y, -0.5 * b0 + 2.0 * y0) < 1e-13
+    # ragged n (not a multiple of any tile size)
+    n2 = 70001
+    G = cf.gramian(cf.EQ(), X[:n2].T)
+    b0 = G @ a[:n2]
+    assert relerr(G.set_symmetric(True) @ a[:n2], b0) < 1e-13

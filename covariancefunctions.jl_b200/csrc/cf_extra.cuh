@@ -304,8 +304,8 @@ cudaError_t cf_mm_launch(const cf_mm_params& P, int row_tiles, cudaStream_t stre
 
 // ---- K6: vector helpers for conjugate gradients (Float64) -------------------------------------------------------------
 // z = a x + b y
-static __global__ void cf_axpby_kernel(double* __restrict__ z, double a, const double* __restrict__ x, double b,
-                                const double* __restrict__ y, int64_t n) {
+// (no __restrict__: the CG driver updates in place, z aliases x or y)
+static __global__ void cf_axpby_kernel(double* z, double a, const double* x, double b, const double* y, int64_t n) {
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x)
         z[q] = a * x[q] + b * y[q];
 }

@@ -296,9 +296,16 @@ def main():
     XT = X.T  # d x n, column-major (columns are points): the layout of a Julia Matrix passed to gramian(k, X)
 
     def step_e2e():
-        Ge = cf.gramian(k, XT).set_row_range(r0, r1)  # create: packs + uploads X (reference: gramian(k, x) is O(1) lazy)
+        t_a = time.perf_counter()
+        Ge = cf.gramian(k, XT).set_row_range(r0, r1)  # create: uploads X (reference: gramian(k, x) is O(1) lazy)
+        Ge.handle()
+        t_b = time.perf_counter()
         cf.mul_(b_np, Ge, a_np)
+        t_c = time.perf_counter()
         Ge.close()
+        if os.environ.get("CF_BENCH_DEBUG"):
+            print(f"[e2e] create {1e3 * (t_b - t_a):.1f} ms, mul_ {1e3 * (t_c - t_b):.1f} ms, close {1e3 * (time.perf_counter() - t_c):.1f} ms",
+                  file=sys.stderr)
 
     step_e2e()
     barrier()
@@ -306,7 +313,10 @@ def main():
     e2e_steps = max(2, min(args.steps, 3))
     for _ in range(e2e_steps):
         step_e2e()
+    t_loop = time.perf_counter()
     barrier()
+    if os.environ.get("CF_BENCH_DEBUG"):
+        print(f"[e2e] loop {1e3 * (t_loop - t0):.1f} ms, barrier {1e3 * (time.perf_counter() - t_loop):.1f} ms", file=sys.stderr)
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     if dist is not None:
         tt = torch.tensor([e2e_s], device=dev, dtype=torch.float64)

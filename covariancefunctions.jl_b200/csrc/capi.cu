@@ -37,6 +37,19 @@ int fail(int code, const char* fmt, ...) {
         if (e__ != cudaSuccess) return fail(CF_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__)); \
     } while (0)
 
+// Handle-owned device memory comes from the device's stream-ordered pool (cudaMallocAsync) with the release threshold
+// raised to "never": creating and destroying Gramian handles (one per mul! in the end-to-end path) then costs no
+// cudaMalloc / cudaFree, whose implicit device synchronisation and unmapping were measured at up to 0.7 s per destroy.
+// Allocation is followed by a synchronisation of the null stream's ordering point, so the pointer may be used on any stream.
+inline cudaError_t dev_alloc(void** p, size_t bytes) {
+    cudaError_t e = cudaMallocAsync(p, bytes, (cudaStream_t)0);
+    if (e != cudaSuccess) return e;
+    return cudaStreamSynchronize((cudaStream_t)0);
+}
+inline void dev_free(void* p) {
+    if (p) cudaFreeAsync(p, (cudaStream_t)0);
+}
+
 // ---- devices --------------------------------------------------------------------------------------------
 struct DeviceCtx {
     int dev = -1;
@@ -59,6 +72,12 @@ int get_ctx(int dev, DeviceCtx** out) {
     if (prop.major < 10)
         return fail(CF_ERR_CUDA, "device %d is sm_%d%d; this library contains sm_100a code only", dev, prop.major, prop.minor);
     c.sms = prop.multiProcessorCount;
+    {
+        cudaMemPool_t pool;
+        CF_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+        unsigned long long keep = ~0ull; // keep freed blocks cached in the pool
+        CF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     double tbl[CF_EXP_TBL];
     for (int j = 0; j < CF_EXP_TBL; j++) tbl[j] = (double)exp2l((long double)j / CF_EXP_TBL);
     CF_CUDA(cudaMalloc(&c.exp2_tbl, sizeof(tbl)));
@@ -83,14 +102,14 @@ struct Buf {
     size_t cap = 0;
     int ensure(size_t bytes) {
         if (bytes <= cap) return CF_OK;
-        if (p) cudaFree(p);
+        dev_free(p);
         p = nullptr;
         cap = 0;
-        CF_CUDA(cudaMalloc(&p, bytes));
+        CF_CUDA(dev_alloc(&p, bytes));
         cap = bytes;
         return CF_OK;
     }
-    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    void release() { dev_free(p); p = nullptr; cap = 0; }
 };
 
 struct Shard {
@@ -535,8 +554,8 @@ int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, co
 int upload_points(int dtype, const void* H, int64_t ld, int64_t n, int d, int D, void** dX, void** dN, Buf& scratch,
                   double* flags_dev, cudaStream_t st) {
     const size_t es = esize(dtype);
-    CF_CUDA(cudaMalloc(dX, std::max<size_t>(16, (size_t)n * D * es)));
-    CF_CUDA(cudaMalloc(dN, std::max<size_t>(16, (size_t)n * es)));
+    CF_CUDA(dev_alloc(dX, std::max<size_t>(16, (size_t)n * D * es)));
+    CF_CUDA(dev_alloc(dN, std::max<size_t>(16, (size_t)n * es)));
     if (n == 0) return CF_OK;
     // a 2-D copy of n rows of d*es bytes is processed row by row by the driver (150 ms for 2^20 points): use the 1-D form
     // whenever the host buffer is dense (ld == d), which is the layout of a Julia Matrix / vecofvec column views
@@ -564,10 +583,11 @@ int upload_points(int dtype, const void* H, int64_t ld, int64_t n, int d, int D,
 int destroy_impl(cf_gramian_s* g) {
     for (auto& sh : g->shards) {
         if (sh.ctx) cudaSetDevice(sh.ctx->dev);
-        if (sh.Y && sh.Y != sh.X) cudaFree(sh.Y);
-        if (sh.X) cudaFree(sh.X);
-        if (sh.yn && sh.yn != sh.xn) cudaFree(sh.yn);
-        if (sh.xn) cudaFree(sh.xn);
+        if (sh.stream) cudaStreamSynchronize(sh.stream); // nothing of this handle may still be running when its memory returns to the pool
+        if (sh.Y && sh.Y != sh.X) dev_free(sh.Y);
+        dev_free(sh.X);
+        if (sh.yn && sh.yn != sh.xn) dev_free(sh.yn);
+        dev_free(sh.xn);
         sh.a.release(); sh.y.release(); sh.partial.release(); sh.apad.release(); sh.ypad.release(); sh.at.release(); sh.sym_items.release(); sh.bsym.release();
         for (auto& b : sh.cg) b.release();
         if (sh.ev0) cudaEventDestroy(sh.ev0);
@@ -686,7 +706,7 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
         {
             // flags[0] = number of non-finite coordinates, flags[1] = max squared norm (as ordered bits)
             double* flags = nullptr;
-            CF_CREATE_CUDA(cudaMalloc(&flags, 16));
+            CF_CREATE_CUDA(dev_alloc((void**)&flags, 16));
             CF_CREATE_CUDA(cudaMemsetAsync(flags, 0, 16, sh.stream));
             rc = upload_points(dtype, X, ldx, n, d, g->D, &sh.X, &sh.xn, sh.apad, flags, sh.stream);
             if (!rc) {
@@ -696,7 +716,7 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
             unsigned long long hflags[2] = {0, 0};
             if (!rc && cudaMemcpyAsync(hflags, flags, 16, cudaMemcpyDeviceToHost, sh.stream) != cudaSuccess) rc = fail(CF_ERR_CUDA, "flag copy failed");
             if (!rc && cudaStreamSynchronize(sh.stream) != cudaSuccess) rc = fail(CF_ERR_CUDA, "upload failed: %s", cudaGetErrorString(cudaGetLastError()));
-            cudaFree(flags);
+            dev_free(flags);
             if (!rc && hflags[0] != 0) rc = fail(CF_ERR_NONFINITE, "%llu point coordinates are not finite (NaN or Inf)", hflags[0]);
             if (rc) { destroy_impl(g); return rc; }
             double ms;

@@ -129,6 +129,32 @@ function BlockFactorizations.blockmul!(y::AbstractVector{<:AbstractVector{T}},
     return y
 end
 
+# DotProductInput kernels use the same entry point (the library dispatches on the lowered program's trait), and
+# ValueGradientKernel blocks have d + 1 entries, entry 1 the value observation (src/gradient.jl:217-239, 400-474):
+function BlockFactorizations.blockmul!(y::AbstractVector{<:AbstractVector{T}},
+                                       G::Gramian{<:Any, <:GradientKernel{<:Any, <:Lowerable, CovarianceFunctions.DotProductInput}},
+                                       x::AbstractVector{<:AbstractVector{T}}, α::Real = 1, β::Real = 0) where {T<:Float64}
+    prog = program(G.k.k)
+    prog === nothing && return invoke(BlockFactorizations.blockmul!, Tuple{Any, Gramian, Any, Real, Real}, y, G, x, α, β)
+    yf, xf = parent(first(y)), parent(first(x))
+    h = handle(G, prog)
+    GC.@preserve yf xf check(ccall((:cf_gradient_mul, libcovfn), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Int64, Cdouble, Cdouble), h.ptr, yf, length(yf), xf, length(xf), 1, α, β))
+    return y
+end
+function BlockFactorizations.blockmul!(y::AbstractVector{<:AbstractVector{T}},
+                                       G::Gramian{<:Any, <:CovarianceFunctions.ValueGradientKernel{<:Any, <:Lowerable}},
+                                       x::AbstractVector{<:AbstractVector{T}}, α::Real = 1, β::Real = 0) where {T<:Float64}
+    prog = program(G.k.k)
+    (prog === nothing || !(input_trait(G.k) isa Union{IsotropicInput, CovarianceFunctions.DotProductInput})) &&
+        return invoke(BlockFactorizations.blockmul!, Tuple{Any, Gramian, Any, Real, Real}, y, G, x, α, β)
+    yf, xf = parent(first(y)), parent(first(x))
+    h = handle(G, prog)
+    GC.@preserve yf xf check(ccall((:cf_value_gradient_mul, libcovfn), Cint,
+        (Ptr{Cvoid}, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64, Int64, Cdouble, Cdouble), h.ptr, yf, length(yf), xf, length(xf), 1, α, β))
+    return y
+end
+
 # ---- (σ²I + K) \ b on the device (src/gramian.jl:55-60, src/lazy_linear_algebra.jl:135-144) ------------------------------------
 function solve(G::Gramian{Float64, <:Lowerable}, σ²::Real, b::Vector{Float64}; reltol = 0.0, maxiter = 0, x0 = zeros(length(b)))
     prog = program(G.k)

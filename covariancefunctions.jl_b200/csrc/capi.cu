@@ -16,6 +16,7 @@
 #include "cf_lower.h"
 #include "cf_registry.h"
 #include "cf_extra.cuh"
+#include "bigd.cuh"
 
 namespace {
 
@@ -120,7 +121,7 @@ struct Shard {
     void* Y = nullptr;  // m x D (== X when symmetric)
     void* xn = nullptr;  // squared norms of the padded points (multi-RHS kernel)
     void* yn = nullptr;
-    Buf a, y, partial, apad, ypad, at, cg[6], sym_items, bsym;
+    Buf a, y, partial, apad, ypad, at, cg[6], sym_items, bsym, bd_t, bd_s;
     int sym_nitems = 0;
     int64_t r0 = 0, r1 = 0; // rows owned
 };
@@ -390,6 +391,72 @@ int peak_probe_impl(int kind, int iters, double* lane_ops_per_s, float* ms_out) 
     return CF_OK;
 }
 
+// ---- d > 32 (bigd.cuh): row blocks sized so that the two [rows][m] scratch matrices stay <= 1 GiB each ------------------
+int64_t bigd_row_block(int64_t nrows, int64_t m) {
+    int64_t rb = ((int64_t(1) << 27) / std::max<int64_t>(m, 1) / CF_BD_T) * CF_BD_T;
+    return std::max<int64_t>(CF_BD_T, std::min<int64_t>(rb, ((nrows + CF_BD_T - 1) / CF_BD_T) * CF_BD_T));
+}
+
+int launch_bigd_mvm(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, const double* d_a, double alpha, double beta,
+                    cudaStream_t stream) {
+    const int64_t nrows = sh.r1 - sh.r0, m = g->m;
+    const int64_t rb = bigd_row_block(nrows, m);
+    if (int rc = sh.bd_t.ensure((size_t)rb * m * 8)) return rc;
+    if (int rc = sh.bd_s.ensure((size_t)rb * m * 8)) return rc;
+    for (int64_t b0 = 0; b0 < nrows; b0 += rb) {
+        const int64_t nb = std::min(rb, nrows - b0);
+        const dim3 grid((unsigned)((m + CF_BD_T - 1) / CF_BD_T), (unsigned)((nb + CF_BD_T - 1) / CF_BD_T));
+        bigd_pair_kernel<CF_GRAD_ISO, false><<<grid, 256, 0, stream>>>((const double*)sh.X, (const double*)sh.Y, nullptr, g->D,
+                                                                       sh.r0 + b0, nb, m, (double*)sh.bd_t.p, (double*)sh.bd_s.p);
+        CF_CUDA(cudaGetLastError());
+        const int blocks = (int)std::min<int64_t>(nb, 148 * 8);
+        bigd_value_kernel<<<blocks, 256, CF_EXP_TBL_DOUBLES * 8, stream>>>((const double*)sh.bd_t.p, (const double*)sh.bd_s.p, d_a, nb, m,
+                                                                           g->sop_val, sh.ctx->exp2_tbl, d_y + b0,
+                                                                           d_yin ? d_yin + b0 : nullptr, alpha, beta);
+        CF_CUDA(cudaGetLastError());
+        g->last_launches += 2;
+    }
+    return CF_OK;
+}
+
+int launch_bigd_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, const double* d_a, double alpha, double beta,
+                     cudaStream_t stream) {
+    const int64_t nrows = sh.r1 - sh.r0, m = g->m;
+    const int d = g->d, D = g->D;
+    const int64_t rb = bigd_row_block(nrows, m);
+    if (int rc = sh.bd_t.ensure((size_t)rb * m * 8)) return rc;
+    if (int rc = sh.bd_s.ensure((size_t)rb * m * 8)) return rc;
+    if (int rc = sh.apad.ensure((size_t)m * D * 8)) return rc;
+    cf_pad_points<double><<<(int)std::min<int64_t>((m * D + 255) / 256, 8192), 256, 0, stream>>>(d_a, d, d, (double*)sh.apad.p, D, m);
+    CF_CUDA(cudaGetLastError());
+    const bool dot = g->prog.dotproduct != 0;
+    for (int64_t b0 = 0; b0 < nrows; b0 += rb) {
+        const int64_t nb = std::min(rb, nrows - b0);
+        const dim3 grid((unsigned)((m + CF_BD_T - 1) / CF_BD_T), (unsigned)((nb + CF_BD_T - 1) / CF_BD_T));
+        const dim3 ugrid((unsigned)((D + CF_BD_T - 1) / CF_BD_T), (unsigned)((nb + CF_BD_T - 1) / CF_BD_T));
+        const int jb = (int)std::min<int64_t>((nb * m + 255) / 256, 148 * 16);
+        double* T = (double*)sh.bd_t.p;
+        double* S = (double*)sh.bd_s.p;
+        const double* X = (const double*)sh.X;
+        const double* Y = (const double*)sh.Y;
+        const double* A = (const double*)sh.apad.p;
+        double* out = d_y + b0 * d;
+        const double* yin = d_yin ? d_yin + b0 * d : nullptr;
+        if (dot) {
+            bigd_pair_kernel<CF_GRAD_DOT, true><<<grid, 256, 0, stream>>>(X, Y, A, D, sh.r0 + b0, nb, m, T, S);
+            bigd_jet_kernel<CF_GRAD_DOT><<<jb, 256, CF_EXP_TBL_DOUBLES * 8, stream>>>(T, S, nb * m, g->sop_grad, sh.ctx->exp2_tbl);
+            bigd_update_kernel<CF_GRAD_DOT><<<ugrid, 256, 0, stream>>>(X, Y, A, D, d, sh.r0 + b0, nb, m, T, S, out, yin, alpha, beta);
+        } else {
+            bigd_pair_kernel<CF_GRAD_ISO, true><<<grid, 256, 0, stream>>>(X, Y, A, D, sh.r0 + b0, nb, m, T, S);
+            bigd_jet_kernel<CF_GRAD_ISO><<<jb, 256, CF_EXP_TBL_DOUBLES * 8, stream>>>(T, S, nb * m, g->sop_grad, sh.ctx->exp2_tbl);
+            bigd_update_kernel<CF_GRAD_ISO><<<ugrid, 256, 0, stream>>>(X, Y, A, D, d, sh.r0 + b0, nb, m, T, S, out, yin, alpha, beta);
+        }
+        CF_CUDA(cudaGetLastError());
+        g->last_launches += 3;
+    }
+    return CF_OK;
+}
+
 // symmetric variant (gram_mvm_sym.cuh): diagonal row blocks with the plain kernel, everything beyond them once
 int launch_mvm_sym(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, const double* d_a, double alpha, double beta,
                    cudaStream_t stream) {
@@ -453,6 +520,7 @@ int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const v
         launch_scale(dt, d_y, d_yin, nrows, beta, stream);
         return CF_OK;
     }
+    if (!g->entry) return launch_bigd_mvm(g, sh, (double*)d_y, (const double*)d_yin, (const double*)d_a, alpha, beta, stream);
     const cf_mvm_config& cfg = g->entry->mvm_cfg[dt];
     if (g->opt_symmetric && g->symmetric && dt == CF_F64 && sh.r0 == 0 && sh.r1 == g->n && g->n >= 65536 &&
         (((uintptr_t)d_a) % 16) == 0)
@@ -505,6 +573,7 @@ int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, co
         launch_scale(CF_F64, d_y, d_yin, nrows * bs, beta, stream);
         return CF_OK;
     }
+    if (!g->entry) return launch_bigd_grad(g, sh, d_y, d_yin, d_a, alpha, beta, stream);
     const cf_mvm_config& cfg = g->entry->grad_cfg[vg];
     Plan pl = make_plan(nrows, g->m, cfg, sh.ctx->sms);
     const double* a_use = d_a;
@@ -588,7 +657,7 @@ int destroy_impl(cf_gramian_s* g) {
         dev_free(sh.X);
         if (sh.yn && sh.yn != sh.xn) dev_free(sh.yn);
         dev_free(sh.xn);
-        sh.a.release(); sh.y.release(); sh.partial.release(); sh.apad.release(); sh.ypad.release(); sh.at.release(); sh.sym_items.release(); sh.bsym.release();
+        sh.a.release(); sh.y.release(); sh.partial.release(); sh.apad.release(); sh.ypad.release(); sh.at.release(); sh.sym_items.release(); sh.bsym.release(); sh.bd_t.release(); sh.bd_s.release();
         for (auto& b : sh.cg) b.release();
         if (sh.ev0) cudaEventDestroy(sh.ev0);
         if (sh.ev1) cudaEventDestroy(sh.ev1);
@@ -648,13 +717,14 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
     } catch (...) {
         return fail(CF_ERR_INTERNAL, "cf_gramian_create: unexpected failure while lowering the kernel program");
     }
-    const cf_kernel_entry* entry = find_entry(d);
-    if (!entry) return fail(CF_ERR_UNSUPPORTED, "cf_gramian_create: d = %d > 32 is not supported yet", d);
+    const cf_kernel_entry* entry = find_entry(d);  // nullptr for d > 32: tiled contraction kernels (bigd.cuh), Float64 only
+    if (!entry && dtype != CF_F64) return fail(CF_ERR_UNSUPPORTED, "cf_gramian_create: d = %d > 32 is supported in Float64 only", d);
+    if (d > (1 << 20)) return fail(CF_ERR_UNSUPPORTED, "cf_gramian_create: d = %d is too large", d);
     if (cf_device_count() < 1) return fail(CF_ERR_CUDA, "cf_gramian_create: no CUDA device available (this library has no CPU path)");
 
     cf_gramian_s* g = new (std::nothrow) cf_gramian_s;
     if (!g) return fail(CF_ERR_INTERNAL, "out of host memory");
-    g->dtype = dtype; g->d = d; g->D = entry->D; g->n = n; g->m = m;
+    g->dtype = dtype; g->d = d; g->D = entry ? entry->D : ((d + CF_BD_K - 1) / CF_BD_K) * CF_BD_K; g->n = n; g->m = m;
     g->symmetric = (Y == nullptr);
     g->row_begin = 0; g->row_end = n;
     g->prog = lowered;
@@ -777,6 +847,10 @@ static int check_derivative(cf_gramian_s* g) {
     if (!g->grad_ok) return fail(CF_ERR_UNSUPPORTED, "derivative operators: kernel too complex (more than 4 terms or 3 base kernels)");
     return CF_OK;
 }
+static int check_vg_dim(cf_gramian_s* g, int deriv) {
+    if (deriv == 2 && !g->entry) return fail(CF_ERR_UNSUPPORTED, "ValueGradientKernel: d > 32 is not supported yet");
+    return CF_OK;
+}
 
 static int mul_host_impl(cf_gramian_t g, void* y, int64_t ldy, const void* x, int64_t ldx, int64_t nrhs, double alpha,
                          double beta, int deriv) {
@@ -791,8 +865,10 @@ static int mul_host_impl(cf_gramian_t g, void* y, int64_t ldy, const void* x, in
     if (nrhs > 1 && (ldy < rows || ldx < cols))
         return fail(CF_ERR_DIMENSION, "leading dimension too small: ldy = %lld (rows %lld), ldx = %lld (cols %lld)", (long long)ldy,
                     (long long)rows, (long long)ldx, (long long)cols);
-    if (gradient)
+    if (gradient) {
         if (int rc = check_derivative(g)) return rc;
+        if (int rc = check_vg_dim(g, deriv)) return rc;
+    }
     if (nrhs == 1) { ldy = rows; ldx = cols; }
     std::lock_guard<std::mutex> lk(g->mu);
     const size_t es = esize(g->dtype);
@@ -811,7 +887,7 @@ static int mul_host_impl(cf_gramian_t g, void* y, int64_t ldy, const void* x, in
             CF_CUDA(cudaMemcpy2DAsync(sh.y.p, srows * es, (const char*)y + off * es, ldy * es, srows * es, nrhs,
                                       cudaMemcpyHostToDevice, sh.stream));
         CF_CUDA(cudaEventRecord(sh.ev0, sh.stream));
-        if (!gradient && nrhs > 1) {
+        if (!gradient && nrhs > 1 && g->entry) {
             int rc = launch_mm(g, sh, sh.y.p, srows, sh.a.p, cols, nrhs, alpha, beta, sh.stream);
             if (rc) return rc;
         } else {
@@ -870,8 +946,10 @@ static int mul_device_impl(cf_gramian_t g, void* d_y, int64_t ldy, const void* d
     if (!d_y || (!d_x && cols > 0)) return fail(CF_ERR_BAD_ARGUMENT, "NULL device pointer");
     if (nrhs == 1) { ldy = rows; ldx = cols; }
     if (ldy < rows || ldx < cols) return fail(CF_ERR_DIMENSION, "leading dimension too small");
-    if (gradient)
+    if (gradient) {
         if (int rc = check_derivative(g)) return rc;
+        if (int rc = check_vg_dim(g, deriv)) return rc;
+    }
     std::lock_guard<std::mutex> lk(g->mu);
     Shard& sh = g->shards[0];
     CF_CUDA(cudaSetDevice(sh.ctx->dev));
@@ -879,7 +957,7 @@ static int mul_device_impl(cf_gramian_t g, void* d_y, int64_t ldy, const void* d
     const size_t es = esize(g->dtype);
     g->last_launches = 0;
     CF_CUDA(cudaEventRecord(sh.ev0, st));
-    if (!gradient && nrhs > 1) {
+    if (!gradient && nrhs > 1 && g->entry) {
         int rc = launch_mm(g, sh, d_y, ldy, d_x, ldx, nrhs, alpha, beta, st);
         if (rc) return rc;
     } else {
@@ -970,8 +1048,10 @@ int cf_cg_solve(cf_gramian_t g, double sigma2, void* x, const void* b, double re
     if (g->dtype != CF_F64) return fail(CF_ERR_UNSUPPORTED, "cf_cg_solve: Float64 only");
     if (g->row_begin != 0 || g->row_end != g->n) return fail(CF_ERR_UNSUPPORTED, "cf_cg_solve: handle is restricted to a row range");
     if (gradient < 0 || gradient > 2) return fail(CF_ERR_BAD_ARGUMENT, "cf_cg_solve: gradient must be 0, 1 or 2");
-    if (gradient)
+    if (gradient) {
         if (int rc = check_derivative(g)) return rc;
+        if (int rc = check_vg_dim(g, gradient)) return rc;
+    }
     std::lock_guard<std::mutex> lk(g->mu);
     return cg_solve_impl(g, sigma2, (double*)x, (const double*)b, reltol, maxiter, gradient, iters, resnorm);
 }

@@ -251,9 +251,162 @@ int launch_mm(cf_gramian_s* g, Shard& sh, void* d_B, int64_t ldb, const void* d_
 }
 
 int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const void* d_a, double alpha, double beta,
-               cudaStream_t stream);
+               cudaStream_t stream, const cf_peer_out* peers = nullptr);
 int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, const double* d_a, double alpha, double beta,
-                cudaStream_t stream, int vg);
+                cudaStream_t stream, int vg, const cf_peer_out* peers = nullptr);
+
+// Multi-GPU CG, SPMD inside one process: every device holds the full iterates and updates them redundantly (identical
+// arithmetic, so identical decisions); each device computes its row block of A u and the kernel epilogue stores the block
+// straight into every peer's copy over NVLink (cf_peer_out) -- the all-gather is fused into the producing kernel, there is no
+// staging through device 0 and no separate collective.  Cross-device ordering uses two events per device: "block written"
+// (peers wait for it before reading the assembled vector) and "vector consumed" (peers wait for it before overwriting it).
+// Returns 1 if peer access is unavailable (caller falls back to the gather-through-device-0 path).
+int cg_solve_spmd(cf_gramian_s* g, double sigma2, double* x, const double* b, double reltol, int maxiter, int deriv, int* iters,
+                  double* resnorm) {
+    const int S = (int)g->shards.size();
+    const bool gradient = deriv != 0;
+    const int vg = deriv == 2 ? 1 : 0;
+    const int64_t blk = deriv == 0 ? 1 : g->d + vg;
+    const int64_t N = g->n * blk;
+    if (S > 8 || !g->entry) return 1;
+    for (int s = 0; s < S; s++)
+        for (int t = 0; t < S; t++) {
+            if (s == t) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, g->shards[s].ctx->dev, g->shards[t].ctx->dev) != cudaSuccess || !can) return 1;
+        }
+    for (int s = 0; s < S; s++) {
+        CF_CUDA(cudaSetDevice(g->shards[s].ctx->dev));
+        for (int t = 0; t < S; t++) {
+            if (s == t) continue;
+            cudaError_t e = cudaDeviceEnablePeerAccess(g->shards[t].ctx->dev, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) { cudaGetLastError(); return 1; }
+            // handle memory comes from the stream-ordered pool: its blocks must be made peer-accessible explicitly
+            cudaMemPool_t pool;
+            cudaMemAccessDesc desc;
+            std::memset(&desc, 0, sizeof(desc));
+            desc.location.type = cudaMemLocationTypeDevice;
+            desc.location.id = g->shards[t].ctx->dev;
+            desc.flags = cudaMemAccessFlagsProtReadWrite;
+            if (cudaDeviceGetDefaultMemPool(&pool, g->shards[s].ctx->dev) != cudaSuccess ||
+                cudaMemPoolSetAccess(pool, &desc, 1) != cudaSuccess) { cudaGetLastError(); return 1; }
+        }
+    }
+    if (reltol <= 0) reltol = std::sqrt(2.220446049250313e-16);
+    if (maxiter <= 0) maxiter = (int)std::min<int64_t>(N, 2147483647);
+    std::vector<cudaEvent_t> ev_written(S), ev_consumed(S);
+    for (int s = 0; s < S; s++) {
+        Shard& sh = g->shards[s];
+        CF_CUDA(cudaSetDevice(sh.ctx->dev));
+        for (int q = 0; q < 5; q++)
+            if (int rc = sh.cg[q].ensure((size_t)N * 8)) return rc;
+        if (int rc = sh.cg[5].ensure(64)) return rc;
+        CF_CUDA(cudaEventCreateWithFlags(&ev_written[s], cudaEventDisableTiming));
+        CF_CUDA(cudaEventCreateWithFlags(&ev_consumed[s], cudaEventDisableTiming));
+        CF_CUDA(cudaMemcpyAsync(sh.cg[0].p, x, N * 8, cudaMemcpyHostToDevice, sh.stream));
+        CF_CUDA(cudaMemcpyAsync(sh.cg[4].p, b, N * 8, cudaMemcpyHostToDevice, sh.stream));
+        CF_CUDA(cudaMemsetAsync(sh.cg[2].p, 0, N * 8, sh.stream));
+    }
+    auto vec = [&](int s, int q) { return (double*)g->shards[s].cg[q].p; };
+    const int vb = (int)std::min<int64_t>((N + 255) / 256, 4096);
+    g->last_launches = 0;
+    int rc_all = CF_OK;
+
+    // out = sigma2 * in + K in on every device (out, in: indices into cg[])
+    auto apply = [&](int out, int in) -> int {
+        for (int s = 0; s < S; s++) {
+            Shard& sh = g->shards[s];
+            const int64_t off = sh.r0 * blk, cnt = (sh.r1 - sh.r0) * blk;
+            CF_CUDA(cudaSetDevice(sh.ctx->dev));
+            for (int t = 0; t < S; t++)
+                if (t != s) CF_CUDA(cudaStreamWaitEvent(sh.stream, ev_consumed[t], 0)); // peers are done reading the old `out`
+            if (cnt == 0) { CF_CUDA(cudaEventRecord(ev_written[s], sh.stream)); continue; }
+            const int sb = (int)std::min<int64_t>((cnt + 255) / 256, 4096);
+            cf_axpby_kernel<<<sb, 256, 0, sh.stream>>>(vec(s, out) + off, sigma2, vec(s, in) + off, 0.0, vec(s, in) + off, cnt);
+            CF_CUDA(cudaGetLastError());
+            cf_peer_out peers;
+            std::memset(&peers, 0, sizeof(peers));
+            for (int t = 0; t < S; t++)
+                if (t != s) peers.ptr[peers.n++] = vec(t, out) + off;
+            int rc = gradient ? launch_grad(g, sh, vec(s, out) + off, vec(s, out) + off, vec(s, in), 1.0, 1.0, sh.stream, vg, &peers)
+                              : launch_mvm(g, sh, vec(s, out) + off, vec(s, out) + off, vec(s, in), 1.0, 1.0, sh.stream, &peers);
+            if (rc) return rc;
+            CF_CUDA(cudaEventRecord(ev_written[s], sh.stream));
+        }
+        for (int s = 0; s < S; s++) {
+            CF_CUDA(cudaSetDevice(g->shards[s].ctx->dev));
+            for (int t = 0; t < S; t++)
+                if (t != s) CF_CUDA(cudaStreamWaitEvent(g->shards[s].stream, ev_written[t], 0)); // all blocks have landed here
+        }
+        return CF_OK;
+    };
+    // z = a x + b y on every device
+    auto axpby_all = [&](int z, double a_, int xq, double b_, int yq) -> int {
+        for (int s = 0; s < S; s++) {
+            CF_CUDA(cudaSetDevice(g->shards[s].ctx->dev));
+            cf_axpby_kernel<<<vb, 256, 0, g->shards[s].stream>>>(vec(s, z), a_, vec(s, xq), b_, vec(s, yq), N);
+            CF_CUDA(cudaGetLastError());
+        }
+        return CF_OK;
+    };
+    // dot product on every device (same value everywhere); the host reads device 0's copy
+    auto dot_all = [&](int xq, int yq, double* host, bool consumed_after) -> int {
+        for (int s = 0; s < S; s++) {
+            Shard& sh = g->shards[s];
+            CF_CUDA(cudaSetDevice(sh.ctx->dev));
+            cf_dot_kernel<<<1, 1024, 0, sh.stream>>>(vec(s, xq), vec(s, yq), N, (double*)sh.cg[5].p);
+            CF_CUDA(cudaGetLastError());
+            if (consumed_after) CF_CUDA(cudaEventRecord(ev_consumed[s], sh.stream));
+        }
+        Shard& s0 = g->shards[0];
+        CF_CUDA(cudaSetDevice(s0.ctx->dev));
+        CF_CUDA(cudaMemcpyAsync(host, s0.cg[5].p, 8, cudaMemcpyDeviceToHost, s0.stream));
+        CF_CUDA(cudaStreamSynchronize(s0.stream));
+        return CF_OK;
+    };
+    // cg[]: 0 = x, 1 = r, 2 = u, 3 = c, 4 = b
+    double rr = 0, residual = 0, prev_residual = 1.0;
+    int it = 0;
+    do {
+        if ((rc_all = apply(3, 0))) break;                         // c = A x
+        if ((rc_all = axpby_all(1, 1.0, 4, -1.0, 3))) break;       // r = b - c
+        if ((rc_all = dot_all(1, 1, &rr, true))) break;            // c consumed
+        residual = std::sqrt(rr);
+        const double tol = reltol * residual;
+        while (residual > tol && it < maxiter) {
+            const double beta = (residual * residual) / (prev_residual * prev_residual);
+            if ((rc_all = axpby_all(2, 1.0, 1, beta, 2))) break;   // u = r + beta u
+            if ((rc_all = apply(3, 2))) break;                     // c = A u
+            double uc = 0;
+            if ((rc_all = dot_all(2, 3, &uc, false))) break;
+            const double alpha = (residual * residual) / uc;
+            if ((rc_all = axpby_all(0, 1.0, 0, alpha, 2))) break;  // x += alpha u
+            if ((rc_all = axpby_all(1, 1.0, 1, -alpha, 3))) break; // r -= alpha c
+            prev_residual = residual;
+            if ((rc_all = dot_all(1, 1, &rr, true))) break;        // c consumed
+            residual = std::sqrt(rr);
+            it++;
+        }
+    } while (false);
+    if (!rc_all) {
+        Shard& s0 = g->shards[0];
+        cudaSetDevice(s0.ctx->dev);
+        if (cudaMemcpyAsync(x, s0.cg[0].p, N * 8, cudaMemcpyDeviceToHost, s0.stream) != cudaSuccess ||
+            cudaStreamSynchronize(s0.stream) != cudaSuccess)
+            rc_all = fail(CF_ERR_CUDA, "cg_solve: result copy failed");
+    }
+    for (int s = 0; s < S; s++) {
+        cudaSetDevice(g->shards[s].ctx->dev);
+        cudaStreamSynchronize(g->shards[s].stream);
+        cudaEventDestroy(ev_written[s]);
+        cudaEventDestroy(ev_consumed[s]);
+    }
+    if (rc_all) return rc_all;
+    if (iters) *iters = it;
+    if (resnorm) *resnorm = residual;
+    return CF_OK;
+}
 
 // conjugate gradients on (sigma2 I + K) x = b; restates IterativeSolvers.cg! 0.9.2 [upstream] behind
 // ldiv!(x, ::LazyMatrixSum, b) (reference src/lazy_linear_algebra.jl:126-144).  State lives on shard 0; with several shards
@@ -268,6 +421,10 @@ int cg_solve_impl(cf_gramian_s* g, double sigma2, double* x, const double* b, do
     if (reltol <= 0) reltol = std::sqrt(2.220446049250313e-16);
     if (maxiter <= 0) maxiter = (int)std::min<int64_t>(N, 2147483647);
     if (N == 0) { if (iters) *iters = 0; if (resnorm) *resnorm = 0; return CF_OK; }
+    if (g->shards.size() > 1) {
+        int rc = cg_solve_spmd(g, sigma2, x, b, reltol, maxiter, deriv, iters, resnorm);
+        if (rc != 1) return rc; // 1: no peer access -> gather through device 0 below
+    }
     Shard& s0 = g->shards[0];
     CF_CUDA(cudaSetDevice(s0.ctx->dev));
     for (int q = 0; q < 5; q++)
@@ -512,7 +669,10 @@ int launch_mvm_sym(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin,
 
 // one column of  y <- alpha K a + beta y  on one shard; device pointers; asynchronous on sh.stream
 int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const void* d_a, double alpha, double beta,
-               cudaStream_t stream) {
+               cudaStream_t stream, const cf_peer_out* peers) {
+    cf_peer_out no_peers;
+    std::memset(&no_peers, 0, sizeof(no_peers));
+    if (!peers) peers = &no_peers;
     const int64_t nrows = sh.r1 - sh.r0;
     if (nrows <= 0) return CF_OK;
     const int dt = g->dtype;
@@ -534,10 +694,10 @@ int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const v
     P.row0 = sh.r0; P.nrows = nrows; P.m = g->m;
     P.cols_per_chunk = pl.cols_per_chunk;
     P.alpha = alpha * g->coef; P.beta = beta;
-    P.coef = g->coef;
     P.use_tma = (((uintptr_t)d_a) % 16 == 0) ? 1 : 0;
     if (g->prog.single) P.atom = g->prog.atoms[g->prog.terms[0].fac[0].atom].v;
     P.direct = (pl.chunks == 1) ? 1 : 0;
+    P.peers = *peers;
     if (P.direct) {
         P.out = d_y; P.yin = d_yin;
     } else {
@@ -552,10 +712,10 @@ int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const v
         const int blocks = (int)std::min<int64_t>((nrows + 255) / 256, 4096);
         if (dt == CF_F64)
             gram_reduce_partials<double><<<blocks, 256, 0, stream>>>((const double*)sh.partial.p, pl.chunks, nrows, (double*)d_y,
-                                                                      (const double*)d_yin, alpha * g->coef, beta);
+                                                                      (const double*)d_yin, alpha * g->coef, beta, *peers);
         else
             gram_reduce_partials<float><<<blocks, 256, 0, stream>>>((const double*)sh.partial.p, pl.chunks, nrows, (float*)d_y,
-                                                                     (const float*)d_yin, alpha * g->coef, beta);
+                                                                     (const float*)d_yin, alpha * g->coef, beta, *peers);
         CF_CUDA(cudaGetLastError());
         g->last_launches++;
     }
@@ -565,7 +725,10 @@ int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const v
 // derivative operators, one right-hand side, device pointers (unpadded flat vectors with blocks of d + vg entries):
 // vg = 0 GradientKernel, vg = 1 ValueGradientKernel (entry 0 of every block is the value part)
 int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, const double* d_a, double alpha, double beta,
-                cudaStream_t stream, int vg) {
+                cudaStream_t stream, int vg, const cf_peer_out* peers) {
+    cf_peer_out no_peers;
+    std::memset(&no_peers, 0, sizeof(no_peers));
+    if (!peers) peers = &no_peers;
     const int64_t nrows = sh.r1 - sh.r0;
     if (nrows <= 0) return CF_OK;
     const int d = g->d, D = g->D, bs = d + vg;
@@ -612,7 +775,7 @@ int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, co
     g->last_launches++;
     const int blocks = (int)std::min<int64_t>((nrows * bs + 255) / 256, 8192);
     grad_reduce_partials<<<blocks, 256, 0, stream>>>((const double*)sh.partial.p, P.partial0, pl.chunks, nrows, D, d, vg, d_y, d_yin,
-                                                     alpha, beta);
+                                                     alpha, beta, *peers);
     CF_CUDA(cudaGetLastError());
     g->last_launches++;
     return CF_OK;

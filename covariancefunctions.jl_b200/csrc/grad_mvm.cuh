@@ -173,7 +173,7 @@ __global__ void __launch_bounds__(NT, MINB) grad_mvm_kernel(const __grid_constan
 // value part (reference src/gramian.jl:245 for the beta handling)
 static __global__ void grad_reduce_partials(const double* __restrict__ partial, const double* __restrict__ partial0, int chunks,
                                             int64_t nrows, int D, int d, int vg, double* __restrict__ y,
-                                            const double* __restrict__ yin, double alpha, double beta) {
+                                            const double* __restrict__ yin, double alpha, double beta, const cf_peer_out peers) {
     const int bs = d + vg;
     const int64_t total = nrows * bs;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
@@ -188,6 +188,7 @@ static __global__ void grad_reduce_partials(const double* __restrict__ partial, 
         double v = alpha * s;
         if (beta != 0.0) v += beta * yin[q];
         y[q] = v;
+        for (int p = 0; p < peers.n; p++) static_cast<double*>(peers.ptr[p])[q] = v; // NVLink peer stores
     }
 }
 

@@ -19,6 +19,15 @@
 #pragma once
 #include "cf_math.cuh"
 
+// Fused all-gather: when chained MVMs run on several GPUs of one process, the epilogue that produces a row block of the
+// result also stores it into every peer's copy of the vector through peer-mapped pointers (NVLink P2P stores); ptr[p]
+// already points at this row block inside peer p's vector.  n == 0: no peers.
+struct cf_peer_out {
+    int32_t n;
+    int32_t pad_;
+    void* ptr[8];
+};
+
 struct cf_mvm_params {
     const void* X;        // rows: padded AoS, stride D elements
     const void* Y;        // columns: padded AoS, stride D elements
@@ -30,12 +39,12 @@ struct cf_mvm_params {
     int64_t m;            // number of columns
     int64_t cols_per_chunk; // multiple of TJ
     double alpha, beta;
-    double coef;          // leading constant of a single-atom program (folded into alpha by the host when direct)
     int direct;           // 1: write alpha*sum + beta*y, 0: write the raw partial sum
     int use_tma;          // 0: a is not 16-byte aligned -> cooperative loads
     int64_t diag_block;   // > 0: each CTA sweeps only the columns of its own row block of this size (symmetric variant)
     cf_atom_val atom;     // the single atom (specialised kinds)
     cf_sop_val sop;       // generic sum of products (KIND == CF_ATOM_SOP)
+    cf_peer_out peers;    // direct mode: also store the finished rows into these peer vectors
 };
 
 // ---- mbarrier / TMA 1-D bulk copy wrappers (PTX ISA: cp.async.bulk, mbarrier) ------------------------------
@@ -64,9 +73,6 @@ __device__ __forceinline__ void cf_mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
-
-template <typename T>
-struct cf_acc { typedef double type; };
 
 // shared memory carve-up (bytes)
 template <typename T, int D, int TJ, int NS>
@@ -227,6 +233,7 @@ __global__ void __launch_bounds__(NT, MINB) gram_mvm_kernel(const __grid_constan
                 double v = P.alpha * tot[r];
                 if (P.beta != 0.0) v += P.beta * (double)yin[o];
                 out[o] = (T)v;
+                for (int p = 0; p < P.peers.n; p++) static_cast<T*>(P.peers.ptr[p])[o] = (T)v; // NVLink peer stores
             } else {
                 reinterpret_cast<double*>(P.out)[(int64_t)blockIdx.y * P.nrows + o] = tot[r];
             }
@@ -237,13 +244,14 @@ __global__ void __launch_bounds__(NT, MINB) gram_mvm_kernel(const __grid_constan
 // y[o] = alpha * sum_s partial[s][o] + beta * y[o]   (beta == 0 overwrites: reference src/gramian.jl:80)
 template <typename T>
 __global__ void gram_reduce_partials(const double* __restrict__ partial, int chunks, int64_t nrows, T* __restrict__ y,
-                                     const T* __restrict__ yin, double alpha, double beta) {
+                                     const T* __restrict__ yin, double alpha, double beta, const cf_peer_out peers) {
     for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < nrows; o += (int64_t)gridDim.x * blockDim.x) {
         double s = 0.0;
         for (int c = 0; c < chunks; c++) s += partial[(int64_t)c * nrows + o];
         double v = alpha * s;
         if (beta != 0.0) v += beta * (double)yin[o];
         y[o] = (T)v;
+        for (int p = 0; p < peers.n; p++) static_cast<T*>(peers.ptr[p])[o] = (T)v; // NVLink peer stores
     }
 }
 

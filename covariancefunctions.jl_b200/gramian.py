@@ -12,7 +12,6 @@ import ctypes as C
 
 import numpy as np
 
-from . import _lib
 from ._lib import CF_F32, CF_F64, DimensionMismatch, KNode, UnsupportedKernel, check, lib
 from .kernels import ARD, AbstractKernel, Dot, DotProductInput, GradientKernel, IsotropicInput
 

@@ -51,3 +51,30 @@ def test_cg_over_two_devices(cf, O, two_gpus):
     xo, ito, reso, _ = O.cg_solve(k.program(), X, y, 1e-2)
     assert abs(iters - ito) <= max(3, 0.05 * ito)
     assert relerr(x, xo) < 1e-6
+
+
+def test_cg_spmd_matches_single_device(cf, O):
+    # the multi-device solve (fused peer-store all-gather, csrc/capi.cu cg_solve_spmd) against the single-device solve
+    if cf.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    rng = np.random.default_rng(43)
+    n, d = 5003, 3
+    X = rng.standard_normal((n, d))
+    y = rng.standard_normal(n)
+    k = cf.EQ()
+    cf.init([0])
+    x1, it1, res1 = (0.1 * cf.I(n) + cf.gramian(k, X.T)).solve(y)
+    cf.init([0, 1])
+    try:
+        x2, it2, res2 = (0.1 * cf.I(n) + cf.gramian(k, X.T)).solve(y)
+        Gg = cf.gramian(cf.GradientKernel(cf.MaternP(2)), X[:400].T)
+        a = rng.standard_normal(400 * d)
+        Ka = Gg @ a
+        xs, its, ress = (1e-8 * cf.I(400 * d) + Gg).solve(Ka, reltol=1e-10, maxiter=3000)
+    finally:
+        cf.init([0])
+    assert abs(it1 - it2) <= 2
+    assert relerr(x2, x1) < 1e-8
+    M = O.matrix(k.program(), X) + 0.1 * np.eye(n)
+    assert np.linalg.norm(M @ x2 - y) / np.linalg.norm(y) < 1e-6
+    assert np.linalg.norm((Gg @ xs) - Ka) / np.linalg.norm(Ka) < 1e-6

@@ -12,6 +12,8 @@
 #include <string>
 #include <vector>
 
+// this translation unit holds the non-hot kernels (dense instantiation, d > 32): they use the two-step exp reduction
+#define CF_EXP_ACCURATE 1
 #include "../../include/covfn_b200.h"
 #include "cf_lower.h"
 #include "cf_registry.h"

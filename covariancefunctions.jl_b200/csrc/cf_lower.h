@@ -50,6 +50,14 @@ inline void fill_exp(cf_exp_consts& E, long double c) {
     E.c = (double)c;
     E.c1 = (double)(c * 256.0L / ln2);   // CF_EXP_TBL = 256 (cf_math.cuh)
     E.c2 = (double)(-(ln2 / 256.0L) / c);
+    {   // split for CF_EXP_ACCURATE: kk (|kk| < 2^19) times c2_hi is exact in double
+        const long double c2l = -(ln2 / 256.0L) / c;
+        union { double d; uint64_t u; } hv;
+        hv.d = (double)c2l;
+        hv.u &= ~((uint64_t(1) << 19) - 1);
+        E.c2_hi = hv.d;
+        E.c2_lo = (double)(c2l - (long double)hv.d);
+    }
     long double ci = c;
     for (int i = 0; i < CF_EXP_POLY; i++) {
         E.q[i] = (double)(ci / lfact(i + 1));

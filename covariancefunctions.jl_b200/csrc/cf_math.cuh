@@ -41,7 +41,14 @@ __device__ __forceinline__ double cf_exp_cv(double v, const cf_exp_consts& E, cf
     double t = fma(v, E.c1, CF_MAGIC);
     const int kk = __double2loint(t);
     double kd = t - CF_MAGIC;
+#ifdef CF_EXP_ACCURATE
+    // two-step Cody-Waite (kd * c2_hi is exact): <= ~1 ulp for every argument; used by the dense-instantiation and d > 32
+    // translation unit.  The one-step form below adds a relative error of about 0.3 |c v| ulp (the size of the rounding
+    // error r2 itself carries), i.e. an absolute error <= 4e-17 relative to k = 1 -- invisible in a sum, and 2 cycles cheaper.
+    double u = fma(kd, E.c2_lo, fma(kd, E.c2_hi, v));
+#else
     double u = fma(kd, E.c2, v);
+#endif
     double p = fma(E.q[3], u, E.q[2]);
     p = fma(p, u, E.q[1]);
     p = fma(p, u, E.q[0]);
@@ -131,21 +138,23 @@ __device__ __forceinline__ void cf_atom_matern_n(const double (&r2)[N], const cf
 #pragma unroll
     for (int u = 0; u < N; u++) out[u] = mp[u] * e[u];
 }
+// (1 + w r2)^-a, a a positive Int: one reciprocal of base^a (a - 1 multiplications), clamped so that an overflowing power
+// returns ~0 instead of feeding Inf to the Newton steps
 __device__ __forceinline__ double cf_atom_rq_int(double r2, const cf_atom_val& A) {
     double base = fma(r2, A.w, 1.0);
-    return cf_powi(cf_rcp(base), A.p);
+    return cf_rcp(fmin(cf_powi(base, A.p), 1e300));
 }
 template <int N>
 __device__ __forceinline__ void cf_atom_rq_int_n(const double (&r2)[N], const cf_atom_val& A, double (&out)[N]) {
-    double ib[N];
+    double base[N], pw[N];
 #pragma unroll
-    for (int u = 0; u < N; u++) ib[u] = cf_rcp(fma(r2[u], A.w, 1.0));
-#pragma unroll
-    for (int u = 0; u < N; u++) out[u] = ib[u];
+    for (int u = 0; u < N; u++) { base[u] = fma(r2[u], A.w, 1.0); pw[u] = base[u]; }
     for (int i = 1; i < A.p; i++) {
 #pragma unroll
-        for (int u = 0; u < N; u++) out[u] *= ib[u];
+        for (int u = 0; u < N; u++) pw[u] *= base[u];
     }
+#pragma unroll
+    for (int u = 0; u < N; u++) out[u] = cf_rcp(fmin(pw[u], 1e300));
 }
 // pow() is a large routine: keep one out-of-line copy per kernel instead of one per call site (instruction cache)
 static __device__ __noinline__ double cf_pow_outlined(double base, double e) { return pow(base, e); }

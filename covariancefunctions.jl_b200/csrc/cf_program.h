@@ -26,6 +26,7 @@ enum cf_atom_kind {
 struct cf_exp_consts {
     double c1;             // c * 256 / ln2
     double c2;             // -(ln2 / 256) / c
+    double c2_hi, c2_lo;   // the same constant split for the two-step (accurate) reduction: c2_hi has 34 significant bits
     double q[CF_EXP_POLY]; // c^(i+1) / (i+1)!
     double c;              // the plain multiplier (fp32 path, derivative formulas)
     double vmax;           // clamp: c*vmax = -700 (result ~1e-304, i.e. 0)

@@ -169,20 +169,21 @@ __global__ void __launch_bounds__(256, 1) gram_mm_kernel(const __grid_constant__
         for (int b = 0; b < 4; b++) acc[a][b] = 0;
 
     auto tile_compute = [&](const T* __restrict__ ys, const T* __restrict__ yns, const T* __restrict__ As, int cnt) {
-        // phase A: 4 entries at a time (independent FMA chains hide the FP64 latency with only 2 warps per scheduler)
-        for (int q0 = 0; q0 < CF_MM_TJ / 2; q0 += 4) {
+        // phase A: AG entries at a time (independent FMA chains hide the FP64 latency with only 2 warps per scheduler)
+        constexpr int AG = 4;  // 8 spills (255 registers) and is 10 % slower
+        for (int q0 = 0; q0 < CF_MM_TJ / 2; q0 += AG) {
             const int jb = jh * (CF_MM_TJ / 2) + q0;
-            T r2[4], dt[4];
+            T r2[AG], dt[AG];
 #pragma unroll
-            for (int u = 0; u < 4; u++) { r2[u] = 0; dt[u] = 0; }
+            for (int u = 0; u < AG; u++) { r2[u] = 0; dt[u] = 0; }
             if (P.use_norms) {
 #pragma unroll
                 for (int c = 0; c < D; c++) {
 #pragma unroll
-                    for (int u = 0; u < 4; u++) dt[u] = fma(x[c], ys[(jb + u) * D + c], dt[u]);
+                    for (int u = 0; u < AG; u++) dt[u] = fma(x[c], ys[(jb + u) * D + c], dt[u]);
                 }
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
+                for (int u = 0; u < AG; u++) {
                     const T v = fma((T)-2, dt[u], xnorm + yns[jb + u]);
                     r2[u] = (v > (T)0) ? v : (T)0;
                 }
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(256, 1) gram_mm_kernel(const __grid_constant__
 #pragma unroll
                 for (int c = 0; c < D; c++) {
 #pragma unroll
-                    for (int u = 0; u < 4; u++) {
+                    for (int u = 0; u < AG; u++) {
                         const T yv = ys[(jb + u) * D + c];
                         const T df = x[c] - yv;
                         r2[u] = fma(df, df, r2[u]);
@@ -198,11 +199,11 @@ __global__ void __launch_bounds__(256, 1) gram_mm_kernel(const __grid_constant__
                     }
                 }
             }
-            T kv[4];
-            if constexpr (sizeof(T) == 8) cf_sop_value_n<4>(r2, dt, P.sop, tbl_lane, kv);
-            else cf_sop_value_f32_n<4>(r2, dt, P.sop, kv);
+            T kv[AG];
+            if constexpr (sizeof(T) == 8) cf_sop_value_n<AG>(r2, dt, P.sop, tbl_lane, kv);
+            else cf_sop_value_f32_n<AG>(r2, dt, P.sop, kv);
 #pragma unroll
-            for (int u = 0; u < 4; u++) Ks[(jb + u) * CF_MM_TI + li] = (jb + u < cnt) ? kv[u] : (T)0; // past the end: no contribution
+            for (int u = 0; u < AG; u++) Ks[(jb + u) * CF_MM_TI + li] = (jb + u < cnt) ? kv[u] : (T)0; // past the end: no contribution
         }
         __syncthreads();
         // phase B: this thread's rows are {32 a2 + 2 rg + b}: the 16 lanes of a half-warp read 256 contiguous bytes of Ks.

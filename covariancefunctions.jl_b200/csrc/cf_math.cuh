@@ -1,12 +1,13 @@
 // cf_math.cuh -- device arithmetic for the Gramian kernels (sm_100a).
 //
 // FP64: there is no FP64 SFU path on the chip (MUFU.EX2 is FP32-only), so exp is built from the FP64
-// FMA pipe: one magic-number rounding, a one-step Cody-Waite reduction against a 64-entry 2^(j/64)
+// FMA pipe: one magic-number rounding, a one-step Cody-Waite reduction against a 256-entry 2^(j/256)
 // table held in shared memory (replicated 16x so that every lane of a half-warp reads its own bank
-// pair: zero bank conflicts for any index pattern) and a degree-5 polynomial -- 9 FP64 issue slots
+// pair: zero bank conflicts for any index pattern) and a degree-4 polynomial -- 9 FP64 issue slots
 // instead of the ~16-20 of a table-free exp.  sqrt and reciprocal take their seed from the SFU
 // (MUFU.RSQ64H / MUFU.RCP64H through rsqrt.approx.ftz.f64 / rcp.approx.ftz.f64) and are finished with
-// FMA Newton steps.  All results are accurate to ~1 ulp (tests/test_gpu_math.py measures it).
+// FMA Newton steps.  Accuracy is measured in tests/test_gpu_math.py: sqrt / reciprocal <= 1.5 ulp, exp <= 1.4 ulp with the
+// two-step reduction (CF_EXP_ACCURATE) and <= (2 + 0.35 |argument|) ulp with the one-step reduction of the hot loop.
 // FP32: ex2.approx / rsqrt.approx / rcp.approx on the SFU.
 #pragma once
 #include <cuda_runtime.h>

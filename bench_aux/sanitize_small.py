@@ -1,0 +1,35 @@
+"""Small exercise of every kernel family for compute-sanitizer (memcheck / racecheck / synccheck)."""
+import os
+import sys
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import covfn_b200 as cf  # noqa: E402
+
+rng = np.random.default_rng(0)
+for d in (3, 16):
+    n, m = 700, 515
+    X, Y = rng.standard_normal((n, d)) / np.sqrt(d), rng.standard_normal((m, d)) / np.sqrt(d)
+    a = rng.standard_normal(m)
+    for k in (cf.EQ(), cf.MaternP(2), cf.RQ(2), 0.5 * cf.RQ(2) + cf.Dot() ** 2):
+        G = cf.gramian(k, X.T, Y.T)
+        G @ a
+        G @ rng.standard_normal((m, 5))
+        G.Matrix()
+    Gs = cf.gramian(cf.EQ(), X.T)
+    Gs @ rng.standard_normal(n)
+    for k in (cf.EQ(), cf.MaternP(2), cf.Dot() ** 3):
+        cf.gramian(cf.GradientKernel(k), X.T, Y.T) @ rng.standard_normal(m * d)
+        cf.gramian(cf.ValueGradientKernel(k), X.T, Y.T) @ rng.standard_normal(m * (d + 1))
+    (1e-2 * cf.I(n) + Gs).solve(rng.standard_normal(n), maxiter=5)
+Xf = rng.standard_normal((300, 3)).astype(np.float32)
+cf.gramian(cf.EQ(), Xf.T) @ rng.standard_normal(300).astype(np.float32)
+Xb = rng.standard_normal((150, 40)) / 6
+cf.gramian(cf.EQ(), Xb.T) @ rng.standard_normal(150)
+cf.gramian(cf.GradientKernel(cf.EQ()), Xb.T) @ rng.standard_normal(150 * 40)
+if os.environ.get("CF_SAN_SYM"):  # symmetric variant at its minimum size (slow under the sanitizer)
+    n = 65536
+    Xs = rng.standard_normal((n, 3))
+    cf.gramian(cf.EQ(), Xs.T).set_symmetric(True) @ rng.standard_normal(n)
+print("sanitize_small: done")

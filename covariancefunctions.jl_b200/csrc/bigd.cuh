@@ -88,7 +88,8 @@ static __global__ void __launch_bounds__(256) bigd_value_kernel(const double* __
     __shared__ double red[8];
     cf_fill_exp_table(tbl, exp2_tbl, threadIdx.x, 256);
     __syncthreads();
-    const cf_tbl_t tbl_lane = cf_tbl_lane(tbl, threadIdx.x);
+    cf_tbl_t tbl_lane = cf_tbl_lane(tbl, threadIdx.x);
+    cf_tbl_publish(tbl_lane);
     for (int64_t i = blockIdx.x; i < nrows; i += gridDim.x) {
         double acc = 0.0;
         for (int64_t j = threadIdx.x; j < m; j += 256)
@@ -116,7 +117,8 @@ __global__ void __launch_bounds__(256) bigd_jet_kernel(double* __restrict__ Tm, 
     double* tbl = reinterpret_cast<double*>(bd_smem);
     cf_fill_exp_table(tbl, exp2_tbl, threadIdx.x, 256);
     __syncthreads();
-    const cf_tbl_t tbl_lane = cf_tbl_lane(tbl, threadIdx.x);
+    cf_tbl_t tbl_lane = cf_tbl_lane(tbl, threadIdx.x);
+    cf_tbl_publish(tbl_lane);
     for (int64_t q = (int64_t)blockIdx.x * 256 + threadIdx.x; q < total; q += (int64_t)gridDim.x * 256) {
         double k, k1, k2;
         cf_sop_jet(Tm[q], prog, tbl_lane, k, k1, k2);

@@ -744,7 +744,8 @@ int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, co
     const double* a_use = d_a;
     const double* a0_use = nullptr;
     if (vg || D != d || (((uintptr_t)d_a) % 16) != 0) {
-        int rc = sh.apad.ensure((size_t)g->m * (D + 1) * sizeof(double));
+        const size_t a0_off = (((size_t)g->m * D + 1) / 2) * 2; // the value weights follow the gradient weights, 16-byte aligned (TMA source)
+        int rc = sh.apad.ensure((a0_off + (size_t)g->m + 2) * sizeof(double));
         if (rc) return rc;
         const int blocks = (int)std::min<int64_t>((g->m * D + 255) / 256, 8192);
         cf_pad_points<double><<<blocks, 256, 0, stream>>>(d_a + vg, bs, d, (double*)sh.apad.p, D, g->m);
@@ -752,7 +753,7 @@ int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, co
         g->last_launches++;
         a_use = (const double*)sh.apad.p;
         if (vg) {
-            double* a0 = (double*)sh.apad.p + (size_t)g->m * D;
+            double* a0 = (double*)sh.apad.p + a0_off;
             cf_pad_points<double><<<(int)std::min<int64_t>((g->m + 255) / 256, 8192), 256, 0, stream>>>(d_a, bs, 1, a0, 1, g->m);
             CF_CUDA(cudaGetLastError());
             g->last_launches++;

@@ -19,7 +19,8 @@ __global__ void gram_dense_kernel(const T* __restrict__ X, const T* __restrict__
     __shared__ double tbl[CF_EXP_TBL_DOUBLES];
     cf_fill_exp_table(tbl, exp2_tbl, threadIdx.x, blockDim.x);
     __syncthreads();
-    const cf_tbl_t tbl_lane = cf_tbl_lane(tbl, threadIdx.x);
+    cf_tbl_t tbl_lane = cf_tbl_lane(tbl, threadIdx.x);
+    cf_tbl_publish(tbl_lane);
     const int64_t total = nrows * ncols;
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
         const int64_t jj = q / nrows, ii = q - jj * nrows;
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(256, 1) gram_mm_kernel(const __grid_constant__
     T* Ks = reinterpret_cast<T*>(smem + S::tbl_bytes + S::bar_bytes);
     unsigned char* stages = smem + S::tbl_bytes + S::bar_bytes + S::ks_bytes;
     const int tid = threadIdx.x;
-    const cf_tbl_t tbl_lane = cf_tbl_lane(tbl, tid);
+    cf_tbl_t tbl_lane = cf_tbl_lane(tbl, tid);
     const T* __restrict__ Xg = static_cast<const T*>(P.X);
     const T* __restrict__ Yg = static_cast<const T*>(P.Y);
     const T* __restrict__ yng = static_cast<const T*>(P.yn);
@@ -137,6 +138,7 @@ __global__ void __launch_bounds__(256, 1) gram_mm_kernel(const __grid_constant__
         cf_fence_barrier_init();
     }
     __syncthreads();
+    cf_tbl_publish(tbl_lane);
     const int nfull = (int)(P.m / CF_MM_TJ);
     auto issue = [&](int tile) {
         const int s = tile % CF_MM_NS;

@@ -23,6 +23,11 @@
 typedef uint32_t cf_tbl_t; // shared-space byte address of this lane's replica column of the exp table
 __device__ __forceinline__ uint32_t cf_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ cf_tbl_t cf_tbl_lane(const double* tbl, int tid) { return cf_smem_u32(tbl + (tid & 15)); }
+// The table is read with `ld.shared` inside non-volatile asm (so that the loads can be scheduled freely among the FMA
+// chains).  The compiler therefore does not know they read memory and could hoist them above the barrier that publishes the
+// table (compute-sanitizer racecheck caught exactly that).  Every kernel calls this right after that barrier: it makes the
+// table address -- an input of every table load -- the output of a volatile asm that cannot cross the barrier.
+__device__ __forceinline__ void cf_tbl_publish(cf_tbl_t& tbl_lane) { asm volatile("" : "+r"(tbl_lane) : : "memory"); }
 
 // Copy the 2^(j/256) table (256 doubles in global memory, written once per device by the host, correctly
 // rounded from long double) into shared memory, 16 replicas per entry: entry j for lane l lives at

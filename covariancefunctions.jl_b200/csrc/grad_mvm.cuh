@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(NT, MINB) grad_mvm_kernel(const __grid_constan
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::tbl_bytes);
     unsigned char* stages = smem + S::tbl_bytes + S::bar_bytes;
     const int tid = threadIdx.x;
-    const cf_tbl_t tbl_lane = cf_tbl_lane(tbl, tid);
+    cf_tbl_t tbl_lane = cf_tbl_lane(tbl, tid);
 
     const int64_t c0 = (int64_t)blockIdx.y * P.cols_per_chunk;
     const int64_t c1 = (c0 + P.cols_per_chunk < P.m) ? c0 + P.cols_per_chunk : P.m;
@@ -68,6 +68,7 @@ __global__ void __launch_bounds__(NT, MINB) grad_mvm_kernel(const __grid_constan
         cf_fence_barrier_init();
     }
     __syncthreads();
+    cf_tbl_publish(tbl_lane);
     auto issue = [&](int tile) {
         const int s = tile % NS;
         unsigned char* st = stages + (size_t)s * S::stage_bytes;

@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(NT, MINB) gram_mvm_kernel(const __grid_constan
     unsigned char* stages = smem + S::tbl_bytes + S::bar_bytes;
 
     const int tid = threadIdx.x;
-    const cf_tbl_t tbl_lane = cf_tbl_lane(tbl, tid);
+    cf_tbl_t tbl_lane = cf_tbl_lane(tbl, tid);
     const T* __restrict__ Xg = static_cast<const T*>(P.X);
     const T* __restrict__ Yg = static_cast<const T*>(P.Y);
     const T* __restrict__ ag = static_cast<const T*>(P.a);
@@ -152,6 +152,7 @@ __global__ void __launch_bounds__(NT, MINB) gram_mvm_kernel(const __grid_constan
         cf_fence_barrier_init();
     }
     __syncthreads();
+    cf_tbl_publish(tbl_lane);
 
     auto issue = [&](int tile) {
         const int s = tile % NS;

@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(NT, MINB) gram_mvm_sym_kernel(const __grid_con
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + S::tbl_bytes);
     unsigned char* stages = smem + S::tbl_bytes + S::bar_bytes;
     const int tid = threadIdx.x, lane = tid & 31;
-    const cf_tbl_t tbl_lane = cf_tbl_lane(tbl, tid);
+    cf_tbl_t tbl_lane = cf_tbl_lane(tbl, tid);
     const cf_sym_item it = P.items[blockIdx.x];
     const int64_t c0 = it.col0, c1 = it.col1;
     const int nfull = P.use_tma ? (int)((c1 - c0) / TJ) : 0;
@@ -62,6 +62,7 @@ __global__ void __launch_bounds__(NT, MINB) gram_mvm_sym_kernel(const __grid_con
         cf_fence_barrier_init();
     }
     __syncthreads();
+    cf_tbl_publish(tbl_lane);
     auto issue = [&](int tile) {
         const int s = tile % NS;
         unsigned char* st = stages + (size_t)s * S::stage_bytes;

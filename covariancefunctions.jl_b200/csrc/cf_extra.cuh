@@ -118,8 +118,13 @@ __global__ void cf_sqnorm_validate_kernel(const T* __restrict__ X, int D, int64_
     if (mx > 0.0 && isfinite(mx)) atomicMax(&f[1], (unsigned long long)__double_as_longlong(mx));
 }
 
-template <typename T, int D>
-__global__ void __launch_bounds__(256, 1) gram_mm_kernel(const __grid_constant__ cf_mm_params P) {
+// NTB = 256: 8 x 4 register tiles, 16 entries per thread in phase A; NTB = 512: 4 x 4 tiles, 8 entries (<= 128 registers,
+// twice the warps to hide FP64 and shared-memory latency)
+template <typename T, int D, int NTB>
+__global__ void __launch_bounds__(NTB, 1) gram_mm_kernel(const __grid_constant__ cf_mm_params P) {
+    constexpr int JQ = NTB / 128;            // column groups in phase A
+    constexpr int EPT = CF_MM_TJ / JQ;        // entries per thread in phase A
+    constexpr int RH = (NTB == 256) ? 4 : 2;  // LDS.128 of K per k step in phase B; rows per thread = 2 RH
     using S = cf_mm_smem<T, D>;
     extern __shared__ __align__(128) unsigned char smem[];
     double* tbl = reinterpret_cast<double*>(smem);
@@ -132,7 +137,7 @@ __global__ void __launch_bounds__(256, 1) gram_mm_kernel(const __grid_constant__
     const T* __restrict__ Yg = static_cast<const T*>(P.Y);
     const T* __restrict__ yng = static_cast<const T*>(P.yn);
     const T* __restrict__ Atg = static_cast<const T*>(P.At);
-    if (sizeof(T) == 8) cf_fill_exp_table(tbl, P.exp2_tbl, tid, 256);
+    if (sizeof(T) == 8) cf_fill_exp_table(tbl, P.exp2_tbl, tid, NTB);
     if (tid == 0) {
         for (int s = 0; s < CF_MM_NS; s++) cf_mbar_init(&bars[s], 1);
         cf_fence_barrier_init();
@@ -163,18 +168,21 @@ __global__ void __launch_bounds__(256, 1) gram_mm_kernel(const __grid_constant__
         for (int c = 0; c < D; c++) x[c] = Xg[i * D + c];
         xnorm = static_cast<const T*>(P.xn)[i];
     }
-    const int rg = tid & 15, cg = tid >> 4; // phase B tile: rows {32 a2 + 2 rg + b}, columns 4 cg .. 4 cg + 3
-    T acc[8][4];
+    // phase B tile: rows {rbase_b + 32 h + 2 rg + b : h < RH, b < 2}, columns 4 cg .. 4 cg + 3
+    const int rg = tid & 15;
+    const int rbase_b = (NTB == 256) ? 0 : 64 * ((tid >> 4) & 1);
+    const int cg = (NTB == 256) ? (tid >> 4) : (tid >> 5);
+    T acc[2 * RH][4];
 #pragma unroll
-    for (int a = 0; a < 8; a++)
+    for (int a = 0; a < 2 * RH; a++)
 #pragma unroll
         for (int b = 0; b < 4; b++) acc[a][b] = 0;
 
     auto tile_compute = [&](const T* __restrict__ ys, const T* __restrict__ yns, const T* __restrict__ As, int cnt) {
         // phase A: AG entries at a time (independent FMA chains hide the FP64 latency with only 2 warps per scheduler)
         constexpr int AG = 4;  // 8 spills (255 registers) and is 10 % slower
-        for (int q0 = 0; q0 < CF_MM_TJ / 2; q0 += AG) {
-            const int jb = jh * (CF_MM_TJ / 2) + q0;
+        for (int q0 = 0; q0 < EPT; q0 += AG) {
+            const int jb = jh * EPT + q0;
             T r2[AG], dt[AG];
 #pragma unroll
             for (int u = 0; u < AG; u++) { r2[u] = 0; dt[u] = 0; }
@@ -210,12 +218,12 @@ __global__ void __launch_bounds__(256, 1) gram_mm_kernel(const __grid_constant__
         __syncthreads();
         // phase B: this thread's rows are {32 a2 + 2 rg + b}: the 16 lanes of a half-warp read 256 contiguous bytes of Ks.
         // Software pipelined: the operands of step k+1 are loaded while the 32 FMAs of step k issue.
-        T kr[2][8], ac[2][4];
-        auto loadk = [&](int k, T (&krr)[8], T (&acc_)[4]) {
+        T kr[2][2 * RH], ac[2][4];
+        auto loadk = [&](int k, T (&krr)[2 * RH], T (&acc_)[4]) {
             if constexpr (sizeof(T) == 8) {
 #pragma unroll
-                for (int h = 0; h < 4; h++) {
-                    const double2 v = *reinterpret_cast<const double2*>(&Ks[k * CF_MM_TI + 32 * h + 2 * rg]);
+                for (int h = 0; h < RH; h++) {
+                    const double2 v = *reinterpret_cast<const double2*>(&Ks[k * CF_MM_TI + rbase_b + 32 * h + 2 * rg]);
                     krr[2 * h] = v.x; krr[2 * h + 1] = v.y;
                 }
 #pragma unroll
@@ -225,8 +233,8 @@ __global__ void __launch_bounds__(256, 1) gram_mm_kernel(const __grid_constant__
                 }
             } else {
 #pragma unroll
-                for (int h = 0; h < 4; h++) {
-                    const float2 v = *reinterpret_cast<const float2*>(&Ks[k * CF_MM_TI + 32 * h + 2 * rg]);
+                for (int h = 0; h < RH; h++) {
+                    const float2 v = *reinterpret_cast<const float2*>(&Ks[k * CF_MM_TI + rbase_b + 32 * h + 2 * rg]);
                     krr[2 * h] = v.x; krr[2 * h + 1] = v.y;
                 }
                 const float4 v = *reinterpret_cast<const float4*>(&As[k * CF_MM_PC + 4 * cg]);
@@ -238,12 +246,12 @@ __global__ void __launch_bounds__(256, 1) gram_mm_kernel(const __grid_constant__
         for (int k = 0; k < CF_MM_TJ; k += 2) {
             loadk(k + 1, kr[1], ac[1]);
 #pragma unroll
-            for (int a = 0; a < 8; a++)
+            for (int a = 0; a < 2 * RH; a++)
 #pragma unroll
                 for (int b = 0; b < 4; b++) acc[a][b] = fma(kr[0][a], ac[0][b], acc[a][b]);
             if (k + 2 < CF_MM_TJ) loadk(k + 2, kr[0], ac[0]);
 #pragma unroll
-            for (int a = 0; a < 8; a++)
+            for (int a = 0; a < 2 * RH; a++)
 #pragma unroll
                 for (int b = 0; b < 4; b++) acc[a][b] = fma(kr[1][a], ac[1][b], acc[a][b]);
         }
@@ -265,9 +273,9 @@ __global__ void __launch_bounds__(256, 1) gram_mm_kernel(const __grid_constant__
         T* yns = reinterpret_cast<T*>(stages + S::y_bytes);
         T* As = reinterpret_cast<T*>(stages + S::y_bytes + S::n_bytes);
         __syncthreads();
-        for (int q = tid; q < CF_MM_TJ * D; q += 256) ys[q] = (q < cnt * D) ? Yg[j0 * D + q] : (T)0;
-        for (int q = tid; q < CF_MM_TJ; q += 256) yns[q] = (q < cnt) ? yng[j0 + q] : (T)0;
-        for (int q = tid; q < CF_MM_TJ * CF_MM_PC; q += 256) As[q] = (q < cnt * CF_MM_PC) ? Atg[j0 * CF_MM_PC + q] : (T)0;
+        for (int q = tid; q < CF_MM_TJ * D; q += NTB) ys[q] = (q < cnt * D) ? Yg[j0 * D + q] : (T)0;
+        for (int q = tid; q < CF_MM_TJ; q += NTB) yns[q] = (q < cnt) ? yng[j0 + q] : (T)0;
+        for (int q = tid; q < CF_MM_TJ * CF_MM_PC; q += NTB) As[q] = (q < cnt * CF_MM_PC) ? Atg[j0 * CF_MM_PC + q] : (T)0;
         __syncthreads();
         tile_compute(ys, yns, As, cnt);
     }
@@ -277,8 +285,8 @@ __global__ void __launch_bounds__(256, 1) gram_mm_kernel(const __grid_constant__
         const int c = 4 * cg + b;
         if (c >= P.nrhs) continue;
 #pragma unroll
-        for (int a = 0; a < 8; a++) {
-            const int64_t i = rbase + 32 * (a >> 1) + 2 * rg + (a & 1);
+        for (int a = 0; a < 2 * RH; a++) {
+            const int64_t i = rbase + rbase_b + 32 * (a >> 1) + 2 * rg + (a & 1);
             if (i >= rend) continue;
             T* o = Bg + (i - P.row0) + P.ldb * c;
             double v = P.alpha * (double)acc[a][b];
@@ -289,10 +297,10 @@ __global__ void __launch_bounds__(256, 1) gram_mm_kernel(const __grid_constant__
 }
 
 typedef cudaError_t (*cf_mm_launch_fn)(const cf_mm_params& P, int row_tiles, cudaStream_t stream);
-template <typename T, int D>
+template <typename T, int D, int NTB>
 cudaError_t cf_mm_launch(const cf_mm_params& P, int row_tiles, cudaStream_t stream) {
     using S = cf_mm_smem<T, D>;
-    auto kern = gram_mm_kernel<T, D>;
+    auto kern = gram_mm_kernel<T, D, NTB>;
     static bool configured[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -301,7 +309,7 @@ cudaError_t cf_mm_launch(const cf_mm_params& P, int row_tiles, cudaStream_t stre
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
-    kern<<<row_tiles, 256, S::total, stream>>>(P);
+    kern<<<row_tiles, NTB, S::total, stream>>>(P);
     return cudaGetLastError();
 }
 

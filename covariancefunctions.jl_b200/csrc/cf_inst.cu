@@ -30,7 +30,7 @@ const cf_kernel_entry entry = {
       &cf_grad_launch<D, CF_ATOM_SOP, CF_GRAD_DOT, true, TU::GR, TU::GNT, TU::GTJ, TU::NS, TU::GMINB>}},
     {{TU::GNT * TU::GR, TU::GTJ, cf_grad_smem<D, TU::GTJ, TU::NS, false>::total, TU::GMINB},
      {TU::GNT * TU::GR, TU::GTJ, cf_grad_smem<D, TU::GTJ, TU::NS, true>::total, TU::GMINB}},
-    {&cf_mm_launch<float, D>, &cf_mm_launch<double, D>},
+    {&cf_mm_launch<float, D, 512>, &cf_mm_launch<double, D, 256>},  // fp64 at 512 threads spills (x_i alone is 64 registers)
     {&cf_sym_launch<D, CF_ATOM_EQ, TU::R, TU::NT, TU::TJ, TU::NS, 1>, &cf_sym_launch<D, CF_ATOM_MATERN, TU::R, TU::NT, TU::TJ, TU::NS, 1>,
      &cf_sym_launch<D, CF_ATOM_RQ_INT, TU::R, TU::NT, TU::TJ, TU::NS, 1>, &cf_sym_launch<D, CF_ATOM_SOP, TU::R, TU::NT, TU::TJ, TU::NS, 1>},
 };

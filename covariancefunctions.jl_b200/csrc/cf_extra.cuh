@@ -63,7 +63,9 @@ struct cf_mm_smem {
     static constexpr int n_bytes = CF_MM_TJ * (int)sizeof(T);
     static constexpr int a_bytes = CF_MM_TJ * CF_MM_PC * (int)sizeof(T);    // As[j][c]
     static constexpr int stage_bytes = ((y_bytes + n_bytes + a_bytes + 127) / 128) * 128;
+    static constexpr int xs_bytes = CF_MM_TI * D * (int)sizeof(T);              // Xs[c][i] (NTB = 512 fp64: x_i lives in shared memory)
     static constexpr int total = tbl_bytes + bar_bytes + ks_bytes + CF_MM_NS * stage_bytes;
+    static constexpr int total_xs = total + xs_bytes;
 };
 
 struct cf_mm_params {
@@ -125,6 +127,7 @@ __global__ void __launch_bounds__(NTB, 1) gram_mm_kernel(const __grid_constant__
     constexpr int JQ = NTB / 128;            // column groups in phase A
     constexpr int EPT = CF_MM_TJ / JQ;        // entries per thread in phase A
     constexpr int RH = (NTB == 256) ? 4 : 2;  // LDS.128 of K per k step in phase B; rows per thread = 2 RH
+    constexpr bool XS = (NTB == 512 && sizeof(T) == 8); // keep x_i in shared memory instead of 2 D registers
     using S = cf_mm_smem<T, D>;
     extern __shared__ __align__(128) unsigned char smem[];
     double* tbl = reinterpret_cast<double*>(smem);
@@ -160,14 +163,21 @@ __global__ void __launch_bounds__(NTB, 1) gram_mm_kernel(const __grid_constant__
     const int64_t rbase = P.row0 + (int64_t)blockIdx.x * CF_MM_TI;
     const int64_t rend = P.row0 + P.nrows;
     const int li = tid & 127, jh = tid >> 7;
-    T x[D], xnorm;
+    T x[XS ? 1 : D], xnorm;
+    T* Xs = reinterpret_cast<T*>(smem + S::total); // [c][row], conflict-free for a warp of consecutive rows
     {
         int64_t i = rbase + li;
         if (i >= rend) i = rend - 1;
+        if constexpr (XS) {
+            if (jh == 0)
+                for (int c = 0; c < D; c++) Xs[c * CF_MM_TI + li] = Xg[i * D + c];
+        } else {
 #pragma unroll
-        for (int c = 0; c < D; c++) x[c] = Xg[i * D + c];
+            for (int c = 0; c < D; c++) x[c] = Xg[i * D + c];
+        }
         xnorm = static_cast<const T*>(P.xn)[i];
     }
+    if constexpr (XS) __syncthreads();
     // phase B tile: rows {rbase_b + 32 h + 2 rg + b : h < RH, b < 2}, columns 4 cg .. 4 cg + 3
     const int rg = tid & 15;
     const int rbase_b = (NTB == 256) ? 0 : 64 * ((tid >> 4) & 1);
@@ -189,8 +199,9 @@ __global__ void __launch_bounds__(NTB, 1) gram_mm_kernel(const __grid_constant__
             if (P.use_norms) {
 #pragma unroll
                 for (int c = 0; c < D; c++) {
+                    const T xc = XS ? Xs[c * CF_MM_TI + li] : x[XS ? 0 : c];
 #pragma unroll
-                    for (int u = 0; u < AG; u++) dt[u] = fma(x[c], ys[(jb + u) * D + c], dt[u]);
+                    for (int u = 0; u < AG; u++) dt[u] = fma(xc, ys[(jb + u) * D + c], dt[u]);
                 }
 #pragma unroll
                 for (int u = 0; u < AG; u++) {
@@ -200,12 +211,13 @@ __global__ void __launch_bounds__(NTB, 1) gram_mm_kernel(const __grid_constant__
             } else {
 #pragma unroll
                 for (int c = 0; c < D; c++) {
+                    const T xc = XS ? Xs[c * CF_MM_TI + li] : x[XS ? 0 : c];
 #pragma unroll
                     for (int u = 0; u < AG; u++) {
                         const T yv = ys[(jb + u) * D + c];
-                        const T df = x[c] - yv;
+                        const T df = xc - yv;
                         r2[u] = fma(df, df, r2[u]);
-                        dt[u] = fma(x[c], yv, dt[u]);
+                        dt[u] = fma(xc, yv, dt[u]);
                     }
                 }
             }
@@ -300,16 +312,17 @@ typedef cudaError_t (*cf_mm_launch_fn)(const cf_mm_params& P, int row_tiles, cud
 template <typename T, int D, int NTB>
 cudaError_t cf_mm_launch(const cf_mm_params& P, int row_tiles, cudaStream_t stream) {
     using S = cf_mm_smem<T, D>;
+    constexpr int smem_bytes = (NTB == 512 && sizeof(T) == 8) ? S::total_xs : S::total;
     auto kern = gram_mm_kernel<T, D, NTB>;
     static bool configured[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
     if (!configured[dev & 63]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::total);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (e != cudaSuccess) return e;
         configured[dev & 63] = true;
     }
-    kern<<<row_tiles, NTB, S::total, stream>>>(P);
+    kern<<<row_tiles, NTB, smem_bytes, stream>>>(P);
     return cudaGetLastError();
 }
 

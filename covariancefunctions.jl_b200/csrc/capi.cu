@@ -123,7 +123,8 @@ struct Shard {
     void* Y = nullptr;  // m x D (== X when symmetric)
     void* xn = nullptr;  // squared norms of the padded points (multi-RHS kernel)
     void* yn = nullptr;
-    Buf a, y, partial, apad, ypad, at, cg[6], sym_items, bsym, bd_t, bd_s;
+    Buf a, y, partial, apad, ypad, at, cg[6], sym_items, bsym, bd_t, bd_s, xp, yp;
+    bool mmd_ready = false; // xp / yp hold the padded point copies of the DMMA multi-RHS kernel
     int sym_nitems = 0;
     int64_t r0 = 0, r1 = 0; // rows owned
 };
@@ -217,6 +218,11 @@ int launch_dense(cf_gramian_s* g, Shard& sh, void* d_M, int64_t ld, int64_t j0, 
     return CF_OK;
 }
 
+static bool env_flag(const char* name) {
+    const char* e = std::getenv(name);
+    return e && std::atoi(e) != 0;
+}
+
 // B <- alpha K A + beta B, device pointers, column-major with leading dimensions (elements)
 int launch_mm(cf_gramian_s* g, Shard& sh, void* d_B, int64_t ldb, const void* d_A, int64_t lda, int64_t nrhs, double alpha,
               double beta, cudaStream_t stream) {
@@ -228,7 +234,10 @@ int launch_mm(cf_gramian_s* g, Shard& sh, void* d_B, int64_t ldb, const void* d_
             if (int rc = launch_scale(g->dtype, (char*)d_B + c * ldb * es, (char*)d_B + c * ldb * es, nrows, beta, stream)) return rc;
         return CF_OK;
     }
-    if (int rc = sh.at.ensure((size_t)g->m * CF_MM_PC * es)) return rc;
+    // Float64, well-scaled points, d >= 8: FP64 tensor-core kernel (gram_mm_dmma.cuh); COVFN_MM_SCALAR=1 forces the scalar one
+    const bool dmma = g->dtype == CF_F64 && g->use_norms && g->entry->mm_dmma != nullptr && !env_flag("COVFN_MM_SCALAR");
+    const int ldat = dmma ? CF_MMD_SA : CF_MM_PC;
+    if (int rc = sh.at.ensure((size_t)g->m * ldat * es)) return rc;
     cf_mm_params P;
     std::memset(&P, 0, sizeof(P));
     P.X = sh.X; P.Y = sh.Y; P.xn = sh.xn; P.yn = sh.yn; P.At = sh.at.p;
@@ -236,17 +245,33 @@ int launch_mm(cf_gramian_s* g, Shard& sh, void* d_B, int64_t ldb, const void* d_
     P.row0 = sh.r0; P.nrows = nrows; P.m = g->m; P.ldb = ldb;
     P.alpha = alpha; P.beta = beta;
     P.use_norms = g->use_norms ? 1 : 0;
+    P.ldat = ldat;
+    if (dmma) {
+        const int sx = (g->D % 8 == 4) ? g->D : g->D + 4;
+        if (!sh.mmd_ready) {
+            if (int rc = sh.xp.ensure((size_t)g->n * sx * 8)) return rc;
+            cf_pad_rows_kernel<<<148 * 8, 256, 0, stream>>>((const double*)sh.X, g->D, sx, g->n, (double*)sh.xp.p);
+            if (sh.Y != sh.X) {
+                if (int rc = sh.yp.ensure((size_t)g->m * sx * 8)) return rc;
+                cf_pad_rows_kernel<<<148 * 8, 256, 0, stream>>>((const double*)sh.Y, g->D, sx, g->m, (double*)sh.yp.p);
+            }
+            CF_CUDA(cudaGetLastError());
+            sh.mmd_ready = true;
+        }
+        P.X = sh.xp.p;
+        P.Y = (sh.Y != sh.X) ? sh.yp.p : sh.xp.p;
+    }
     const int row_tiles = (int)((nrows + CF_MM_TI - 1) / CF_MM_TI);
     for (int64_t c0 = 0; c0 < nrhs; c0 += CF_MM_PC) {
         P.nrhs = (int)std::min<int64_t>(CF_MM_PC, nrhs - c0);
         const dim3 tg((unsigned)((g->m + 31) / 32), CF_MM_PC / 32), tb(32, 8);
         if (g->dtype == CF_F64)
-            cf_transpose_rhs<double><<<tg, tb, 0, stream>>>((const double*)d_A + c0 * lda, lda, g->m, P.nrhs, (double*)sh.at.p);
+            cf_transpose_rhs<double><<<tg, tb, 0, stream>>>((const double*)d_A + c0 * lda, lda, g->m, P.nrhs, (double*)sh.at.p, ldat);
         else
-            cf_transpose_rhs<float><<<tg, tb, 0, stream>>>((const float*)d_A + c0 * lda, lda, g->m, P.nrhs, (float*)sh.at.p);
+            cf_transpose_rhs<float><<<tg, tb, 0, stream>>>((const float*)d_A + c0 * lda, lda, g->m, P.nrhs, (float*)sh.at.p, ldat);
         CF_CUDA(cudaGetLastError());
         P.B = (char*)d_B + c0 * ldb * es;
-        CF_CUDA(g->entry->mm[g->dtype](P, row_tiles, stream));
+        CF_CUDA((dmma ? g->entry->mm_dmma : g->entry->mm[g->dtype])(P, row_tiles, stream));
         g->last_launches += 2;
     }
     return CF_OK;

@@ -54,6 +54,9 @@ __global__ void gram_dense_kernel(const T* __restrict__ X, const T* __restrict__
 #define CF_MM_PC 64
 #define CF_MM_NS 2
 
+#ifndef CF_MM_AG
+#define CF_MM_AG 8
+#endif
 template <typename T, int D>
 struct cf_mm_smem {
     static constexpr int tbl_bytes = CF_EXP_TBL_DOUBLES * 8;
@@ -63,9 +66,13 @@ struct cf_mm_smem {
     static constexpr int n_bytes = CF_MM_TJ * (int)sizeof(T);
     static constexpr int a_bytes = CF_MM_TJ * CF_MM_PC * (int)sizeof(T);    // As[j][c]
     static constexpr int stage_bytes = ((y_bytes + n_bytes + a_bytes + 127) / 128) * 128;
-    static constexpr int xs_bytes = CF_MM_TI * D * (int)sizeof(T);              // Xs[c][i] (NTB = 512 fp64: x_i lives in shared memory)
-    static constexpr int total = tbl_bytes + bar_bytes + ks_bytes + CF_MM_NS * stage_bytes;
-    static constexpr int total_xs = total + xs_bytes;
+    // fp64, d >= 8: the row tile's points live in shared memory, row-major with stride D + 2 (LDS.128 of a warp's 32
+    // consecutive rows is conflict-free for every even D), which frees 2 D registers for wider phase-A groups
+    static constexpr bool xs = (sizeof(T) == 8 && D >= 8 && D % 2 == 0);
+    static constexpr int xstr = D + 2;
+    static constexpr int xs_bytes = xs ? CF_MM_TI * xstr * (int)sizeof(T) : 0;
+    static constexpr int total_nox = tbl_bytes + bar_bytes + ks_bytes + CF_MM_NS * stage_bytes;
+    static constexpr int total = total_nox + xs_bytes;
 };
 
 struct cf_mm_params {
@@ -76,13 +83,14 @@ struct cf_mm_params {
     int64_t row0, nrows, m, ldb;
     int nrhs;         // columns in this pass (<= CF_MM_PC)
     int use_norms;
+    int ldat;         // row stride of At (elements)
     double alpha, beta;
     cf_sop_val sop;
 };
 
 // At[j][c] = c < nrhs ? A[j + lda c] : 0   (one pass of <= CF_MM_PC columns)
 template <typename T>
-__global__ void cf_transpose_rhs(const T* __restrict__ A, int64_t lda, int64_t m, int nrhs, T* __restrict__ At) {
+__global__ void cf_transpose_rhs(const T* __restrict__ A, int64_t lda, int64_t m, int nrhs, T* __restrict__ At, int ldat) {
     __shared__ T tile[32][33];
     const int64_t j0 = (int64_t)blockIdx.x * 32;
     const int c0 = blockIdx.y * 32;
@@ -95,7 +103,7 @@ __global__ void cf_transpose_rhs(const T* __restrict__ A, int64_t lda, int64_t m
     for (int jj = threadIdx.y; jj < 32; jj += blockDim.y) {
         const int64_t j = j0 + jj;
         const int c = c0 + threadIdx.x;
-        if (j < m && c < CF_MM_PC) At[j * CF_MM_PC + c] = tile[threadIdx.x][jj];
+        if (j < m && c < CF_MM_PC) At[j * ldat + c] = tile[threadIdx.x][jj];
     }
 }
 
@@ -122,12 +130,13 @@ __global__ void cf_sqnorm_validate_kernel(const T* __restrict__ X, int D, int64_
 
 // NTB = 256: 8 x 4 register tiles, 16 entries per thread in phase A; NTB = 512: 4 x 4 tiles, 8 entries (<= 128 registers,
 // twice the warps to hide FP64 and shared-memory latency)
-template <typename T, int D, int NTB>
+template <typename T, int D, int NTB, int AGP = CF_MM_AG>
 __global__ void __launch_bounds__(NTB, 1) gram_mm_kernel(const __grid_constant__ cf_mm_params P) {
     constexpr int JQ = NTB / 128;            // column groups in phase A
     constexpr int EPT = CF_MM_TJ / JQ;        // entries per thread in phase A
     constexpr int RH = (NTB == 256) ? 4 : 2;  // LDS.128 of K per k step in phase B; rows per thread = 2 RH
-    constexpr bool XS = (NTB == 512 && sizeof(T) == 8); // keep x_i in shared memory instead of 2 D registers
+    constexpr bool XS = cf_mm_smem<T, D>::xs; // fp64, d >= 8: x_i lives in shared memory instead of 2 D registers
+    constexpr int XSTR = cf_mm_smem<T, D>::xstr;
     using S = cf_mm_smem<T, D>;
     extern __shared__ __align__(128) unsigned char smem[];
     double* tbl = reinterpret_cast<double*>(smem);
@@ -164,13 +173,17 @@ __global__ void __launch_bounds__(NTB, 1) gram_mm_kernel(const __grid_constant__
     const int64_t rend = P.row0 + P.nrows;
     const int li = tid & 127, jh = tid >> 7;
     T x[XS ? 1 : D], xnorm;
-    T* Xs = reinterpret_cast<T*>(smem + S::total); // [c][row], conflict-free for a warp of consecutive rows
+    T* Xs = reinterpret_cast<T*>(smem + S::total_nox);
     {
         int64_t i = rbase + li;
         if (i >= rend) i = rend - 1;
         if constexpr (XS) {
-            if (jh == 0)
-                for (int c = 0; c < D; c++) Xs[c * CF_MM_TI + li] = Xg[i * D + c];
+            for (int q = tid; q < CF_MM_TI * D; q += NTB) {
+                const int row = q / D, c = q - row * D;
+                int64_t ir = rbase + row;
+                if (ir >= rend) ir = rend - 1;
+                Xs[row * XSTR + c] = Xg[ir * D + c];
+            }
         } else {
 #pragma unroll
             for (int c = 0; c < D; c++) x[c] = Xg[i * D + c];
@@ -189,17 +202,50 @@ __global__ void __launch_bounds__(NTB, 1) gram_mm_kernel(const __grid_constant__
         for (int b = 0; b < 4; b++) acc[a][b] = 0;
 
     auto tile_compute = [&](const T* __restrict__ ys, const T* __restrict__ yns, const T* __restrict__ As, int cnt) {
-        // phase A: AG entries at a time (independent FMA chains hide the FP64 latency with only 2 warps per scheduler)
-        constexpr int AG = 4;  // 8 spills (255 registers) and is 10 % slower
+        // phase A: AG entries at a time (independent FMA chains hide the FP64 latency with only 2 warps per scheduler;
+        // the program decode of cf_sop_value_n is paid once per group)
+        constexpr int AG = XS ? (AGP < EPT ? AGP : EPT) : 4;
         for (int q0 = 0; q0 < EPT; q0 += AG) {
             const int jb = jh * EPT + q0;
             T r2[AG], dt[AG];
 #pragma unroll
             for (int u = 0; u < AG; u++) { r2[u] = 0; dt[u] = 0; }
-            if (P.use_norms) {
+            if constexpr (XS) {
+                if (P.use_norms) {
+#pragma unroll
+                    for (int c = 0; c < D; c += 2) {
+                        const double2 xv = *reinterpret_cast<const double2*>(&Xs[li * XSTR + c]);
+#pragma unroll
+                        for (int u = 0; u < AG; u++) {
+                            const double2 yv = *reinterpret_cast<const double2*>(&ys[(jb + u) * D + c]);
+                            dt[u] = fma(xv.x, yv.x, dt[u]);
+                            dt[u] = fma(xv.y, yv.y, dt[u]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < AG; u++) {
+                        const T v = fma((T)-2, dt[u], xnorm + yns[jb + u]);
+                        r2[u] = (v > (T)0) ? v : (T)0;
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < D; c += 2) {
+                        const double2 xv = *reinterpret_cast<const double2*>(&Xs[li * XSTR + c]);
+#pragma unroll
+                        for (int u = 0; u < AG; u++) {
+                            const double2 yv = *reinterpret_cast<const double2*>(&ys[(jb + u) * D + c]);
+                            const T d0 = xv.x - yv.x, d1 = xv.y - yv.y;
+                            r2[u] = fma(d0, d0, r2[u]);
+                            r2[u] = fma(d1, d1, r2[u]);
+                            dt[u] = fma(xv.x, yv.x, dt[u]);
+                            dt[u] = fma(xv.y, yv.y, dt[u]);
+                        }
+                    }
+                }
+            } else if (P.use_norms) {
 #pragma unroll
                 for (int c = 0; c < D; c++) {
-                    const T xc = XS ? Xs[c * CF_MM_TI + li] : x[XS ? 0 : c];
+                    const T xc = x[XS ? 0 : c];
 #pragma unroll
                     for (int u = 0; u < AG; u++) dt[u] = fma(xc, ys[(jb + u) * D + c], dt[u]);
                 }
@@ -211,7 +257,7 @@ __global__ void __launch_bounds__(NTB, 1) gram_mm_kernel(const __grid_constant__
             } else {
 #pragma unroll
                 for (int c = 0; c < D; c++) {
-                    const T xc = XS ? Xs[c * CF_MM_TI + li] : x[XS ? 0 : c];
+                    const T xc = x[XS ? 0 : c];
 #pragma unroll
                     for (int u = 0; u < AG; u++) {
                         const T yv = ys[(jb + u) * D + c];
@@ -309,11 +355,11 @@ __global__ void __launch_bounds__(NTB, 1) gram_mm_kernel(const __grid_constant__
 }
 
 typedef cudaError_t (*cf_mm_launch_fn)(const cf_mm_params& P, int row_tiles, cudaStream_t stream);
-template <typename T, int D, int NTB>
+template <typename T, int D, int NTB, int AGP = CF_MM_AG>
 cudaError_t cf_mm_launch(const cf_mm_params& P, int row_tiles, cudaStream_t stream) {
     using S = cf_mm_smem<T, D>;
-    constexpr int smem_bytes = (NTB == 512 && sizeof(T) == 8) ? S::total_xs : S::total;
-    auto kern = gram_mm_kernel<T, D, NTB>;
+    constexpr int smem_bytes = S::total;
+    auto kern = gram_mm_kernel<T, D, NTB, AGP>;
     static bool configured[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);

@@ -33,6 +33,7 @@ const cf_kernel_entry entry = {
     // fp32: 512 threads (+15 %).  fp64: 256 threads; the 512-thread form (x_i in shared memory, 122 registers, no spills) measured
     // the same 0.98 s at config 3, so the extra warps are not what limits it -- kept selectable for the next tuning round.
     {&cf_mm_launch<float, D, 512>, &cf_mm_launch<double, D, 256>},
+    cf_mmd_entry<D>::fn,
     {&cf_sym_launch<D, CF_ATOM_EQ, TU::R, TU::NT, TU::TJ, TU::NS, 1>, &cf_sym_launch<D, CF_ATOM_MATERN, TU::R, TU::NT, TU::TJ, TU::NS, 1>,
      &cf_sym_launch<D, CF_ATOM_RQ_INT, TU::R, TU::NT, TU::TJ, TU::NS, 1>, &cf_sym_launch<D, CF_ATOM_SOP, TU::R, TU::NT, TU::TJ, TU::NS, 1>},
 };

@@ -213,6 +213,25 @@ __device__ __forceinline__ void cf_atom_value_dyn_n(const double (&r2)[N], const
             for (int u = 0; u < N; u++) out[u] = dt[u] + A.sigma;
     }
 }
+// out = atom^pw for N pairs (pw >= 1; the common pw = 1, 2 cost no copies)
+template <int N>
+__device__ __forceinline__ void cf_atom_pow_n(const double (&r2)[N], const double (&dt)[N], const cf_atom_val& A, int pw,
+                                              cf_tbl_t tbl_lane, double (&out)[N]) {
+    cf_atom_value_dyn_n<N>(r2, dt, A, tbl_lane, out);
+    if (pw == 2) {
+#pragma unroll
+        for (int u = 0; u < N; u++) out[u] *= out[u];
+    } else if (pw > 2) {
+        double a[N];
+#pragma unroll
+        for (int u = 0; u < N; u++) a[u] = out[u];
+        for (int q = 1; q < pw; q++) {
+#pragma unroll
+            for (int u = 0; u < N; u++) out[u] *= a[u];
+        }
+    }
+}
+// value = sum_t coef_t prod_f atom^pw: the coefficient is applied with the final FMA, the first factor initialises the product
 template <int N>
 __device__ __forceinline__ void cf_sop_value_n(const double (&r2)[N], const double (&dt)[N], const cf_sop_val& P,
                                                cf_tbl_t tbl_lane, double (&val)[N]) {
@@ -221,23 +240,22 @@ __device__ __forceinline__ void cf_sop_value_n(const double (&r2)[N], const doub
     const int nt = P.nterms;
     for (int t = 0; t < nt; t++) {
         const cf_sop_term& T = P.terms[t];
+        const int nf = T.nfac;
+        if (nf == 0) { // constant term
+#pragma unroll
+            for (int u = 0; u < N; u++) val[u] += T.coef;
+            continue;
+        }
         double prod[N];
+        cf_atom_pow_n<N>(r2, dt, P.atoms[T.atom[0]], T.power[0], tbl_lane, prod);
+        for (int f = 1; f < nf; f++) {
+            double a[N];
+            cf_atom_pow_n<N>(r2, dt, P.atoms[T.atom[f]], T.power[f], tbl_lane, a);
 #pragma unroll
-        for (int u = 0; u < N; u++) prod[u] = T.coef;
-        for (int f = 0; f < T.nfac; f++) {
-            double a[N], r[N];
-            cf_atom_value_dyn_n<N>(r2, dt, P.atoms[T.atom[f]], tbl_lane, a);
-#pragma unroll
-            for (int u = 0; u < N; u++) r[u] = a[u];
-            for (int q = 1; q < T.power[f]; q++) {
-#pragma unroll
-                for (int u = 0; u < N; u++) r[u] *= a[u];
-            }
-#pragma unroll
-            for (int u = 0; u < N; u++) prod[u] *= r[u];
+            for (int u = 0; u < N; u++) prod[u] *= a[u];
         }
 #pragma unroll
-        for (int u = 0; u < N; u++) val[u] += prod[u];
+        for (int u = 0; u < N; u++) val[u] = fma(T.coef, prod[u], val[u]);
     }
 }
 __device__ __forceinline__ double cf_sop_value(double r2, double dt, const cf_sop_val& P, cf_tbl_t tbl_lane) {

@@ -4,6 +4,7 @@
 #include "grad_mvm.cuh"
 #include "cf_extra.cuh"
 #include "gram_mvm_sym.cuh"
+#include "gram_mm_dmma.cuh"
 
 #define CF_NKINDS 4 /* EQ, MATERN, RQ_INT, SOP */
 inline int cf_kind_slot(int kind) {
@@ -23,6 +24,7 @@ struct cf_kernel_entry {
     cf_grad_launch_fn grad[2][3];
     cf_mvm_config grad_cfg[2];
     cf_mm_launch_fn mm[2]; // [dtype]
+    cf_mm_launch_fn mm_dmma; // Float64 tensor-core (DMMA) variant, nullptr when D % 4 != 0 or D < 8
     cf_sym_launch_fn sym[CF_NKINDS]; // Float64 symmetric variant, [kind slot]
 };
 

@@ -76,6 +76,7 @@ SYMBOLS = {
     "cf_cg_solve": (_int, [_vp, _dbl, _vp, _vp, _dbl, _int, _int, C.POINTER(_int), C.POINTER(_dbl)]),
     "cf_last_timing": (_int, [_vp, C.POINTER(C.c_float), C.POINTER(_int)]),
     "cf_peak_probe": (_int, [_int, _int, C.POINTER(_dbl), C.POINTER(C.c_float)]),
+    "cf_jit_stats": (_int, [C.POINTER(_int), C.POINTER(_int), C.POINTER(_int), C.POINTER(_dbl)]),
 }
 
 _lib = None

@@ -17,6 +17,7 @@
 #include "../../include/covfn_b200.h"
 #include "cf_lower.h"
 #include "cf_registry.h"
+#include "cf_jit.h"
 #include "cf_extra.cuh"
 #include "bigd.cuh"
 
@@ -262,6 +263,9 @@ int launch_mm(cf_gramian_s* g, Shard& sh, void* d_B, int64_t ldb, const void* d_
         P.Y = (sh.Y != sh.X) ? sh.yp.p : sh.xp.p;
     }
     const int row_tiles = (int)((nrows + CF_MM_TI - 1) / CF_MM_TI);
+    cfjit::Kernel* jit = nullptr;
+    if (dmma && cfjit::wanted((double)nrows * (double)g->m))
+        jit = cfjit::get_kernel(g->sop_val, "gram_mm_dmma.cuh", "gram_mm_dmma_kernel<" + std::to_string(g->D) + ">");
     for (int64_t c0 = 0; c0 < nrhs; c0 += CF_MM_PC) {
         P.nrhs = (int)std::min<int64_t>(CF_MM_PC, nrhs - c0);
         const dim3 tg((unsigned)((g->m + 31) / 32), CF_MM_PC / 32), tb(32, 8);
@@ -271,7 +275,12 @@ int launch_mm(cf_gramian_s* g, Shard& sh, void* d_B, int64_t ldb, const void* d_
             cf_transpose_rhs<float><<<tg, tb, 0, stream>>>((const float*)d_A + c0 * lda, lda, g->m, P.nrhs, (float*)sh.at.p, ldat);
         CF_CUDA(cudaGetLastError());
         P.B = (char*)d_B + c0 * ldb * es;
-        CF_CUDA((dmma ? g->entry->mm_dmma : g->entry->mm[g->dtype])(P, row_tiles, stream));
+        bool launched = false;
+        if (jit) {  // same kernel source, program structure compiled in (cf_jit.h); any failure falls back to the interpreter build
+            launched = cfjit::launch(jit, &P, (unsigned)row_tiles, 1, 256, (unsigned)g->entry->mm_dmma_smem, stream) == 0;
+            if (!launched) jit = nullptr;
+        }
+        if (!launched) CF_CUDA((dmma ? g->entry->mm_dmma : g->entry->mm[g->dtype])(P, row_tiles, stream));
         g->last_launches += 2;
     }
     return CF_OK;
@@ -732,8 +741,20 @@ int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const v
         if (rc) return rc;
         P.out = sh.partial.p;
     }
-    cf_mvm_launch_fn fn = g->entry->mvm[dt][cf_kind_slot(g->kind)];
-    CF_CUDA(fn(P, dim3(pl.row_tiles, pl.chunks), stream));
+    bool launched = false;
+    if (dt == CF_F64 && g->kind == CF_ATOM_SOP && cfjit::wanted((double)nrows * (double)g->m)) {
+        // composite program, large problem: the same kernel with the program structure compiled in (cf_jit.h)
+        const int* tu = g->entry->tune;
+        const std::string name = "gram_mvm_kernel<double, " + std::to_string(g->D) + ", " + std::to_string((int)CF_ATOM_SOP) + ", " +
+                                 std::to_string(tu[0]) + ", " + std::to_string(tu[1]) + ", " + std::to_string(tu[2]) + ", " +
+                                 std::to_string(tu[3]) + ", " + std::to_string(tu[4]) + ">";
+        if (cfjit::Kernel* jit = cfjit::get_kernel(g->sop_val, "gram_mvm.cuh", name))
+            launched = cfjit::launch(jit, &P, (unsigned)pl.row_tiles, (unsigned)pl.chunks, (unsigned)tu[1], (unsigned)cfg.smem_bytes, stream) == 0;
+    }
+    if (!launched) {
+        cf_mvm_launch_fn fn = g->entry->mvm[dt][cf_kind_slot(g->kind)];
+        CF_CUDA(fn(P, dim3(pl.row_tiles, pl.chunks), stream));
+    }
     g->last_launches++;
     if (!P.direct) {
         const int blocks = (int)std::min<int64_t>((nrows + 255) / 256, 4096);
@@ -1258,6 +1279,16 @@ int cf_peak_probe(int kind, int iters, double* lane_ops_per_s, float* ms) {
     if (cf_device_count() < 1) return fail(CF_ERR_CUDA, "cf_peak_probe: no CUDA device available");
     if (kind < 0 || kind > 2 || iters < 1) return fail(CF_ERR_BAD_ARGUMENT, "cf_peak_probe: bad arguments");
     return peak_probe_impl(kind, iters, lane_ops_per_s, ms);
+}
+
+int cf_jit_stats(int* compiled, int* cache_hits, int* failures, double* compile_seconds) {
+    cfjit::State& st = cfjit::state();
+    std::lock_guard<std::mutex> lk(st.mu);
+    if (compiled) *compiled = st.stats.compiled;
+    if (cache_hits) *cache_hits = st.stats.hits;
+    if (failures) *failures = st.stats.failures;
+    if (compile_seconds) *compile_seconds = st.stats.compile_seconds;
+    return CF_OK;
 }
 
 }  // extern "C"

@@ -354,6 +354,7 @@ __global__ void __launch_bounds__(NTB, 1) gram_mm_kernel(const __grid_constant__
     }
 }
 
+#ifndef __CUDACC_RTC__ // host side: not part of run-time specialised builds
 typedef cudaError_t (*cf_mm_launch_fn)(const cf_mm_params& P, int row_tiles, cudaStream_t stream);
 template <typename T, int D, int NTB, int AGP = CF_MM_AG>
 cudaError_t cf_mm_launch(const cf_mm_params& P, int row_tiles, cudaStream_t stream) {
@@ -371,6 +372,7 @@ cudaError_t cf_mm_launch(const cf_mm_params& P, int row_tiles, cudaStream_t stre
     kern<<<row_tiles, NTB, smem_bytes, stream>>>(P);
     return cudaGetLastError();
 }
+#endif // !__CUDACC_RTC__
 
 // ---- K6: vector helpers for conjugate gradients (Float64) -------------------------------------------------------------
 // z = a x + b y

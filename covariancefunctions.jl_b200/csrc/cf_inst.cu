@@ -34,8 +34,10 @@ const cf_kernel_entry entry = {
     // the same 0.98 s at config 3, so the extra warps are not what limits it -- kept selectable for the next tuning round.
     {&cf_mm_launch<float, D, 512>, &cf_mm_launch<double, D, 256>},
     cf_mmd_entry<D>::fn,
+    cf_mmd_entry<D>::smem,
     {&cf_sym_launch<D, CF_ATOM_EQ, TU::R, TU::NT, TU::TJ, TU::NS, 1>, &cf_sym_launch<D, CF_ATOM_MATERN, TU::R, TU::NT, TU::TJ, TU::NS, 1>,
      &cf_sym_launch<D, CF_ATOM_RQ_INT, TU::R, TU::NT, TU::TJ, TU::NS, 1>, &cf_sym_launch<D, CF_ATOM_SOP, TU::R, TU::NT, TU::TJ, TU::NS, 1>},
+    {TU::R, TU::NT, TU::TJ, TU::NS, TU::MINB},
 };
 }  // namespace
 

@@ -1,0 +1,269 @@
+// cf_jit.h -- run-time specialisation of composite kernel programs (host side, used by capi.cu only).
+//
+// The reference gets a fused, fully specialised evaluation of every kernel composition from Julia's compiler
+// (src/algebra.jl:17,40,62 are inlined per concrete Sum/Product type).  The ahead-of-time kernels here interpret the
+// lowered sum-of-products program instead, which costs ~45 integer/move instructions per pair for a two-term kernel
+// (profiles/r1_ncu_gram_mm_dmma_c3.md).  For large problems the library therefore re-compiles THE SAME hand-written kernel
+// source (embedded at build time, embed_sources.py) with NVRTC, replacing only cf_sop_value_n<N> by a generated body in
+// which atom kinds, integer parameters, powers and the term list are compile-time constants.  Coefficients, length scales
+// and every other real parameter stay in the kernel arguments, so one compilation serves a whole hyper-parameter search.
+//
+// No link-time dependency: libnvrtc and libcuda are dlopen()ed on first use; if either is missing, or compilation fails,
+// the caller keeps using the ahead-of-time kernel (still CUDA -- there is no CPU path).  COVFN_JIT=0 disables, =1 forces
+// specialisation for every composite program, unset = only when one call evaluates >= 2^33 kernel entries.
+#pragma once
+#include <cuda.h>
+#include <dlfcn.h>
+#include <nvrtc.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "cf_program.h"
+#include "cf_jit_sources.inc"
+
+namespace cfjit {
+
+struct Api {
+    bool tried = false, ok = false;
+    std::string why;
+    nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
+    nvrtcResult (*DestroyProgram)(nvrtcProgram*) = nullptr;
+    nvrtcResult (*CompileProgram)(nvrtcProgram, int, const char* const*) = nullptr;
+    nvrtcResult (*GetProgramLogSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetProgramLog)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*GetCUBINSize)(nvrtcProgram, size_t*) = nullptr;
+    nvrtcResult (*GetCUBIN)(nvrtcProgram, char*) = nullptr;
+    nvrtcResult (*AddNameExpression)(nvrtcProgram, const char*) = nullptr;
+    nvrtcResult (*GetLoweredName)(nvrtcProgram, const char*, const char**) = nullptr;
+    CUresult (*LibraryLoadData)(CUlibrary*, const void*, CUjit_option*, void**, unsigned, CUlibraryOption*, void**, unsigned) = nullptr;
+    CUresult (*LibraryGetKernel)(CUkernel*, CUlibrary, const char*) = nullptr;
+    CUresult (*KernelSetAttribute)(CUfunction_attribute, int, CUkernel, CUdevice) = nullptr;
+    CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream, void**,
+                             void**) = nullptr;
+    CUresult (*DeviceGet)(CUdevice*, int) = nullptr;
+};
+
+struct Kernel {
+    CUkernel k = nullptr;
+    bool smem_set[64] = {false};
+};
+
+struct Stats {
+    int compiled = 0, hits = 0, failures = 0;
+    double compile_seconds = 0.0;
+};
+
+struct State {
+    std::mutex mu;
+    Api api;
+    std::map<std::string, Kernel*> cache;  // nullptr entry: compilation failed, do not retry
+    Stats stats;
+};
+inline State& state() {
+    static State s;
+    return s;
+}
+
+template <typename F>
+bool sym(void* h, const char* name, F& out) {
+    out = reinterpret_cast<F>(dlsym(h, name));
+    return out != nullptr;
+}
+
+inline bool load_api(Api& a) {
+    if (a.tried) return a.ok;
+    a.tried = true;
+    void* hn = nullptr;
+    std::vector<std::string> cands;
+    if (const char* e = std::getenv("COVFN_NVRTC_LIB")) cands.push_back(e);
+    cands.insert(cands.end(), {"libnvrtc.so.12", "/usr/local/cuda/lib64/libnvrtc.so.12", "libnvrtc.so"});
+    for (const auto& c : cands)
+        if ((hn = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL))) break;
+    if (!hn) { a.why = "libnvrtc not found"; return false; }
+    void* hc = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
+    if (!hc) { a.why = "libcuda.so.1 not found"; return false; }
+    bool ok = sym(hn, "nvrtcCreateProgram", a.CreateProgram) && sym(hn, "nvrtcDestroyProgram", a.DestroyProgram) &&
+              sym(hn, "nvrtcCompileProgram", a.CompileProgram) && sym(hn, "nvrtcGetProgramLogSize", a.GetProgramLogSize) &&
+              sym(hn, "nvrtcGetProgramLog", a.GetProgramLog) && sym(hn, "nvrtcGetCUBINSize", a.GetCUBINSize) &&
+              sym(hn, "nvrtcGetCUBIN", a.GetCUBIN) && sym(hn, "nvrtcAddNameExpression", a.AddNameExpression) &&
+              sym(hn, "nvrtcGetLoweredName", a.GetLoweredName) && sym(hc, "cuLibraryLoadData", a.LibraryLoadData) &&
+              sym(hc, "cuLibraryGetKernel", a.LibraryGetKernel) && sym(hc, "cuKernelSetAttribute", a.KernelSetAttribute) &&
+              sym(hc, "cuLaunchKernel", a.LaunchKernel) && sym(hc, "cuDeviceGet", a.DeviceGet);
+    if (!ok) a.why = "missing NVRTC / driver entry points";
+    a.ok = ok;
+    return ok;
+}
+
+inline const char* kind_name(int kind) {
+    switch (kind) {
+        case CF_ATOM_EQ: return "CF_ATOM_EQ";
+        case CF_ATOM_MATERN: return "CF_ATOM_MATERN";
+        case CF_ATOM_RQ_INT: return "CF_ATOM_RQ_INT";
+        case CF_ATOM_RQ_REAL: return "CF_ATOM_RQ_REAL";
+        default: return "CF_ATOM_LINE";
+    }
+}
+
+// the structure of a program: everything cf_jit_shape.h bakes in (and nothing else)
+inline std::string shape_key(const cf_sop_val& P) {
+    std::string k = "A";
+    for (int i = 0; i < P.natoms; i++) {
+        const int kind = P.atoms[i].kind;
+        const int ps = (kind == CF_ATOM_MATERN || kind == CF_ATOM_RQ_INT) ? P.atoms[i].p : 0;
+        k += std::to_string(kind) + "." + std::to_string(ps) + ",";
+    }
+    k += "T";
+    for (int t = 0; t < P.nterms; t++) {
+        for (int f = 0; f < P.terms[t].nfac; f++) k += std::to_string(P.terms[t].atom[f]) + "^" + std::to_string(P.terms[t].power[f]) + "*";
+        k += "+";
+    }
+    return k;
+}
+
+// generated cf_jit_shape.h: atoms first (each distinct atom evaluated once per group of N pairs), then the terms
+inline std::string shape_source(const cf_sop_val& P) {
+    std::string s = "// generated by cf_jit.h for program structure " + shape_key(P) + "\n";
+    s += "template <int N>\n__device__ __forceinline__ void cf_sop_value_n(const double (&r2)[N], const double (&dt)[N], "
+         "const cf_sop_val& P, cf_tbl_t tbl_lane, double (&val)[N]) {\n";
+    // highest power needed of each atom decides nothing here: powers are formed per use with static exponents (the compiler
+    // shares common sub-products); an atom is evaluated once
+    for (int i = 0; i < P.natoms; i++) {
+        const int kind = P.atoms[i].kind;
+        const int ps = (kind == CF_ATOM_MATERN || kind == CF_ATOM_RQ_INT) ? P.atoms[i].p : 0;
+        s += "    double a" + std::to_string(i) + "[N];\n";
+        s += "    cf_atom_pow_s<N, " + std::string(kind_name(kind)) + ", " + std::to_string(ps) + ", 1>(r2, dt, P.atoms[" +
+             std::to_string(i) + "], tbl_lane, a" + std::to_string(i) + ");\n";
+    }
+    s += "#pragma unroll\n    for (int u = 0; u < N; u++) {\n        double v = 0.0, p;\n";
+    for (int t = 0; t < P.nterms; t++) {
+        const cf_sop_term& T = P.terms[t];
+        const std::string coef = "P.terms[" + std::to_string(t) + "].coef";
+        if (T.nfac == 0) {
+            s += "        v += " + coef + ";\n";
+            continue;
+        }
+        std::string prod;
+        for (int f = 0; f < T.nfac; f++)
+            for (int q = 0; q < T.power[f]; q++) prod += (prod.empty() ? "" : " * ") + ("a" + std::to_string(T.atom[f]) + "[u]");
+        s += "        p = " + prod + ";\n";
+        s += (t == 0) ? "        v = " + coef + " * p;\n" : "        v = fma(" + coef + ", p, v);\n";
+    }
+    s += "        val[u] = v;\n    }\n}\n";
+    return s;
+}
+
+// Returns the specialised kernel for (shape of P, name_expr), compiling it on first use; nullptr if unavailable.
+inline Kernel* get_kernel(const cf_sop_val& P, const std::string& entry_header, const std::string& name_expr) {
+    State& st = state();
+    std::lock_guard<std::mutex> lk(st.mu);
+    const std::string key = name_expr + "|" + shape_key(P);
+    auto it = st.cache.find(key);
+    if (it != st.cache.end()) {
+        if (it->second) st.stats.hits++;
+        return it->second;
+    }
+    Kernel*& slot = st.cache[key];
+    slot = nullptr;
+    if (!load_api(st.api)) {
+        st.stats.failures++;
+        return nullptr;
+    }
+    Api& a = st.api;
+    const bool verbose = std::getenv("COVFN_JIT_VERBOSE") != nullptr;
+    const std::string shape = shape_source(P);
+    const std::string main_src = "#include \"" + entry_header + "\"\n";
+    std::vector<const char*> names(cf_jit_header_names, cf_jit_header_names + cf_jit_num_headers);
+    std::vector<const char*> srcs(cf_jit_header_srcs, cf_jit_header_srcs + cf_jit_num_headers);
+    names.push_back("cf_jit_shape.h");
+    srcs.push_back(shape.c_str());
+    nvrtcProgram prog = nullptr;
+    struct timespec t0, t1;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    if (a.CreateProgram(&prog, main_src.c_str(), "cf_jit.cu", (int)names.size(), srcs.data(), names.data()) != NVRTC_SUCCESS) {
+        st.stats.failures++;
+        return nullptr;
+    }
+    a.AddNameExpression(prog, name_expr.c_str());
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-DCF_JIT_SHAPE=1"};
+    const nvrtcResult rc = a.CompileProgram(prog, 4, opts);
+    if (rc != NVRTC_SUCCESS) {
+        size_t n = 0;
+        a.GetProgramLogSize(prog, &n);
+        std::string log(n, ' ');
+        if (n) a.GetProgramLog(prog, &log[0]);
+        std::fprintf(stderr, "[covfn_b200] run-time specialisation failed for %s (falling back to the interpreter kernel):\n%s\n%s\n",
+                     key.c_str(), log.c_str(), verbose ? shape.c_str() : "");
+        a.DestroyProgram(&prog);
+        st.stats.failures++;
+        return nullptr;
+    }
+    const char* lowered = nullptr;
+    size_t nb = 0;
+    std::vector<char> cubin;
+    CUlibrary lib = nullptr;
+    CUkernel kern = nullptr;
+    bool ok = a.GetLoweredName(prog, name_expr.c_str(), &lowered) == NVRTC_SUCCESS && lowered &&
+              a.GetCUBINSize(prog, &nb) == NVRTC_SUCCESS && nb > 0;
+    if (ok) {
+        cubin.resize(nb);
+        ok = a.GetCUBIN(prog, cubin.data()) == NVRTC_SUCCESS &&
+             a.LibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == CUDA_SUCCESS &&
+             a.LibraryGetKernel(&kern, lib, lowered) == CUDA_SUCCESS;
+    }
+    a.DestroyProgram(&prog);
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    if (!ok) {
+        std::fprintf(stderr, "[covfn_b200] run-time specialisation: loading the compiled kernel failed for %s\n", key.c_str());
+        st.stats.failures++;
+        return nullptr;
+    }
+    const double secs = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
+    st.stats.compiled++;
+    st.stats.compile_seconds += secs;
+    if (verbose) std::fprintf(stderr, "[covfn_b200] specialised %s in %.2f s\n%s", key.c_str(), secs, shape.c_str());
+    slot = new Kernel();
+    slot->k = kern;
+    return slot;
+}
+
+// launch with one by-value parameter struct (all kernels here take `const __grid_constant__ params P`)
+inline int launch(Kernel* K, const void* params, unsigned gx, unsigned gy, unsigned block, unsigned smem_bytes, cudaStream_t stream) {
+    State& st = state();
+    Api& a = st.api;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(st.mu);
+        if (!K->smem_set[dev & 63]) {
+            CUdevice cd;
+            if (a.DeviceGet(&cd, dev) != CUDA_SUCCESS) return 1;
+            if (a.KernelSetAttribute(CU_FUNC_ATTRIBUTE_MAX_DYNAMIC_SHARED_SIZE_BYTES, (int)smem_bytes, K->k, cd) != CUDA_SUCCESS) return 1;
+            K->smem_set[dev & 63] = true;
+        }
+    }
+    void* args[] = {const_cast<void*>(params)};
+    return a.LaunchKernel(reinterpret_cast<CUfunction>(K->k), gx, gy, 1, block, 1, 1, smem_bytes, reinterpret_cast<CUstream>(stream), args,
+                          nullptr) == CUDA_SUCCESS
+               ? 0
+               : 1;
+}
+
+// policy: 0 = never, 1 = always for composite programs, -1 (unset) = by problem size
+inline int mode() {
+    const char* e = std::getenv("COVFN_JIT");
+    if (!e) return -1;
+    return std::atoi(e) != 0 ? 1 : 0;
+}
+inline bool wanted(double entries_per_call) {
+    const int m = mode();
+    if (m == 0) return false;
+    if (m == 1) return true;
+    return entries_per_call >= 8589934592.0;  // 2^33: ~0.1 s of kernel time, against ~1.5 s of compilation paid once per shape
+}
+
+}  // namespace cfjit

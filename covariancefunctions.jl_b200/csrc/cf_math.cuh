@@ -10,8 +10,10 @@
 // two-step reduction (CF_EXP_ACCURATE) and <= (2 + 0.35 |argument|) ulp with the one-step reduction of the hot loop.
 // FP32: ex2.approx / rsqrt.approx / rcp.approx on the SFU.
 #pragma once
+#ifndef __CUDACC_RTC__
 #include <cuda_runtime.h>
 #include <stdint.h>
+#endif
 #include "cf_program.h"
 
 #define CF_EXP_TBL_BITS 8
@@ -120,14 +122,15 @@ __device__ __forceinline__ double cf_atom_matern(double r2, const cf_atom_val& A
 }
 // N pairs at once: every stage (sqrt, exp, Horner step) is issued for all N values before the next one, so the N
 // dependent chains interleave and the runtime loop over p costs one branch per N values
-template <int N>
+// PS >= 0: the integer parameter is a compile-time constant (run-time specialised builds, cf_jit.h): loops unroll fully
+template <int N, int PS = -1>
 __device__ __forceinline__ void cf_atom_matern_n(const double (&r2)[N], const cf_atom_val& A, cf_tbl_t tbl_lane, double (&out)[N]) {
     double g[N], e[N];
 #pragma unroll
     for (int u = 0; u < N; u++) g[u] = cf_clamp_v(cf_sqrt_pos(r2[u]), A.e);
 #pragma unroll
     for (int u = 0; u < N; u++) e[u] = cf_exp_cv(g[u], A.e, tbl_lane);
-    const int p = A.p;
+    const int p = (PS >= 0) ? PS : A.p;
     if (p == 0) {
 #pragma unroll
         for (int u = 0; u < N; u++) out[u] = e[u];
@@ -136,10 +139,20 @@ __device__ __forceinline__ void cf_atom_matern_n(const double (&r2)[N], const cf
     double mp[N];
 #pragma unroll
     for (int u = 0; u < N; u++) mp[u] = A.mat[p];
-    for (int i = p - 1; i >= 0; i--) {
-        const double ci = A.mat[i];
+    if constexpr (PS >= 0) {
 #pragma unroll
-        for (int u = 0; u < N; u++) mp[u] = fma(mp[u], g[u], ci);
+        for (int i = PS - 1; i >= 0; i--) {
+            const double ci = A.mat[i];
+#pragma unroll
+            for (int u = 0; u < N; u++) mp[u] = fma(mp[u], g[u], ci);
+        }
+    } else {
+#pragma unroll 1
+        for (int i = p - 1; i >= 0; i--) {
+            const double ci = A.mat[i];
+#pragma unroll
+            for (int u = 0; u < N; u++) mp[u] = fma(mp[u], g[u], ci);
+        }
     }
 #pragma unroll
     for (int u = 0; u < N; u++) out[u] = mp[u] * e[u];
@@ -150,14 +163,24 @@ __device__ __forceinline__ double cf_atom_rq_int(double r2, const cf_atom_val& A
     double base = fma(r2, A.w, 1.0);
     return cf_rcp(fmin(cf_powi(base, A.p), 1e300));
 }
-template <int N>
+template <int N, int PS = -1>
 __device__ __forceinline__ void cf_atom_rq_int_n(const double (&r2)[N], const cf_atom_val& A, double (&out)[N]) {
     double base[N], pw[N];
 #pragma unroll
     for (int u = 0; u < N; u++) { base[u] = fma(r2[u], A.w, 1.0); pw[u] = base[u]; }
-    for (int i = 1; i < A.p; i++) {
+    const int p = (PS >= 0) ? PS : A.p;
+    if constexpr (PS >= 0) {
 #pragma unroll
-        for (int u = 0; u < N; u++) pw[u] *= base[u];
+        for (int i = 1; i < PS; i++) {
+#pragma unroll
+            for (int u = 0; u < N; u++) pw[u] *= base[u];
+        }
+    } else {
+#pragma unroll 1
+        for (int i = 1; i < p; i++) {
+#pragma unroll
+            for (int u = 0; u < N; u++) pw[u] *= base[u];
+        }
     }
 #pragma unroll
     for (int u = 0; u < N; u++) out[u] = cf_rcp(fmin(pw[u], 1e300));
@@ -213,6 +236,42 @@ __device__ __forceinline__ void cf_atom_value_dyn_n(const double (&r2)[N], const
             for (int u = 0; u < N; u++) out[u] = dt[u] + A.sigma;
     }
 }
+// out = atom^PW with the atom kind, its integer parameter and the power known at compile time
+template <int N, int KIND, int PS, int PW>
+__device__ __forceinline__ void cf_atom_pow_s(const double (&r2)[N], const double (&dt)[N], const cf_atom_val& A, cf_tbl_t tbl_lane,
+                                              double (&out)[N]) {
+    if constexpr (KIND == CF_ATOM_EQ) {
+#pragma unroll
+        for (int u = 0; u < N; u++) out[u] = cf_atom_eq(r2[u], A, tbl_lane);
+    } else if constexpr (KIND == CF_ATOM_MATERN) {
+        cf_atom_matern_n<N, PS>(r2, A, tbl_lane, out);
+    } else if constexpr (KIND == CF_ATOM_RQ_INT) {
+        cf_atom_rq_int_n<N, PS>(r2, A, out);
+    } else if constexpr (KIND == CF_ATOM_RQ_REAL) {
+#pragma unroll
+        for (int u = 0; u < N; u++) out[u] = cf_atom_rq_real(r2[u], A);
+    } else {
+#pragma unroll
+        for (int u = 0; u < N; u++) out[u] = dt[u] + A.sigma;
+    }
+    if constexpr (PW > 1) {
+        double a[N];
+#pragma unroll
+        for (int u = 0; u < N; u++) a[u] = out[u];
+#pragma unroll
+        for (int q = 1; q < PW; q++) {
+#pragma unroll
+            for (int u = 0; u < N; u++) out[u] *= a[u];
+        }
+    }
+}
+
+#ifdef CF_JIT_SHAPE
+// run-time specialised build (capi.cu, cf_jit.h): the generated header defines cf_sop_value_n<N> for ONE program structure --
+// atom kinds, integer parameters, powers and the term list are compile-time constants, only the coefficients and atom
+// parameters stay in the kernel arguments.  Same signature and same results as the interpreter below.
+#include "cf_jit_shape.h"
+#else
 // out = atom^pw for N pairs (pw >= 1; the common pw = 1, 2 cost no copies)
 template <int N>
 __device__ __forceinline__ void cf_atom_pow_n(const double (&r2)[N], const double (&dt)[N], const cf_atom_val& A, int pw,
@@ -225,6 +284,7 @@ __device__ __forceinline__ void cf_atom_pow_n(const double (&r2)[N], const doubl
         double a[N];
 #pragma unroll
         for (int u = 0; u < N; u++) a[u] = out[u];
+#pragma unroll 1
         for (int q = 1; q < pw; q++) {
 #pragma unroll
             for (int u = 0; u < N; u++) out[u] *= a[u];
@@ -258,6 +318,7 @@ __device__ __forceinline__ void cf_sop_value_n(const double (&r2)[N], const doub
         for (int u = 0; u < N; u++) val[u] = fma(T.coef, prod[u], val[u]);
     }
 }
+#endif // CF_JIT_SHAPE
 __device__ __forceinline__ double cf_sop_value(double r2, double dt, const cf_sop_val& P, cf_tbl_t tbl_lane) {
     double a[1] = {r2}, b[1] = {dt}, v[1];
     cf_sop_value_n<1>(a, b, P, tbl_lane, v);

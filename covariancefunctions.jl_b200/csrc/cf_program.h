@@ -5,7 +5,14 @@
 // sum-of-products instead:   k(x,y) = sum_t coef_t * prod_f atom_f(r2 or x.y)^power_f
 // with ONE r2 and ONE x.y per pair shared by every atom (kernel K3).
 #pragma once
+#ifdef __CUDACC_RTC__ // NVRTC has no system headers
+typedef int int32_t;
+typedef unsigned int uint32_t;
+typedef long long int64_t;
+typedef unsigned long long uint64_t;
+#else
 #include <stdint.h>
+#endif
 
 #define CF_MAX_MATERN_P 12
 #define CF_MAX_TERMS 16

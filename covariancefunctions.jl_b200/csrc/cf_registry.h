@@ -25,7 +25,9 @@ struct cf_kernel_entry {
     cf_mvm_config grad_cfg[2];
     cf_mm_launch_fn mm[2]; // [dtype]
     cf_mm_launch_fn mm_dmma; // Float64 tensor-core (DMMA) variant, nullptr when D % 4 != 0 or D < 8
+    int mm_dmma_smem;        // its dynamic shared memory (run-time specialised launches need it)
     cf_sym_launch_fn sym[CF_NKINDS]; // Float64 symmetric variant, [kind slot]
+    int tune[5];                     // R, NT, TJ, NS, MINB of the value MVM kernel (names the instantiation for cf_jit.h)
 };
 
 // tuning per D: rows per thread R, threads NT, tile TJ, stages NS, min CTAs/SM

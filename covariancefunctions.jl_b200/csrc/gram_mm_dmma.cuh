@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(256, 1) gram_mm_dmma_kernel(const __grid_const
         }
 }
 
+#ifndef __CUDACC_RTC__ // host side: not part of run-time specialised builds
 template <int D>
 cudaError_t cf_mmd_launch(const cf_mm_params& P, int row_tiles, cudaStream_t stream) {
     using S = cf_mmd_smem<D>;
@@ -229,10 +230,11 @@ cudaError_t cf_mmd_launch(const cf_mm_params& P, int row_tiles, cudaStream_t str
 template <int D, bool OK = (D >= 8 && D % 4 == 0)>
 struct cf_mmd_entry {
     static constexpr cf_mm_launch_fn fn = nullptr;
-    static constexpr int sx = 0;
+    static constexpr int sx = 0, smem = 0;
 };
 template <int D>
 struct cf_mmd_entry<D, true> {
     static constexpr cf_mm_launch_fn fn = &cf_mmd_launch<D>;
-    static constexpr int sx = cf_mmd_smem<D>::sx;
+    static constexpr int sx = cf_mmd_smem<D>::sx, smem = cf_mmd_smem<D>::total;
 };
+#endif // !__CUDACC_RTC__

@@ -263,6 +263,7 @@ struct cf_mvm_config {
     int smem_bytes;
     int min_blocks;
 };
+#ifndef __CUDACC_RTC__ // host side: not part of run-time specialised builds
 typedef cudaError_t (*cf_mvm_launch_fn)(const cf_mvm_params& P, dim3 grid, cudaStream_t stream);
 
 template <typename T, int D, int KIND, int R, int NT, int TJ, int NS, int MINB>
@@ -280,3 +281,4 @@ cudaError_t cf_mvm_launch(const cf_mvm_params& P, dim3 grid, cudaStream_t stream
     kern<<<grid, NT, S::total, stream>>>(P);
     return cudaGetLastError();
 }
+#endif // !__CUDACC_RTC__

@@ -333,3 +333,11 @@ def peak_probe(kind: str = "dfma", iters: int = 1 << 16):
     ops, ms = C.c_double(), C.c_float()
     check(lib().cf_peak_probe(code, iters, C.byref(ops), C.byref(ms)))
     return ops.value, ms.value
+
+
+def jit_stats():
+    """Counters of the run-time specialisation of composite kernel programs (csrc/cf_jit.h): kernels compiled, cache hits,
+    failures (each falls back to the ahead-of-time interpreter kernel) and seconds spent compiling, since process start."""
+    c, h, f, t = C.c_int(), C.c_int(), C.c_int(), C.c_double()
+    check(lib().cf_jit_stats(C.byref(c), C.byref(h), C.byref(f), C.byref(t)))
+    return {"compiled": c.value, "cache_hits": h.value, "failures": f.value, "compile_seconds": t.value}

@@ -187,6 +187,12 @@ int cf_last_timing(cf_gramian_t g, float* kernel_ms, int* launches);
 /* measured pipe peaks on the current device: issues `iters` dependent-chain-free FMAs per thread.
  * kind: 0 = FP64 DFMA, 1 = FP32 FFMA, 2 = MUFU.EX2.  Returns lane-instructions per second. */
 int cf_peak_probe(int kind, int iters, double* lane_ops_per_s, float* ms);
+/* Run-time specialisation of composite kernel programs (csrc/cf_jit.h): the reference gets a fused evaluation of every
+ * kernel composition from Julia's compiler (src/algebra.jl:17,40,62 inline per concrete Sum/Product type); here large
+ * multi-RHS products re-compile the same kernel source with the program STRUCTURE as compile-time constants (NVRTC,
+ * once per structure; hyper-parameters stay run-time arguments).  Counters since process start; any pointer may be NULL.
+ * Environment: COVFN_JIT=0 never, =1 always, unset = calls evaluating >= 2^33 entries. */
+int cf_jit_stats(int* compiled, int* cache_hits, int* failures, double* compile_seconds);
 
 #ifdef __cplusplus
 }

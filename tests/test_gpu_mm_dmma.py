@@ -102,3 +102,40 @@ def test_ill_scaled_points_use_direct_differences(cf, O):
     k = cf.EQ()
     G = cf.gramian(k, X.T.copy())
     assert relerr(G @ A, O.mul_mat(k.program(), X, A)) < TOL64
+
+
+def test_runtime_specialised_program_matches_interpreter(cf, O):
+    """COVFN_JIT=1 re-compiles the DMMA kernel with the program structure as compile-time constants (csrc/cf_jit.h).  The
+    specialised and the interpreted evaluation must agree with the oracle and with each other for every structure."""
+    rng = np.random.default_rng(31)
+    n, m, d, p = 300, 260, 16, 7
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    Y = rng.standard_normal((m, d)) / np.sqrt(d)
+    A = rng.standard_normal((m, p))
+    ks = dict(_kernels(cf))
+    ks["matern5_x_line"] = cf.MaternP(5) * (cf.Dot() + 0.5) + 2.0 * cf.RQ(3)
+    ks["rq_real"] = cf.RQ(0.7) + cf.Exp()
+    ks["square_of_sum"] = (cf.EQ() + cf.RQ(1)) ** 2
+    before = cf.jit_stats()
+    os.environ["COVFN_JIT"] = "1"
+    try:
+        for name, k in ks.items():
+            G = cf.gramian(k, X.T.copy(), Y.T.copy())
+            Bj = G @ A
+            os.environ["COVFN_JIT"] = "0"
+            Bi = G @ A
+            os.environ["COVFN_JIT"] = "1"
+            ref = O.mul_mat(k.program(), X, A, Y=Y)
+            assert relerr(Bj, ref) < TOL64, name
+            assert relerr(Bj, Bi) < 1e-13, name
+        # same structure, different hyper-parameters: served from the cache, no new compilation
+        mid = cf.jit_stats()
+        k2 = 0.25 * cf.Lengthscale(cf.RQ(2), 1.7) + 3.0 * cf.Dot() ** 2
+        G = cf.gramian(k2, X.T.copy(), Y.T.copy())
+        assert relerr(G @ A, O.mul_mat(k2.program(), X, A, Y=Y)) < TOL64
+        after = cf.jit_stats()
+    finally:
+        del os.environ["COVFN_JIT"]
+    assert mid["failures"] == before["failures"], "run-time specialisation fell back to the interpreter"
+    assert mid["compiled"] - before["compiled"] >= 1
+    assert after["compiled"] == mid["compiled"] and after["cache_hits"] > mid["cache_hits"]

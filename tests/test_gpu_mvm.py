@@ -222,3 +222,33 @@ def test_ard_lengthscales(cf):
         assert relerr(G @ a, M @ a) < 1e-12
         assert relerr(G.Matrix(), M) < 1e-13
     assert isinstance(cf.ARD(cf.EQ(), 2.0), cf.Lengthscale)  # ARD(k, l::Real) = Lengthscale(k, l)
+
+
+def test_runtime_specialised_mvm_matches_interpreter(cf, O):
+    """composite-kernel MVM with the program structure compiled in at run time (COVFN_JIT=1, csrc/cf_jit.h) against the
+    interpreter kernel and the oracle, for row tiles of every R (d = 3: R = 4, d = 8: R = 2, d = 20: R = 1)"""
+    import os
+    rng = np.random.default_rng(41)
+    for d in (3, 8, 20):
+        n, m = 700, 1100
+        X = rng.standard_normal((n, d)) / np.sqrt(d)
+        Y = rng.standard_normal((m, d)) / np.sqrt(d)
+        a = rng.standard_normal(m)
+        for k in (0.5 * cf.EQ() + cf.MaternP(2) * cf.RQ(2), cf.Exp() + 0.1 * (cf.Dot() + 1.0) ** 2, (cf.EQ() + cf.RQ(1.5)) ** 2):
+            G = cf.gramian(k, X.T.copy(), Y.T.copy())
+            before = cf.jit_stats()
+            os.environ["COVFN_JIT"] = "1"
+            try:
+                bj = G @ a
+            finally:
+                os.environ["COVFN_JIT"] = "0"
+            try:
+                bi = G @ a
+            finally:
+                del os.environ["COVFN_JIT"]
+            after = cf.jit_stats()
+            assert after["failures"] == before["failures"]
+            assert after["compiled"] + after["cache_hits"] > before["compiled"] + before["cache_hits"]
+            ref = O.mul_vec(k.program(), X, a, Y=Y)
+            assert relerr(bj, ref) < TOL64 and relerr(bi, ref) < TOL64
+            assert relerr(bj, bi) < 1e-13

@@ -31,7 +31,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SLOTS = {"c1": 35, "c2": 23, "c3": 111, "c4": 97, "c5": 45, "x1": 80}  # FP64 issue slots per pair/block
+SLOTS = {"c1": 35, "c2": 23, "c3": 111, "c4": 97, "c5": 45, "x1": 80, "x2": 81, "x3": 61}  # FP64 issue slots per pair/block
 
 
 def workload(name):
@@ -52,6 +52,12 @@ def workload(name):
     if name == "x1":  # not a BASELINE config: composite-kernel MVM used to measure the interpreter vs run-time specialisation
         return dict(kernel=0.5 * cf.EQ() + cf.MaternP(2) * cf.RQ(2), kname="1/2*EQ+MaternP(2)*RQ(2)", d=3, n=262144, nrhs=1,
                     gradient=False, desc="composite-kernel Gramian MVM, d=3, n=262144, Float64 (auxiliary)")
+    if name == "x2":  # auxiliary: high-dimensional single-RHS MVM (README.md:369-395 shape at larger n)
+        return dict(kernel=cf.EQ(), kname="EQ", d=32, n=131072, nrhs=1, gradient=False,
+                    desc="EQ Gramian MVM, d=32, n=131072, Float64 (auxiliary)")
+    if name == "x3":
+        return dict(kernel=cf.MaternP(2), kname="MaternP(2)", d=16, n=131072, nrhs=1, gradient=False,
+                    desc="MaternP(2) Gramian MVM, d=16, n=131072, Float64 (auxiliary)")
     raise SystemExit(f"unknown config {name}")
 
 

@@ -1013,6 +1013,10 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
         const double eps = dtype == CF_F64 ? 2.220446049250313e-16 : 1.1920928955078125e-07;
         const double bound = dtype == CF_F64 ? 1e-13 : 1e-5;
         g->use_norms = (d >= 8) && ((d + 2) * eps * 2.0 * max_sq < bound);
+        // exp(-sqrt(r2)) (Exp = MaternP(0)) is not differentiable in r2 at 0: an absolute error of 1e-16 in r2 of coincident points
+        // (the diagonal of every symmetric Gramian) becomes 1e-8 in k.  Kernels with that atom keep direct differences.
+        for (int i = 0; i < g->prog.natoms; i++)
+            if (g->prog.atoms[i].v.kind == CF_ATOM_MATERN && g->prog.atoms[i].v.p == 0) g->use_norms = false;
     }
     (void)es;
     split_rows(g);

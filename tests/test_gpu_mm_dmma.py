@@ -139,3 +139,23 @@ def test_runtime_specialised_program_matches_interpreter(cf, O):
     assert mid["failures"] == before["failures"], "run-time specialisation fell back to the interpreter"
     assert mid["compiled"] - before["compiled"] >= 1
     assert after["compiled"] == mid["compiled"] and after["cache_hits"] > mid["cache_hits"]
+
+
+def test_sqrt_kernels_on_symmetric_gramians_keep_direct_differences(cf, O):
+    """Exp = exp(-sqrt(r2)) has an infinite derivative in r2 at 0, so the norm expansion (error ~1e-16 in r2 on the diagonal of a
+    symmetric Gramian) would cost 1e-8 in k: such programs must not use it.  MaternP(p >= 1) is smooth in r2 and may."""
+    rng = np.random.default_rng(17)
+    n, d, p = 400, 16, 6
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    X[7] = X[5] + 1e-9 * rng.standard_normal(d)  # a near-duplicate: r2 ~ 1e-17, far below the rounding error of the norm expansion
+    A = rng.standard_normal((n, p))
+    for k in (cf.Exp(), cf.MaternP(0) * cf.RQ(2), 0.3 * cf.Exp() + cf.EQ(), cf.MaternP(1), cf.MaternP(3)):
+        G = cf.gramian(k, X.T.copy())
+        B = G @ A
+        ref = O.mul_mat(k.program(), X, A)
+        assert relerr(B, ref) < TOL64
+        # entry-wise: K_55 must be k(0) and K_75 = k(x_7, x_5) to rounding, not k(1e-8)
+        a1 = np.zeros(n); a1[5] = 1.0
+        col = G @ np.stack([a1, a1], axis=1)
+        assert abs(col[5, 0] - k(X[5], X[5])) < 1e-13
+        assert abs(col[7, 0] - k(X[7], X[5])) < 1e-13

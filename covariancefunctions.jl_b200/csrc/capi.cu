@@ -219,6 +219,21 @@ int launch_dense(cf_gramian_s* g, Shard& sh, void* d_M, int64_t ld, int64_t j0, 
     return CF_OK;
 }
 
+// point copies with the row stride (= 4 mod 8 doubles) the DMMA kernels read fragments from, built once per shard
+int ensure_padded_points(cf_gramian_s* g, Shard& sh, cudaStream_t stream) {
+    if (sh.mmd_ready) return CF_OK;
+    const int sx = (g->D % 8 == 4) ? g->D : g->D + 4;
+    if (int rc = sh.xp.ensure((size_t)g->n * sx * 8)) return rc;
+    cf_pad_rows_kernel<<<148 * 8, 256, 0, stream>>>((const double*)sh.X, g->D, sx, g->n, (double*)sh.xp.p);
+    if (sh.Y != sh.X) {
+        if (int rc = sh.yp.ensure((size_t)g->m * sx * 8)) return rc;
+        cf_pad_rows_kernel<<<148 * 8, 256, 0, stream>>>((const double*)sh.Y, g->D, sx, g->m, (double*)sh.yp.p);
+    }
+    CF_CUDA(cudaGetLastError());
+    sh.mmd_ready = true;
+    return CF_OK;
+}
+
 static bool env_flag(const char* name) {
     const char* e = std::getenv(name);
     return e && std::atoi(e) != 0;
@@ -248,17 +263,7 @@ int launch_mm(cf_gramian_s* g, Shard& sh, void* d_B, int64_t ldb, const void* d_
     P.use_norms = g->use_norms ? 1 : 0;
     P.ldat = ldat;
     if (dmma) {
-        const int sx = (g->D % 8 == 4) ? g->D : g->D + 4;
-        if (!sh.mmd_ready) {
-            if (int rc = sh.xp.ensure((size_t)g->n * sx * 8)) return rc;
-            cf_pad_rows_kernel<<<148 * 8, 256, 0, stream>>>((const double*)sh.X, g->D, sx, g->n, (double*)sh.xp.p);
-            if (sh.Y != sh.X) {
-                if (int rc = sh.yp.ensure((size_t)g->m * sx * 8)) return rc;
-                cf_pad_rows_kernel<<<148 * 8, 256, 0, stream>>>((const double*)sh.Y, g->D, sx, g->m, (double*)sh.yp.p);
-            }
-            CF_CUDA(cudaGetLastError());
-            sh.mmd_ready = true;
-        }
+        if (int rc = ensure_padded_points(g, sh, stream)) return rc;
         P.X = sh.xp.p;
         P.Y = (sh.Y != sh.X) ? sh.yp.p : sh.xp.p;
     }
@@ -704,6 +709,49 @@ int launch_mvm_sym(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin,
 }
 
 // one column of  y <- alpha K a + beta y  on one shard; device pointers; asynchronous on sh.stream
+int launch_mvm_dmma(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, const double* d_a, double alpha, double beta,
+                    cudaStream_t stream, const cf_peer_out* peers) {
+    const int64_t nrows = sh.r1 - sh.r0;
+    const cf_mvm_config& cfg = g->entry->mvm_dmma_cfg;
+    const int slot = cf_kind_slot(g->kind);
+    if (int rc = ensure_padded_points(g, sh, stream)) return rc;
+    Plan pl = make_plan(nrows, g->m, cfg, sh.ctx->sms);
+    cf_mvm_params P;
+    std::memset(&P, 0, sizeof(P));
+    P.X = sh.xp.p; P.Y = (sh.Y != sh.X) ? sh.yp.p : sh.xp.p; P.xn = sh.xn; P.yn = sh.yn; P.a = d_a;
+    P.exp2_tbl = sh.ctx->exp2_tbl;
+    P.sop = g->sop_val;
+    P.row0 = sh.r0; P.nrows = nrows; P.m = g->m;
+    P.cols_per_chunk = pl.cols_per_chunk;
+    P.alpha = alpha * g->coef; P.beta = beta;
+    P.use_tma = (((uintptr_t)d_a) % 16 == 0) ? 1 : 0;
+    if (g->prog.single) P.atom = g->prog.atoms[g->prog.terms[0].fac[0].atom].v;
+    P.direct = (pl.chunks == 1) ? 1 : 0;
+    P.peers = *peers;
+    if (P.direct) {
+        P.out = d_y; P.yin = d_yin;
+    } else {
+        if (int rc = sh.partial.ensure((size_t)pl.chunks * nrows * sizeof(double))) return rc;
+        P.out = sh.partial.p;
+    }
+    bool launched = false;
+    if (g->kind == CF_ATOM_SOP && cfjit::wanted((double)nrows * (double)g->m)) {
+        const std::string name = "gram_mvm_dmma_kernel<" + std::to_string(g->D) + ", " + std::to_string((int)CF_ATOM_SOP) + ">";
+        if (cfjit::Kernel* jit = cfjit::get_kernel(g->sop_val, "gram_mvm_dmma.cuh", name))
+            launched = cfjit::launch(jit, &P, (unsigned)pl.row_tiles, (unsigned)pl.chunks, 256, (unsigned)cfg.smem_bytes, stream) == 0;
+    }
+    if (!launched) CF_CUDA(g->entry->mvm_dmma[slot](P, dim3(pl.row_tiles, pl.chunks), stream));
+    g->last_launches++;
+    if (!P.direct) {
+        const int blocks = (int)std::min<int64_t>((nrows + 255) / 256, 4096);
+        gram_reduce_partials<double><<<blocks, 256, 0, stream>>>((const double*)sh.partial.p, pl.chunks, nrows, d_y, d_yin,
+                                                                  alpha * g->coef, beta, *peers);
+        CF_CUDA(cudaGetLastError());
+        g->last_launches++;
+    }
+    return CF_OK;
+}
+
 int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const void* d_a, double alpha, double beta,
                cudaStream_t stream, const cf_peer_out* peers) {
     cf_peer_out no_peers;
@@ -721,6 +769,11 @@ int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const v
     if (g->opt_symmetric && g->symmetric && dt == CF_F64 && sh.r0 == 0 && sh.r1 == g->n && g->n >= 65536 &&
         (((uintptr_t)d_a) % 16) == 0)
         return launch_mvm_sym(g, sh, (double*)d_y, (const double*)d_yin, (const double*)d_a, alpha, beta, stream);
+    // high-dimensional, well-scaled Float64 points: pair distances on the FP64 tensor cores (gram_mvm_dmma.cuh);
+    // COVFN_MVM_SCALAR=1 keeps the scalar kernel
+    const int slot = cf_kind_slot(g->kind);
+    const bool dmma = dt == CF_F64 && g->use_norms && g->entry->mvm_dmma[slot] != nullptr && !env_flag("COVFN_MVM_SCALAR");
+    if (dmma) return launch_mvm_dmma(g, sh, (double*)d_y, (const double*)d_yin, (const double*)d_a, alpha, beta, stream, peers);
     Plan pl = make_plan(nrows, g->m, cfg, sh.ctx->sms);
     cf_mvm_params P;
     std::memset(&P, 0, sizeof(P));

@@ -5,6 +5,7 @@
 #include "cf_extra.cuh"
 #include "gram_mvm_sym.cuh"
 #include "gram_mm_dmma.cuh"
+#include "gram_mvm_dmma.cuh"
 
 #define CF_NKINDS 4 /* EQ, MATERN, RQ_INT, SOP */
 inline int cf_kind_slot(int kind) {
@@ -27,6 +28,8 @@ struct cf_kernel_entry {
     cf_mm_launch_fn mm_dmma; // Float64 tensor-core (DMMA) variant, nullptr when D % 4 != 0 or D < 8
     int mm_dmma_smem;        // its dynamic shared memory (run-time specialised launches need it)
     cf_sym_launch_fn sym[CF_NKINDS]; // Float64 symmetric variant, [kind slot]
+    cf_mvm_launch_fn mvm_dmma[CF_NKINDS]; // Float64 tensor-core value MVM (gram_mvm_dmma.cuh), nullptr when unavailable for D
+    cf_mvm_config mvm_dmma_cfg;
     int tune[5];                     // R, NT, TJ, NS, MINB of the value MVM kernel (names the instantiation for cf_jit.h)
 };
 

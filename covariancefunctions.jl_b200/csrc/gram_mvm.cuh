@@ -45,6 +45,8 @@ struct cf_mvm_params {
     cf_atom_val atom;     // the single atom (specialised kinds)
     cf_sop_val sop;       // generic sum of products (KIND == CF_ATOM_SOP)
     cf_peer_out peers;    // direct mode: also store the finished rows into these peer vectors
+    const void* xn;       // squared norms of the rows / columns (tensor-core variant gram_mvm_dmma.cuh only; X, Y then point at
+    const void* yn;       // the point copies with the padded row stride)
 };
 
 // ---- mbarrier / TMA 1-D bulk copy wrappers (PTX ISA: cp.async.bulk, mbarrier) ------------------------------
@@ -72,6 +74,13 @@ __device__ __forceinline__ void cf_mbar_wait(uint64_t* bar, uint32_t parity) {
         "}" ::"r"(cf_smem_u32(bar)),
         "r"(parity)
         : "memory");
+}
+
+__device__ __forceinline__ double cf_shfl_xor_f64(double v, int mask) {
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_xor_sync(0xffffffffu, lo, mask);
+    hi = __shfl_xor_sync(0xffffffffu, hi, mask);
+    return __hiloint2double(hi, lo);
 }
 
 // shared memory carve-up (bytes)

@@ -35,13 +35,6 @@ struct cf_sym_params {
     cf_sop_val sop;
 };
 
-__device__ __forceinline__ double cf_shfl_xor_f64(double v, int mask) {
-    int lo = __double2loint(v), hi = __double2hiint(v);
-    lo = __shfl_xor_sync(0xffffffffu, lo, mask);
-    hi = __shfl_xor_sync(0xffffffffu, hi, mask);
-    return __hiloint2double(hi, lo);
-}
-
 template <int D, int KIND, int R, int NT, int TJ, int NS, int MINB>
 __global__ void __launch_bounds__(NT, MINB) gram_mvm_sym_kernel(const __grid_constant__ cf_sym_params P) {
     using S = cf_mvm_smem<double, D, TJ, NS>;

@@ -78,3 +78,31 @@ def test_cg_spmd_matches_single_device(cf, O):
     M = O.matrix(k.program(), X) + 0.1 * np.eye(n)
     assert np.linalg.norm(M @ x2 - y) / np.linalg.norm(y) < 1e-6
     assert np.linalg.norm((Gg @ xs) - Ka) / np.linalg.norm(Ka) < 1e-6
+
+
+def test_runtime_specialised_and_tensor_core_kernels_on_two_devices(cf, O, two_gpus):
+    """the run-time specialised kernels are loaded once (cuLibraryLoadData) and launched on both devices' streams; the
+    tensor-core kernels keep one padded point copy per device"""
+    import os
+    rng = np.random.default_rng(77)
+    n, d, p = 2500, 16, 5
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    a = rng.standard_normal(n)
+    A = rng.standard_normal((n, p))
+    k = 0.5 * cf.EQ() + cf.MaternP(2) * cf.RQ(2)
+    before = cf.jit_stats()
+    os.environ["COVFN_JIT"] = "1"
+    try:
+        G = cf.gramian(k, X.T.copy())
+        b = G @ a
+        B = G @ A
+        X3 = rng.standard_normal((n, 3))
+        G3 = cf.gramian(k, X3.T.copy())
+        b3 = G3 @ a
+    finally:
+        del os.environ["COVFN_JIT"]
+    after = cf.jit_stats()
+    assert after["failures"] == before["failures"]
+    assert relerr(b, O.mul_vec(k.program(), X, a)) < 1e-12
+    assert relerr(B, O.mul_mat(k.program(), X, A)) < 1e-12
+    assert relerr(b3, O.mul_vec(k.program(), X3, a)) < 1e-12

@@ -1065,11 +1065,21 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
     {
         const double eps = dtype == CF_F64 ? 2.220446049250313e-16 : 1.1920928955078125e-07;
         const double bound = dtype == CF_F64 ? 1e-13 : 1e-5;
-        g->use_norms = (d >= 8) && ((d + 2) * eps * 2.0 * max_sq < bound);
-        // exp(-sqrt(r2)) (Exp = MaternP(0)) is not differentiable in r2 at 0: an absolute error of 1e-16 in r2 of coincident points
-        // (the diagonal of every symmetric Gramian) becomes 1e-8 in k.  Kernels with that atom keep direct differences.
-        for (int i = 0; i < g->prog.natoms; i++)
-            if (g->prog.atoms[i].v.kind == CF_ATOM_MATERN && g->prog.atoms[i].v.p == 0) g->use_norms = false;
+        // ... times the largest |dk/dr2| of the program's r2-atoms (short length scales amplify an absolute error in r2):
+        // EQ exp(c r2): |c|;  MaternP(p >= 1): |d_1| / l^2 (its slope at 0, the maximum);  RQ (1 + w r2)^-a: a w.
+        // exp(-sqrt(r2)) (Exp = MaternP(0)) is not differentiable in r2 at 0: an absolute error of 1e-16 in r2 of (nearly)
+        // coincident points would become 1e-8 in k, so programs with that atom always keep direct differences.
+        // LINE atoms use x.y, which the tensor-core chain reproduces exactly.
+        double slope = 1.0;
+        bool sqrt_atom = false;
+        for (int i = 0; i < g->prog.natoms; i++) {
+            const cf_atom& A = g->prog.atoms[i];
+            if (A.v.kind == CF_ATOM_EQ) slope = std::max(slope, std::fabs(A.v.e.c));
+            else if (A.v.kind == CF_ATOM_MATERN && A.v.p == 0) sqrt_atom = true;
+            else if (A.v.kind == CF_ATOM_MATERN) slope = std::max(slope, std::fabs(A.tay[1]) * A.inv_l2);
+            else if (A.v.kind == CF_ATOM_RQ_INT || A.v.kind == CF_ATOM_RQ_REAL) slope = std::max(slope, A.v.alpha * A.v.w);
+        }
+        g->use_norms = (d >= 8) && !sqrt_atom && ((d + 2) * eps * 2.0 * max_sq * slope < bound);
     }
     (void)es;
     split_rows(g);

@@ -109,3 +109,21 @@ def test_cg_on_tensor_core_operator_matches_scalar(cf, O):
     assert relerr(x1, x2) < 1e-8 and abs(it1 - it2) <= max(3, it2 // 20)
     K = O.matrix(k.program(), X, X)
     assert relerr(K @ x1 + 1e-2 * x1, y) < 1e-8
+
+
+def test_short_length_scales_disable_the_norm_expansion(cf, O):
+    """|dk/dr2| grows like 1/l^2: with l = 0.02 an absolute error of 1e-15 in r2 would be 1e-12 in k, so the library must keep
+    direct differences (bit-identical to the scalar kernel) -- and stay within tolerance either way"""
+    rng = np.random.default_rng(19)
+    n, d = 600, 16
+    X = rng.standard_normal((n, d)) / np.sqrt(d) * 0.05  # clustered points so that k is not all zeros at l = 0.02
+    a = rng.standard_normal(n)
+    A = rng.standard_normal((n, 3))
+    for k in (cf.Lengthscale(cf.EQ(), 0.02), cf.Lengthscale(cf.MaternP(2), 0.02), cf.Lengthscale(cf.RQ(2), 0.02)):
+        G = cf.gramian(k, (X / 0.05).T.copy())  # unit-scale points, short length scale
+        b = G @ a
+        assert np.array_equal(b, _scalar(lambda: G @ a))
+        assert relerr(b, O.mul_vec(k.program(), X / 0.05, a)) < TOL64
+        G2 = cf.gramian(k, X.T.copy())          # points scaled with the length scale: the expansion is safe again
+        assert relerr(G2 @ a, O.mul_vec(k.program(), X, a)) < TOL64
+        assert relerr(G2 @ A, O.mul_mat(k.program(), X, A)) < TOL64

@@ -124,7 +124,7 @@ struct Shard {
     void* Y = nullptr;  // m x D (== X when symmetric)
     void* xn = nullptr;  // squared norms of the padded points (multi-RHS kernel)
     void* yn = nullptr;
-    Buf a, y, partial, apad, ypad, at, cg[6], sym_items, bsym, bd_t, bd_s, xp, yp;
+    Buf a, y, partial, apad, ypad, at, cg[6], sym_items, bsym, bd_t, bd_s, xp, yp, ap;
     bool mmd_ready = false; // xp / yp hold the padded point copies of the DMMA multi-RHS kernel
     int sym_nitems = 0;
     int64_t r0 = 0, r1 = 0; // rows owned
@@ -137,6 +137,7 @@ struct cf_gramian_s {
     int64_t n = 0, m = 0;
     bool symmetric = false;
     bool use_norms = false; // multi-RHS kernel may use r2 = |x|^2 + |y|^2 - 2 x.y (well-scaled data, d >= 8)
+    bool use_norms_grad = false; // ... and so may the isotropic gradient operator (stricter: needs k'')
     int64_t row_begin = 0, row_end = 0;
     cf_program prog;
     cf_sop_val sop_val;    // parameter-resident program for the value kernels
@@ -838,6 +839,44 @@ int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, co
         return CF_OK;
     }
     if (!g->entry) return launch_bigd_grad(g, sh, d_y, d_yin, d_a, alpha, beta, stream);
+    {   // isotropic GradientKernel on well-scaled Float64 points: every d-dependent operation on the FP64 tensor cores
+        // (grad_mvm_dmma.cuh); COVFN_GRAD_SCALAR=1 keeps the scalar kernel
+        const bool eq = g->prog.single && g->prog.atoms[g->prog.terms[0].fac[0].atom].v.kind == CF_ATOM_EQ;
+        cf_gradd_launch_fn fn = g->entry->grad_dmma[eq ? 0 : 1];
+        if (!vg && !g->prog.dotproduct && g->use_norms_grad && fn && !env_flag("COVFN_GRAD_SCALAR")) {
+            if (int rc = ensure_padded_points(g, sh, stream)) return rc;
+            const int sx = (D % 8 == 4) ? D : D + 4;
+            const cf_mvm_config& cfgd = g->entry->grad_dmma_cfg;
+            Plan pl = make_plan(nrows, g->m, cfgd, sh.ctx->sms);
+            const size_t q_off = (((size_t)g->m * sx + 1) / 2) * 2;  // q follows the padded weights, 16-byte aligned (TMA source)
+            if (int rc = sh.ap.ensure((q_off + (size_t)g->m + 2) * sizeof(double))) return rc;
+            if (int rc = sh.partial.ensure((size_t)pl.chunks * nrows * D * sizeof(double))) return rc;
+            double* ap = (double*)sh.ap.p;
+            const double* yp = (const double*)((sh.Y != sh.X) ? sh.yp.p : sh.xp.p);
+            cf_pad_points<double><<<(int)std::min<int64_t>((g->m * sx + 255) / 256, 8192), 256, 0, stream>>>(d_a, d, d, ap, sx, g->m);
+            cf_rowdot_kernel<<<(int)std::min<int64_t>((g->m + 255) / 256, 4096), 256, 0, stream>>>(yp, ap, sx, g->m, ap + q_off);
+            CF_CUDA(cudaGetLastError());
+            cf_gradd_params PP;
+            std::memset(&PP, 0, sizeof(PP));
+            cf_grad_params& P = PP.g;
+            P.X = (const double*)sh.xp.p; P.Y = yp; P.a = ap;
+            P.partial = (double*)sh.partial.p;
+            P.exp2_tbl = sh.ctx->exp2_tbl;
+            P.sop = g->sop_grad;
+            P.row0 = sh.r0; P.nrows = nrows; P.m = g->m; P.cols_per_chunk = pl.cols_per_chunk;
+            P.single = g->prog.single;
+            P.coef = g->coef_grad;
+            if (g->prog.single) P.atom = g->prog.atoms[g->prog.terms[0].fac[0].atom];
+            PP.xn = (const double*)sh.xn; PP.yn = (const double*)sh.yn; PP.q = ap + q_off;
+            CF_CUDA(fn(PP, dim3(pl.row_tiles, pl.chunks), stream));
+            const int blocks = (int)std::min<int64_t>((nrows * d + 255) / 256, 8192);
+            grad_reduce_partials<<<blocks, 256, 0, stream>>>((const double*)sh.partial.p, nullptr, pl.chunks, nrows, D, d, 0, d_y, d_yin,
+                                                             alpha, beta, *peers);
+            CF_CUDA(cudaGetLastError());
+            g->last_launches += 4;
+            return CF_OK;
+        }
+    }
     const cf_mvm_config& cfg = g->entry->grad_cfg[vg];
     Plan pl = make_plan(nrows, g->m, cfg, sh.ctx->sms);
     const double* a_use = d_a;
@@ -1080,6 +1119,11 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
             else if (A.v.kind == CF_ATOM_RQ_INT || A.v.kind == CF_ATOM_RQ_REAL) slope = std::max(slope, A.v.alpha * A.v.w);
         }
         g->use_norms = (d >= 8) && !sqrt_atom && ((d + 2) * eps * 2.0 * max_sq * slope < bound);
+        // the derivative operators also need k'' (one more factor of the slope) and MaternP(1) has a 1/sqrt(r2) term in k''
+        bool smooth2 = true;
+        for (int i = 0; i < g->prog.natoms; i++)
+            if (g->prog.atoms[i].v.kind == CF_ATOM_MATERN && g->prog.atoms[i].v.p < 2) smooth2 = false;
+        g->use_norms_grad = g->use_norms && smooth2 && ((d + 2) * eps * 2.0 * max_sq * slope * slope < bound);
     }
     (void)es;
     split_rows(g);

@@ -1,0 +1,90 @@
+"""Parity of the Float64 tensor-core isotropic gradient-kernel MVM (csrc/grad_mvm_dmma.cuh, padded D in {8, 16, 24, 32},
+well-scaled points) against the oracle and against the scalar kernel K5 it replaces.  Reference semantics:
+blockmul!(y, G::Gramian, x, alpha, beta) src/gramian.jl:241-253 with mul!(b, ::IsotropicGradientKernelElement, a, alpha, beta)
+src/gradient.jl:86-92; the shapes follow test/gradient.jl:29-52 (lazy operator vs dense matrix, 5-argument mul!)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import relerr
+
+pytestmark = pytest.mark.gpu
+
+TOL64 = 1e-12
+
+
+def _scalar(fn):
+    os.environ["COVFN_GRAD_SCALAR"] = "1"
+    try:
+        return fn()
+    finally:
+        del os.environ["COVFN_GRAD_SCALAR"]
+
+
+def _kernels(cf):
+    return {
+        "eq": cf.EQ(),
+        "eq_ls": 0.7 * cf.Lengthscale(cf.EQ(), 1.3),
+        "matern2": cf.MaternP(2),
+        "matern3": cf.MaternP(3),
+        "rq2": cf.RQ(2),
+        "rq_real": cf.RQ(1.7),
+        "eq_plus_rq": cf.EQ() + 0.5 * cf.RQ(2),
+        "eq_times_matern": cf.EQ() * cf.MaternP(2),
+        "matern1": cf.MaternP(1),  # k'' has a 1/sqrt(r2) term: must stay on the direct-difference kernel
+    }
+
+
+@pytest.mark.parametrize("d", [8, 16, 24, 32])
+def test_grad_dmma_dims_ragged_rectangular(cf, O, d):
+    rng = np.random.default_rng(300 + d)
+    n, m = 203, 301  # neither a multiple of the 128-row / 32-column tiles
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    Y = rng.standard_normal((m, d)) / np.sqrt(d)
+    a = rng.standard_normal(m * d)
+    for name, k in _kernels(cf).items():
+        G = cf.gramian(cf.GradientKernel(k), X.T.copy(), Y.T.copy())
+        b = G @ a
+        ref = O.gradient_mul(k.program(), X, a, Y=Y)
+        assert relerr(b, ref) < TOL64, (d, name)
+        bs = _scalar(lambda: G @ a)
+        assert relerr(b, bs) < 1e-13, (d, name)
+        if name == "matern1":
+            assert np.array_equal(b, bs), "MaternP(1) gradient operators must not use the norm expansion"
+        elif name == "eq":
+            assert not np.array_equal(b, bs), "expected the tensor-core kernel"
+
+
+def test_grad_dmma_alpha_beta_rows_duplicates(cf, O):
+    rng = np.random.default_rng(33)
+    n, d = 1500, 16  # several column chunks -> partial buffer + reduction
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    X[1::2] = X[0::2]  # exact duplicates: r2 and r.a must vanish exactly, no spurious 1e-16 / 1e-16
+    k = cf.MaternP(2)
+    G = cf.gramian(cf.GradientKernel(k), X.T.copy())
+    a = rng.standard_normal(n * d)
+    b0 = rng.standard_normal(n * d)
+    b = b0.copy()
+    cf.mul_(b, G, a, 0.3, -1.1)
+    assert relerr(b, O.gradient_mul(k.program(), X, a, alpha=0.3, beta=-1.1, y0=b0)) < TOL64
+    full = G @ a
+    assert np.array_equal(full, G @ a)  # run-to-run bit-identical
+    G.set_row_range(100, 900)
+    part = G @ a
+    assert part.shape == (800 * d,) and relerr(part, full[100 * d:900 * d]) < 1e-14
+
+
+def test_grad_dmma_dense_operator_and_symmetry(cf, O):
+    # test/gradient.jl:35-45: the lazy operator equals the dense (n d) x (n d) matrix, which is symmetric
+    rng = np.random.default_rng(35)
+    n, d = 40, 8
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    k = cf.EQ()
+    G = cf.gramian(cf.GradientKernel(k), X.T.copy())
+    M = O.gradient_matrix(k.program(), X)
+    E = np.eye(n * d)
+    cols = np.stack([G @ E[:, j] for j in range(0, n * d, 37)], axis=1)
+    assert relerr(cols, M[:, ::37]) < TOL64
+    u, v = rng.standard_normal(n * d), rng.standard_normal(n * d)
+    assert abs(u @ (G @ v) - v @ (G @ u)) < 1e-12 * np.linalg.norm(u) * np.linalg.norm(v) * np.linalg.norm(M, 2)

@@ -110,8 +110,9 @@ __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_cons
         for (int cb = 0; cb < NCB; cb++) out[rb][cb][0] = out[rb][cb][1] = 0.0;
     __syncthreads();
 
+    const double eq_ca = -2.0 * P.atom.v.e.c, eq_cw = -4.0 * P.atom.v.e.c * P.atom.v.e.c;  // EQ: ca = -2 c k, cw = -4 c^2 k (r.a)
     auto tile_compute = [&](const double* __restrict__ ys, const double* __restrict__ as, const double* __restrict__ yns,
-                            const double* __restrict__ qs, int cnt) {
+                            const double* __restrict__ qs, int cnt, const bool ragged) {
         {   // phase A: Dot = Xs . Ys^T and Pa = Xs . As^T share the X fragments
             double c[2][4][2], p[2][4][2];
 #pragma unroll
@@ -153,12 +154,19 @@ __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_cons
                     const double v = fma(-2.0, c[rb][u >> 1][u & 1], xnorm[rb] + yn8[u]);
                     const double r2 = (__double2hiint(v) < 0) ? 0.0 : v;
                     const double sdot = p[rb][u >> 1][u & 1] - q8[u];  // r . a_j
-                    double k, k1, k2;
-                    if constexpr (KIND == CF_ATOM_EQ) cf_atom_jet_t<CF_ATOM_EQ>(r2, P.atom, tbl_lane, k, k1, k2);
-                    else if (P.single) cf_atom_jet(r2, P.atom, tbl_lane, k, k1, k2);
-                    else cf_sop_jet(r2, P.sop, tbl_lane, k, k1, k2);
-                    double ca = -2.0 * k1, cw = -4.0 * k2 * sdot;
-                    if (col >= cnt) { ca = 0.0; cw = 0.0; }  // past the end of a ragged tile: no contribution
+                    double ca, cw;
+                    if constexpr (KIND == CF_ATOM_EQ) {  // k = exp(c r2), k1 = c k, k2 = c^2 k: constants folded
+                        const double k = cf_exp_cv(r2, P.atom.v.e, tbl_lane);
+                        ca = eq_ca * k;
+                        cw = (eq_cw * k) * sdot;
+                    } else {
+                        double k, k1, k2;
+                        if (P.single) cf_atom_jet(r2, P.atom, tbl_lane, k, k1, k2);
+                        else cf_sop_jet(r2, P.sop, tbl_lane, k, k1, k2);
+                        ca = -2.0 * k1;
+                        cw = -4.0 * k2 * sdot;
+                    }
+                    if (ragged && col >= cnt) { ca = 0.0; cw = 0.0; }  // past the end of a ragged tile: no contribution
                     cwsum[rb] += cw;
                     Cc[col * SC + row] = ca;
                     Cc[(TJ + col) * SC + row] = -cw;
@@ -188,7 +196,7 @@ __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_cons
         const unsigned char* st = stages + (size_t)s * S::stage_bytes;
         tile_compute(reinterpret_cast<const double*>(st), reinterpret_cast<const double*>(st + S::y_bytes),
                      reinterpret_cast<const double*>(st + 2 * S::y_bytes),
-                     reinterpret_cast<const double*>(st + 2 * S::y_bytes + S::n_bytes), TJ);
+                     reinterpret_cast<const double*>(st + 2 * S::y_bytes + S::n_bytes), TJ, false);
         __syncthreads();  // Cc and stage s are free again
         if (tid == 0 && t + NS < nfull) issue(t + NS);
     }
@@ -208,7 +216,7 @@ __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_cons
             qs[q] = (q < cnt) ? PP.q[j0 + q] : 0.0;
         }
         __syncthreads();
-        tile_compute(ys, as, yns, qs, cnt);
+        tile_compute(ys, as, yns, qs, cnt, true);
         __syncthreads();
     }
 

@@ -844,8 +844,8 @@ int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, co
         const bool eq = g->prog.single && g->prog.atoms[g->prog.terms[0].fac[0].atom].v.kind == CF_ATOM_EQ;
         cf_gradd_launch_fn fn = g->entry->grad_dmma[eq ? 0 : 1];
         // (below ~2^22 blocks the two extra preparation launches cost more than the tensor cores save)
-        if (!vg && !g->prog.dotproduct && g->use_norms_grad && fn && (double)nrows * (double)g->m >= 4194304.0 &&
-            !env_flag("COVFN_GRAD_SCALAR")) {
+        if (!vg && !g->prog.dotproduct && g->use_norms_grad && fn &&
+            ((double)nrows * (double)g->m >= 4194304.0 || env_flag("COVFN_GRAD_DMMA")) && !env_flag("COVFN_GRAD_SCALAR")) {
             if (int rc = ensure_padded_points(g, sh, stream)) return rc;
             const int sx = (D % 8 == 4) ? D : D + 4;
             const cf_mvm_config& cfgd = g->entry->grad_dmma_cfg;

@@ -14,6 +14,14 @@ pytestmark = pytest.mark.gpu
 TOL64 = 1e-12
 
 
+@pytest.fixture(autouse=True)
+def _force_tensor_core_kernel():
+    # the library only selects the tensor-core kernel above 2^22 blocks per call; the parity tests use small sizes
+    os.environ["COVFN_GRAD_DMMA"] = "1"
+    yield
+    del os.environ["COVFN_GRAD_DMMA"]
+
+
 def _scalar(fn):
     os.environ["COVFN_GRAD_SCALAR"] = "1"
     try:

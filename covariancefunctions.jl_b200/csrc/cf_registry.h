@@ -45,7 +45,7 @@ template <int D> struct cf_tune {
     static constexpr int NS = 3;
     static constexpr int MINB = (D <= 8) ? 2 : 1;
     // gradient kernel
-    static constexpr int GR = (D <= 4 || D == 16) ? 2 : 1; // D = 16: 253 registers, no spills, +2.5 % at config 4
+    static constexpr int GR = (D <= 4) ? 2 : 1; // (D = 16 with 2 rows: +2.5 % at n = 65536 but -45 % at n = 1024: fewer, larger CTAs)
     static constexpr int GNT = (D <= 8) ? 256 : 128;
     static constexpr int GTJ = (D <= 8) ? 128 : (D <= 16 ? 64 : 32);
     static constexpr int GMINB = (D <= 6) ? 2 : 1;

@@ -78,6 +78,7 @@ bool sym(void* h, const char* name, F& out) {
 inline bool load_api(Api& a) {
     if (a.tried) return a.ok;
     a.tried = true;
+    if (std::getenv("COVFN_JIT_TEST_NO_NVRTC")) { a.why = "disabled for testing"; return false; }  // exercises the fallback path
     void* hn = nullptr;
     std::vector<std::string> cands;
     if (const char* e = std::getenv("COVFN_NVRTC_LIB")) cands.push_back(e);

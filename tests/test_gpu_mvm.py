@@ -252,3 +252,27 @@ def test_runtime_specialised_mvm_matches_interpreter(cf, O):
             ref = O.mul_vec(k.program(), X, a, Y=Y)
             assert relerr(bj, ref) < TOL64 and relerr(bi, ref) < TOL64
             assert relerr(bj, bi) < 1e-13
+
+
+def test_runtime_specialisation_unavailable_falls_back_to_interpreter_kernel():
+    """without libnvrtc the library must keep using the ahead-of-time (interpreter) CUDA kernel and count a failure --
+    run in a subprocess because the library probes NVRTC once per process"""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, covfn_b200 as cf\n"
+        "from oracle import oracle as O\n"
+        "rng = np.random.default_rng(3)\n"
+        "X = rng.standard_normal((500, 3)); a = rng.standard_normal(500)\n"
+        "k = 0.5 * cf.EQ() + cf.MaternP(2) * cf.RQ(2)\n"
+        "b = cf.gramian(k, X.T.copy()) @ a\n"
+        "ref = O.mul_vec(k.program(), X, a)\n"
+        "s = cf.jit_stats()\n"
+        "assert np.linalg.norm(b - ref) / np.linalg.norm(ref) < 1e-12\n"
+        "assert s['compiled'] == 0 and s['failures'] >= 1, s\n"
+        "print('fallback ok')\n")
+    env = dict(os.environ, COVFN_JIT="1", COVFN_JIT_TEST_NO_NVRTC="1")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "fallback ok" in out.stdout, out.stderr[-2000:]

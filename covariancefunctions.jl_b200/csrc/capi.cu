@@ -842,27 +842,31 @@ int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, co
     {   // isotropic GradientKernel on well-scaled Float64 points: every d-dependent operation on the FP64 tensor cores
         // (grad_mvm_dmma.cuh); COVFN_GRAD_SCALAR=1 keeps the scalar kernel
         const bool eq = g->prog.single && g->prog.atoms[g->prog.terms[0].fac[0].atom].v.kind == CF_ATOM_EQ;
-        cf_gradd_launch_fn fn = g->entry->grad_dmma[eq ? 0 : 1];
-        // (below ~2^22 blocks the two extra preparation launches cost more than the tensor cores save)
-        if (!vg && !g->prog.dotproduct && g->use_norms_grad && fn &&
+        cf_gradd_launch_fn fn = g->entry->grad_dmma[vg][eq ? 0 : 1];
+        // (below ~2^22 blocks the extra preparation launches cost more than the tensor cores save)
+        if (!g->prog.dotproduct && g->use_norms_grad && fn &&
             ((double)nrows * (double)g->m >= 4194304.0 || env_flag("COVFN_GRAD_DMMA")) && !env_flag("COVFN_GRAD_SCALAR")) {
             if (int rc = ensure_padded_points(g, sh, stream)) return rc;
             const int sx = (D % 8 == 4) ? D : D + 4;
             const cf_mvm_config& cfgd = g->entry->grad_dmma_cfg;
             Plan pl = make_plan(nrows, g->m, cfgd, sh.ctx->sms);
-            const size_t q_off = (((size_t)g->m * sx + 1) / 2) * 2;  // q follows the padded weights, 16-byte aligned (TMA source)
-            if (int rc = sh.ap.ensure((q_off + (size_t)g->m + 2) * sizeof(double))) return rc;
-            if (int rc = sh.partial.ensure((size_t)pl.chunks * nrows * D * sizeof(double))) return rc;
+            // padded gradient weights, then q_j = y_j . a_j, then the value weights (ValueGradient): all 16-byte aligned TMA sources
+            const size_t q_off = (((size_t)g->m * sx + 1) / 2) * 2;
+            const size_t a0_off = q_off + (((size_t)g->m + 1) / 2) * 2;
+            if (int rc = sh.ap.ensure((a0_off + (size_t)g->m + 2) * sizeof(double))) return rc;
+            if (int rc = sh.partial.ensure((size_t)pl.chunks * nrows * (D + 1) * sizeof(double))) return rc;
             double* ap = (double*)sh.ap.p;
             const double* yp = (const double*)((sh.Y != sh.X) ? sh.yp.p : sh.xp.p);
-            cf_pad_points<double><<<(int)std::min<int64_t>((g->m * sx + 255) / 256, 8192), 256, 0, stream>>>(d_a, d, d, ap, sx, g->m);
+            cf_pad_points<double><<<(int)std::min<int64_t>((g->m * sx + 255) / 256, 8192), 256, 0, stream>>>(d_a + vg, bs, d, ap, sx, g->m);
             cf_rowdot_kernel<<<(int)std::min<int64_t>((g->m + 255) / 256, 4096), 256, 0, stream>>>(yp, ap, sx, g->m, ap + q_off);
+            if (vg) cf_pad_points<double><<<(int)std::min<int64_t>((g->m + 255) / 256, 8192), 256, 0, stream>>>(d_a, bs, 1, ap + a0_off, 1, g->m);
             CF_CUDA(cudaGetLastError());
             cf_gradd_params PP;
             std::memset(&PP, 0, sizeof(PP));
             cf_grad_params& P = PP.g;
-            P.X = (const double*)sh.xp.p; P.Y = yp; P.a = ap;
+            P.X = (const double*)sh.xp.p; P.Y = yp; P.a = ap; P.a0 = vg ? ap + a0_off : nullptr;
             P.partial = (double*)sh.partial.p;
+            P.partial0 = (double*)sh.partial.p + (size_t)pl.chunks * nrows * D;
             P.exp2_tbl = sh.ctx->exp2_tbl;
             P.sop = g->sop_grad;
             P.row0 = sh.r0; P.nrows = nrows; P.m = g->m; P.cols_per_chunk = pl.cols_per_chunk;
@@ -871,11 +875,11 @@ int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, co
             if (g->prog.single) P.atom = g->prog.atoms[g->prog.terms[0].fac[0].atom];
             PP.xn = (const double*)sh.xn; PP.yn = (const double*)sh.yn; PP.q = ap + q_off;
             CF_CUDA(fn(PP, dim3(pl.row_tiles, pl.chunks), stream));
-            const int blocks = (int)std::min<int64_t>((nrows * d + 255) / 256, 8192);
-            grad_reduce_partials<<<blocks, 256, 0, stream>>>((const double*)sh.partial.p, nullptr, pl.chunks, nrows, D, d, 0, d_y, d_yin,
+            const int blocks = (int)std::min<int64_t>((nrows * bs + 255) / 256, 8192);
+            grad_reduce_partials<<<blocks, 256, 0, stream>>>((const double*)sh.partial.p, P.partial0, pl.chunks, nrows, D, d, vg, d_y, d_yin,
                                                              alpha, beta, *peers);
             CF_CUDA(cudaGetLastError());
-            g->last_launches += 4;
+            g->last_launches += 4 + vg;
             return CF_OK;
         }
     }

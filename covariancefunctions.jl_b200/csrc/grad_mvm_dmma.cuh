@@ -36,7 +36,7 @@ struct cf_gd_smem {
     static constexpr int cc_bytes = 2 * CF_GD_TJ * CF_GD_SC * 8;  // Cc[0..31] = ca, Cc[32..63] = -cw
     static constexpr int y_bytes = CF_GD_TJ * sx * 8;
     static constexpr int n_bytes = CF_GD_TJ * 8;
-    static constexpr int stage_bytes = ((2 * y_bytes + 2 * n_bytes + 127) / 128) * 128;  // y | a | yn | q
+    static constexpr int stage_bytes = ((2 * y_bytes + 3 * n_bytes + 127) / 128) * 128;  // y | a | yn | q | a0 (value weights, VG)
     static constexpr int total = tbl_bytes + bar_bytes + xs_bytes + cc_bytes + CF_GD_NS * stage_bytes;
 };
 
@@ -49,7 +49,9 @@ static __global__ void cf_rowdot_kernel(const double* __restrict__ Y, const doub
     }
 }
 
-template <int D, int KIND>
+// VG = true: ValueGradientKernel, blocks (d+1) x (d+1) with entry 0 the value observation (reference src/gradient.jl:442-463):
+//   b_g += ca a_g + cw r with cw = -4 k2 (r.a_g) + 2 k1 a_0,   b_0 += k a_0 - 2 k1 (r.a_g)   -- two more per-entry FMAs and a row sum
+template <int D, int KIND, bool VG>
 __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_constant__ cf_gradd_params PP) {
     using S = cf_gd_smem<D>;
     constexpr int SX = S::sx, SC = CF_GD_SC, NTB = 256, TJ = CF_GD_TJ, TI = CF_GD_TI, NS = CF_GD_NS, NCB = D / 8;
@@ -79,11 +81,12 @@ __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_cons
         const int s = tile % NS;
         unsigned char* st = stages + (size_t)s * S::stage_bytes;
         const int64_t j0 = c0 + (int64_t)tile * TJ;
-        cf_mbar_expect_tx(&bars[s], (uint32_t)(2 * S::y_bytes + 2 * S::n_bytes));
+        cf_mbar_expect_tx(&bars[s], (uint32_t)(2 * S::y_bytes + (VG ? 3 : 2) * S::n_bytes));
         cf_tma_load_1d(st, P.Y + j0 * SX, (uint32_t)S::y_bytes, &bars[s]);
         cf_tma_load_1d(st + S::y_bytes, P.a + j0 * SX, (uint32_t)S::y_bytes, &bars[s]);
         cf_tma_load_1d(st + 2 * S::y_bytes, PP.yn + j0, (uint32_t)S::n_bytes, &bars[s]);
         cf_tma_load_1d(st + 2 * S::y_bytes + S::n_bytes, PP.q + j0, (uint32_t)S::n_bytes, &bars[s]);
+        if (VG) cf_tma_load_1d(st + 2 * S::y_bytes + 2 * S::n_bytes, P.a0 + j0, (uint32_t)S::n_bytes, &bars[s]);
     };
     if (tid == 0)
         for (int t = 0; t < NS && t < nfull; t++) issue(t);
@@ -96,7 +99,7 @@ __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_cons
         if (ir >= rend) ir = rend - 1;
         Xs[q] = P.X[ir * SX + (q - row * SX)];
     }
-    double xnorm[2], cwsum[2] = {0.0, 0.0};  // this lane's rows in both phases: 16 w + 8 rb + g
+    double xnorm[2], cwsum[2] = {0.0, 0.0}, b0sum[2] = {0.0, 0.0};  // this lane's rows in both phases: 16 w + 8 rb + g
 #pragma unroll
     for (int rb = 0; rb < 2; rb++) {
         int64_t i = rbase + 16 * w + 8 * rb + g;
@@ -112,7 +115,7 @@ __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_cons
 
     const double eq_ca = -2.0 * P.atom.v.e.c, eq_cw = -4.0 * P.atom.v.e.c * P.atom.v.e.c;  // EQ: ca = -2 c k, cw = -4 c^2 k (r.a)
     auto tile_compute = [&](const double* __restrict__ ys, const double* __restrict__ as, const double* __restrict__ yns,
-                            const double* __restrict__ qs, int cnt, const bool ragged) {
+                            const double* __restrict__ qs, const double* __restrict__ a0s, int cnt, const bool ragged) {
         {   // phase A: Dot = Xs . Ys^T and Pa = Xs . As^T share the X fragments
             double c[2][4][2], p[2][4][2];
 #pragma unroll
@@ -137,13 +140,17 @@ __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_cons
                         cf_dmma884(p[rb][cb], a[rb], ba[cb]);
                     }
             }
-            double yn8[8], q8[8];  // this lane's columns: 8 cb + 2 t4 + e
+            double yn8[8], q8[8], a08[VG ? 8 : 1];  // this lane's columns: 8 cb + 2 t4 + e
 #pragma unroll
             for (int cb = 0; cb < 4; cb++) {
                 const double2 v = *reinterpret_cast<const double2*>(&yns[8 * cb + 2 * t4]);
                 const double2 z = *reinterpret_cast<const double2*>(&qs[8 * cb + 2 * t4]);
                 yn8[2 * cb] = v.x; yn8[2 * cb + 1] = v.y;
                 q8[2 * cb] = z.x; q8[2 * cb + 1] = z.y;
+                if constexpr (VG) {
+                    const double2 z0 = *reinterpret_cast<const double2*>(&a0s[8 * cb + 2 * t4]);
+                    a08[2 * cb] = z0.x; a08[2 * cb + 1] = z0.y;
+                }
             }
 #pragma unroll
             for (int rb = 0; rb < 2; rb++) {
@@ -154,17 +161,23 @@ __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_cons
                     const double v = fma(-2.0, c[rb][u >> 1][u & 1], xnorm[rb] + yn8[u]);
                     const double r2 = (__double2hiint(v) < 0) ? 0.0 : v;
                     const double sdot = p[rb][u >> 1][u & 1] - q8[u];  // r . a_j
-                    double ca, cw;
+                    double ca, cw, kval = 0.0;
                     if constexpr (KIND == CF_ATOM_EQ) {  // k = exp(c r2), k1 = c k, k2 = c^2 k: constants folded
-                        const double k = cf_exp_cv(r2, P.atom.v.e, tbl_lane);
-                        ca = eq_ca * k;
-                        cw = (eq_cw * k) * sdot;
+                        kval = cf_exp_cv(r2, P.atom.v.e, tbl_lane);
+                        ca = eq_ca * kval;
+                        cw = (eq_cw * kval) * sdot;
                     } else {
-                        double k, k1, k2;
-                        if (P.single) cf_atom_jet(r2, P.atom, tbl_lane, k, k1, k2);
-                        else cf_sop_jet(r2, P.sop, tbl_lane, k, k1, k2);
+                        double k1, k2;
+                        if (P.single) cf_atom_jet(r2, P.atom, tbl_lane, kval, k1, k2);
+                        else cf_sop_jet(r2, P.sop, tbl_lane, kval, k1, k2);
                         ca = -2.0 * k1;
                         cw = -4.0 * k2 * sdot;
+                    }
+                    if constexpr (VG) {  // ca = -2 k1 also multiplies the value weight into cw and r.a_g into the value row
+                        double v0 = fma(kval, a08[u], ca * sdot);
+                        if (ragged && col >= cnt) v0 = 0.0;
+                        b0sum[rb] += v0;
+                        cw = fma(-ca, a08[u], cw);
                     }
                     if (ragged && col >= cnt) { ca = 0.0; cw = 0.0; }  // past the end of a ragged tile: no contribution
                     cwsum[rb] += cw;
@@ -196,7 +209,8 @@ __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_cons
         const unsigned char* st = stages + (size_t)s * S::stage_bytes;
         tile_compute(reinterpret_cast<const double*>(st), reinterpret_cast<const double*>(st + S::y_bytes),
                      reinterpret_cast<const double*>(st + 2 * S::y_bytes),
-                     reinterpret_cast<const double*>(st + 2 * S::y_bytes + S::n_bytes), TJ, false);
+                     reinterpret_cast<const double*>(st + 2 * S::y_bytes + S::n_bytes),
+                     reinterpret_cast<const double*>(st + 2 * S::y_bytes + 2 * S::n_bytes), TJ, false);
         __syncthreads();  // Cc and stage s are free again
         if (tid == 0 && t + NS < nfull) issue(t + NS);
     }
@@ -206,6 +220,7 @@ __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_cons
         double* as = reinterpret_cast<double*>(stages + S::y_bytes);
         double* yns = reinterpret_cast<double*>(stages + 2 * S::y_bytes);
         double* qs = reinterpret_cast<double*>(stages + 2 * S::y_bytes + S::n_bytes);
+        double* a0s = reinterpret_cast<double*>(stages + 2 * S::y_bytes + 2 * S::n_bytes);
         __syncthreads();
         for (int q = tid; q < TJ * SX; q += NTB) {
             ys[q] = (q < cnt * SX) ? P.Y[j0 * SX + q] : 0.0;
@@ -214,9 +229,10 @@ __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_cons
         for (int q = tid; q < TJ; q += NTB) {
             yns[q] = (q < cnt) ? PP.yn[j0 + q] : 0.0;
             qs[q] = (q < cnt) ? PP.q[j0 + q] : 0.0;
+            if (VG) a0s[q] = (q < cnt) ? P.a0[j0 + q] : 0.0;
         }
         __syncthreads();
-        tile_compute(ys, as, yns, qs, cnt, true);
+        tile_compute(ys, as, yns, qs, a0s, cnt, true);
         __syncthreads();
     }
 
@@ -226,6 +242,10 @@ __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_cons
     for (int rb = 0; rb < 2; rb++) {
         cwsum[rb] += cf_shfl_xor_f64(cwsum[rb], 1);
         cwsum[rb] += cf_shfl_xor_f64(cwsum[rb], 2);
+        if constexpr (VG) {
+            b0sum[rb] += cf_shfl_xor_f64(b0sum[rb], 1);
+            b0sum[rb] += cf_shfl_xor_f64(b0sum[rb], 2);
+        }
         const int row = 16 * w + 8 * rb + g;
         const int64_t i = rbase + row;
         if (i >= rend) continue;
@@ -237,15 +257,16 @@ __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_cons
                 const int cidx = 8 * cb + 2 * t4 + e;
                 o[cidx] = coef * fma(Xs[row * SX + cidx], cwsum[rb], out[rb][cb][e]);
             }
+        if (VG && t4 == 0) P.partial0[(int64_t)blockIdx.y * P.nrows + (i - P.row0)] = coef * b0sum[rb];
     }
 }
 
 #ifndef __CUDACC_RTC__ // host side
 typedef cudaError_t (*cf_gradd_launch_fn)(const cf_gradd_params& P, dim3 grid, cudaStream_t stream);
-template <int D, int KIND>
+template <int D, int KIND, bool VG>
 cudaError_t cf_gradd_launch(const cf_gradd_params& P, dim3 grid, cudaStream_t stream) {
     using S = cf_gd_smem<D>;
-    auto kern = grad_mvm_dmma_kernel<D, KIND>;
+    auto kern = grad_mvm_dmma_kernel<D, KIND, VG>;
     static bool configured[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -261,12 +282,13 @@ cudaError_t cf_gradd_launch(const cf_gradd_params& P, dim3 grid, cudaStream_t st
 // registry hook: padded dimensions that are multiples of 8 (output fragments are 8 coordinates wide)
 template <int D, bool OK = (D >= 8 && D % 8 == 0)>
 struct cf_gradd_entry {
-    static constexpr cf_gradd_launch_fn fn[2] = {nullptr, nullptr};  // [0] EQ specialised, [1] generic isotropic
+    static constexpr cf_gradd_launch_fn fn[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [value_gradient][0 EQ specialised, 1 generic isotropic]
     static constexpr cf_mvm_config cfg = {CF_GD_TI, CF_GD_TJ, 0, 1};
 };
 template <int D>
 struct cf_gradd_entry<D, true> {
-    static constexpr cf_gradd_launch_fn fn[2] = {&cf_gradd_launch<D, CF_ATOM_EQ>, &cf_gradd_launch<D, CF_ATOM_SOP>};
+    static constexpr cf_gradd_launch_fn fn[2][2] = {{&cf_gradd_launch<D, CF_ATOM_EQ, false>, &cf_gradd_launch<D, CF_ATOM_SOP, false>},
+                                                    {&cf_gradd_launch<D, CF_ATOM_EQ, true>, &cf_gradd_launch<D, CF_ATOM_SOP, true>}};
     static constexpr cf_mvm_config cfg = {CF_GD_TI, CF_GD_TJ, cf_gd_smem<D>::total, 1};
 };
 #endif // !__CUDACC_RTC__

@@ -96,3 +96,32 @@ def test_grad_dmma_dense_operator_and_symmetry(cf, O):
     assert relerr(cols, M[:, ::37]) < TOL64
     u, v = rng.standard_normal(n * d), rng.standard_normal(n * d)
     assert abs(u @ (G @ v) - v @ (G @ u)) < 1e-12 * np.linalg.norm(u) * np.linalg.norm(v) * np.linalg.norm(M, 2)
+
+
+@pytest.mark.parametrize("d", [8, 16, 32])
+def test_value_gradient_dmma(cf, O, d):
+    """ValueGradientKernel blocks (d+1) x (d+1) (reference src/gradient.jl:400-474) on the tensor-core kernel"""
+    rng = np.random.default_rng(400 + d)
+    n, m = 150, 333
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    Y = rng.standard_normal((m, d)) / np.sqrt(d)
+    a = rng.standard_normal(m * (d + 1))
+    for name, k in _kernels(cf).items():
+        G = cf.gramian(cf.ValueGradientKernel(k), X.T.copy(), Y.T.copy())
+        b = G @ a
+        ref = O.derivative_mul(k.program(), X, a, Y=Y, trait="isotropic", value_gradient=True)
+        assert relerr(b, ref) < TOL64, (d, name)
+        bs = _scalar(lambda: G @ a)
+        assert relerr(b, bs) < 1e-13, (d, name)
+        if name == "eq":
+            assert not np.array_equal(b, bs), "expected the tensor-core kernel"
+    # alpha / beta and a symmetric operator with duplicates
+    Xs = X.copy()
+    Xs[1::2] = Xs[0::2]
+    k = cf.MaternP(2)
+    G = cf.gramian(cf.ValueGradientKernel(k), Xs.T.copy())
+    v = rng.standard_normal(n * (d + 1))
+    b0 = rng.standard_normal(n * (d + 1))
+    b = b0.copy()
+    cf.mul_(b, G, v, -0.7, 0.4)
+    assert relerr(b, O.derivative_mul(k.program(), Xs, v, trait="isotropic", value_gradient=True, alpha=-0.7, beta=0.4, y0=b0)) < TOL64

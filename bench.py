@@ -31,7 +31,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SLOTS = {"c1": 35, "c2": 23, "c3": 111, "c4": 97, "c5": 45, "x1": 80, "x2": 81, "x3": 61, "x4": 45}  # FP64 issue slots per pair/block
+SLOTS = {"c1": 35, "c2": 23, "c3": 111, "c4": 97, "c5": 45, "x1": 80, "x2": 81, "x3": 61, "x4": 45, "x5": 110}  # FP64 issue slots per pair/block
 
 
 def workload(name):
@@ -61,6 +61,9 @@ def workload(name):
     if name == "x4":  # auxiliary: the MVM inside BASELINE config 5 (CG), at a quarter of its n
         return dict(kernel=cf.MaternP(2), kname="MaternP(2)", d=8, n=131072, nrhs=1, gradient=False,
                     desc="MaternP(2) Gramian MVM, d=8, n=131072, Float64 (auxiliary; config 5's operator)")
+    if name == "x5":  # auxiliary: gradient operator of a non-EQ kernel (generic jets)
+        return dict(kernel=cf.MaternP(2), kname="GradientKernel(MaternP(2))", d=16, n=32768, nrhs=1, gradient=True,
+                    desc="GradientKernel(MaternP(2)) MVM, d=16, n=32768, Float64 (auxiliary)")
     raise SystemExit(f"unknown config {name}")
 
 

@@ -842,7 +842,9 @@ int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, co
     {   // isotropic GradientKernel on well-scaled Float64 points: every d-dependent operation on the FP64 tensor cores
         // (grad_mvm_dmma.cuh); COVFN_GRAD_SCALAR=1 keeps the scalar kernel
         const bool eq = g->prog.single && g->prog.atoms[g->prog.terms[0].fac[0].atom].v.kind == CF_ATOM_EQ;
-        cf_gradd_launch_fn fn = g->entry->grad_dmma[vg][eq ? 0 : 1];
+        const bool matern = g->prog.single && g->prog.atoms[g->prog.terms[0].fac[0].atom].v.kind == CF_ATOM_MATERN &&
+                            g->prog.atoms[g->prog.terms[0].fac[0].atom].v.p >= 2;
+        cf_gradd_launch_fn fn = g->entry->grad_dmma[vg][eq ? 0 : (matern ? 2 : 1)];
         // (below ~2^22 blocks the extra preparation launches cost more than the tensor cores save)
         if (!g->prog.dotproduct && g->use_norms_grad && fn &&
             ((double)nrows * (double)g->m >= 4194304.0 || env_flag("COVFN_GRAD_DMMA")) && !env_flag("COVFN_GRAD_SCALAR")) {

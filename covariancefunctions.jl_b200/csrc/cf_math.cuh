@@ -375,6 +375,64 @@ __device__ __forceinline__ void cf_atom_jet(double r2, const cf_atom& A, cf_tbl_
     }
 }
 
+// jets of N pairs of ONE Matern atom with p >= 2 (k' and k'' have no singular terms): every stage is issued for all N values, the
+// loops over p are uniform.  The reference's Taylor branch for r2 / l^2 < eps^(1/p) (src/stationary.jl:139-146) is evaluated
+// only by the lanes that have such an entry (coincident points) and selected per entry.
+template <int N>
+__device__ __forceinline__ void cf_matern_jet_n(const double (&r2)[N], const cf_atom& A, cf_tbl_t tbl_lane, double (&k)[N],
+                                                double (&k1)[N], double (&k2)[N]) {
+    double g[N], e[N], m[N], a[N], b[N];
+#pragma unroll
+    for (int u = 0; u < N; u++) g[u] = cf_clamp_v(cf_sqrt_pos(r2[u]), A.v.e);
+#pragma unroll
+    for (int u = 0; u < N; u++) e[u] = cf_exp_cv(g[u], A.v.e, tbl_lane);
+    const int p = A.v.p;
+#pragma unroll
+    for (int u = 0; u < N; u++) { m[u] = A.v.mat[p]; a[u] = A.matA[p - 1]; b[u] = A.matB[p - 2]; }
+#pragma unroll 1
+    for (int i = p - 1; i >= 0; i--) {
+        const double ci = A.v.mat[i];
+#pragma unroll
+        for (int u = 0; u < N; u++) m[u] = fma(m[u], g[u], ci);
+    }
+#pragma unroll 1
+    for (int i = p - 2; i >= 0; i--) {
+        const double ci = A.matA[i];
+#pragma unroll
+        for (int u = 0; u < N; u++) a[u] = fma(a[u], g[u], ci);
+    }
+#pragma unroll 1
+    for (int i = p - 3; i >= 0; i--) {
+        const double ci = A.matB[i];
+#pragma unroll
+        for (int u = 0; u < N; u++) b[u] = fma(b[u], g[u], ci);
+    }
+    bool any_small = false;
+#pragma unroll
+    for (int u = 0; u < N; u++) {
+        k[u] = m[u] * e[u]; k1[u] = a[u] * e[u]; k2[u] = b[u] * e[u];
+        any_small |= (r2[u] * A.inv_l2 < A.taylor_bound);
+    }
+    if (any_small) {
+        double s[N], v[N], d1[N], d2[N];
+#pragma unroll
+        for (int u = 0; u < N; u++) { s[u] = r2[u] * A.inv_l2; v[u] = 0.0; d1[u] = 0.0; d2[u] = 0.0; }
+#pragma unroll 1
+        for (int i = p; i >= 0; i--) {  // Horner with derivatives, as in cf_atom_jet
+            const double ti = A.tay[i];
+#pragma unroll
+            for (int u = 0; u < N; u++) {
+                d2[u] = fma(d2[u], s[u], 2.0 * d1[u]);
+                d1[u] = fma(d1[u], s[u], v[u]);
+                v[u] = fma(v[u], s[u], ti);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < N; u++)
+            if (s[u] < A.taylor_bound) { k[u] = v[u]; k1[u] = d1[u] * A.inv_l2; k2[u] = d2[u] * A.inv_l2 * A.inv_l2; }
+    }
+}
+
 // compile-time specialised jets for the common single-atom gradient kernels (no switch, no inlined dead paths)
 template <int KIND>
 __device__ __forceinline__ void cf_atom_jet_t(double r2, const cf_atom& A, cf_tbl_t tbl_lane, double& k, double& k1, double& k2) {

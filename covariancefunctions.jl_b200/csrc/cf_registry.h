@@ -31,7 +31,7 @@ struct cf_kernel_entry {
     cf_sym_launch_fn sym[CF_NKINDS]; // Float64 symmetric variant, [kind slot]
     cf_mvm_launch_fn mvm_dmma[CF_NKINDS]; // Float64 tensor-core value MVM (gram_mvm_dmma.cuh), nullptr when unavailable for D
     cf_mvm_config mvm_dmma_cfg;
-    cf_gradd_launch_fn grad_dmma[2][2]; // Float64 tensor-core isotropic gradient MVM: [value_gradient][0 EQ, 1 generic]; nullptr when unavailable
+    cf_gradd_launch_fn grad_dmma[2][3]; // Float64 tensor-core isotropic gradient MVM: [value_gradient][0 EQ, 1 generic, 2 MaternP(p>=2)]; nullptr when unavailable
     cf_mvm_config grad_dmma_cfg;
     int tune[5];                     // R, NT, TJ, NS, MINB of the value MVM kernel (names the instantiation for cf_jit.h)
 };

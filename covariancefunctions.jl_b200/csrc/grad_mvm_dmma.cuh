@@ -152,35 +152,99 @@ __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_cons
                     a08[2 * cb] = z0.x; a08[2 * cb + 1] = z0.y;
                 }
             }
+            if constexpr (KIND == CF_ATOM_EQ) {
 #pragma unroll
-            for (int rb = 0; rb < 2; rb++) {
-                const int row = 16 * w + 8 * rb + g;
+                for (int rb = 0; rb < 2; rb++) {
+                    const int row = 16 * w + 8 * rb + g;
 #pragma unroll
-                for (int u = 0; u < 8; u++) {
-                    const int col = 8 * (u >> 1) + 2 * t4 + (u & 1);
-                    const double v = fma(-2.0, c[rb][u >> 1][u & 1], xnorm[rb] + yn8[u]);
-                    const double r2 = (__double2hiint(v) < 0) ? 0.0 : v;
-                    const double sdot = p[rb][u >> 1][u & 1] - q8[u];  // r . a_j
-                    double ca, cw, kval = 0.0;
-                    if constexpr (KIND == CF_ATOM_EQ) {  // k = exp(c r2), k1 = c k, k2 = c^2 k: constants folded
-                        kval = cf_exp_cv(r2, P.atom.v.e, tbl_lane);
-                        ca = eq_ca * kval;
-                        cw = (eq_cw * kval) * sdot;
-                    } else {
-                        double k1, k2;
-                        if (P.single) cf_atom_jet(r2, P.atom, tbl_lane, kval, k1, k2);
-                        else cf_sop_jet(r2, P.sop, tbl_lane, kval, k1, k2);
-                        ca = -2.0 * k1;
-                        cw = -4.0 * k2 * sdot;
+                    for (int u = 0; u < 8; u++) {
+                        const int col = 8 * (u >> 1) + 2 * t4 + (u & 1);
+                        const double v = fma(-2.0, c[rb][u >> 1][u & 1], xnorm[rb] + yn8[u]);
+                        const double r2 = (__double2hiint(v) < 0) ? 0.0 : v;
+                        const double sdot = p[rb][u >> 1][u & 1] - q8[u];  // r . a_j
+                        // k = exp(c r2), k1 = c k, k2 = c^2 k: constants folded
+                        const double kval = cf_exp_cv(r2, P.atom.v.e, tbl_lane);
+                        double ca = eq_ca * kval;
+                        double cw = (eq_cw * kval) * sdot;
+                        if constexpr (VG) {  // ca = -2 k1 also multiplies the value weight into cw and r.a_g into the value row
+                            double v0 = fma(kval, a08[u], ca * sdot);
+                            if (ragged && col >= cnt) v0 = 0.0;
+                            b0sum[rb] += v0;
+                            cw = fma(-ca, a08[u], cw);
+                        }
+                        if (ragged && col >= cnt) { ca = 0.0; cw = 0.0; }  // past the end of a ragged tile: no contribution
+                        cwsum[rb] += cw;
+                        Cc[col * SC + row] = ca;
+                        Cc[(TJ + col) * SC + row] = -cw;
                     }
-                    if constexpr (VG) {  // ca = -2 k1 also multiplies the value weight into cw and r.a_g into the value row
-                        double v0 = fma(kval, a08[u], ca * sdot);
-                        if (ragged && col >= cnt) v0 = 0.0;
-                        b0sum[rb] += v0;
-                        cw = fma(-ca, a08[u], cw);
+                }
+            } else if constexpr (KIND == CF_ATOM_MATERN) {  // one MaternP(p >= 2) atom: 8-wide jets per row block
+#pragma unroll
+                for (int rb = 0; rb < 2; rb++) {
+                    const int row = 16 * w + 8 * rb + g;
+                    double r2[8], kv[8], k1[8], k2[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const double v = fma(-2.0, c[rb][u >> 1][u & 1], xnorm[rb] + yn8[u]);
+                        r2[u] = (__double2hiint(v) < 0) ? 0.0 : v;
                     }
-                    if (ragged && col >= cnt) { ca = 0.0; cw = 0.0; }  // past the end of a ragged tile: no contribution
-                    cwsum[rb] += cw;
+                    cf_matern_jet_n<8>(r2, P.atom, tbl_lane, kv, k1, k2);
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int col = 8 * (u >> 1) + 2 * t4 + (u & 1);
+                        const double sdot = p[rb][u >> 1][u & 1] - q8[u];
+                        double ca = -2.0 * k1[u];
+                        double cw = -4.0 * k2[u] * sdot;
+                        if constexpr (VG) {
+                            double v0 = fma(kv[u], a08[u], ca * sdot);
+                            if (ragged && col >= cnt) v0 = 0.0;
+                            b0sum[rb] += v0;
+                            cw = fma(-ca, a08[u], cw);
+                        }
+                        if (ragged && col >= cnt) { ca = 0.0; cw = 0.0; }
+                        cwsum[rb] += cw;
+                        Cc[col * SC + row] = ca;
+                        Cc[(TJ + col) * SC + row] = -cw;
+                    }
+                }
+            } else {
+                // generic jets: ONE copy of the (large) jet code in a rolled loop over this lane's 16 entries.  r2 and r.a_g are parked
+                // in the entry's own two slots of the coefficient tile (nobody else touches them before the barrier), then
+                // overwritten by ca and -cw.  Sixteen inlined copies of the jet interpreter thrashed the instruction cache (1.8x slower
+                // than the scalar kernel).
+#pragma unroll
+                for (int rb = 0; rb < 2; rb++) {
+                    const int row = 16 * w + 8 * rb + g;
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int col = 8 * (u >> 1) + 2 * t4 + (u & 1);
+                        const double v = fma(-2.0, c[rb][u >> 1][u & 1], xnorm[rb] + yn8[u]);
+                        Cc[col * SC + row] = (__double2hiint(v) < 0) ? 0.0 : v;
+                        Cc[(TJ + col) * SC + row] = p[rb][u >> 1][u & 1] - q8[u];
+                    }
+                }
+#pragma unroll 1
+                for (int e16 = 0; e16 < 16; e16++) {
+                    const int rb = e16 >> 3, u = e16 & 7;
+                    const int row = 16 * w + 8 * rb + g;
+                    const int cl = 8 * (u >> 1) + (u & 1);  // column within the tile, without this lane's 2 t4 offset
+                    const int col = cl + 2 * t4;
+                    const double r2 = Cc[col * SC + row];
+                    const double sdot = Cc[(TJ + col) * SC + row];
+                    double kval, k1, k2;
+                    if (P.single) cf_atom_jet(r2, P.atom, tbl_lane, kval, k1, k2);
+                    else cf_sop_jet(r2, P.sop, tbl_lane, kval, k1, k2);
+                    double ca = -2.0 * k1;
+                    double cw = -4.0 * k2 * sdot;
+                    double v0 = 0.0;
+                    if constexpr (VG) {
+                        const double a0 = a0s[col];
+                        v0 = fma(kval, a0, ca * sdot);
+                        cw = fma(-ca, a0, cw);
+                    }
+                    if (ragged && col >= cnt) { ca = 0.0; cw = 0.0; v0 = 0.0; }
+                    if (rb == 0) { cwsum[0] += cw; b0sum[0] += v0; }
+                    else { cwsum[1] += cw; b0sum[1] += v0; }
                     Cc[col * SC + row] = ca;
                     Cc[(TJ + col) * SC + row] = -cw;
                 }
@@ -282,13 +346,15 @@ cudaError_t cf_gradd_launch(const cf_gradd_params& P, dim3 grid, cudaStream_t st
 // registry hook: padded dimensions that are multiples of 8 (output fragments are 8 coordinates wide)
 template <int D, bool OK = (D >= 8 && D % 8 == 0)>
 struct cf_gradd_entry {
-    static constexpr cf_gradd_launch_fn fn[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};  // [value_gradient][0 EQ specialised, 1 generic isotropic]
+    // [value_gradient][0 EQ specialised, 1 generic isotropic, 2 single MaternP(p >= 2)]
+    static constexpr cf_gradd_launch_fn fn[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
     static constexpr cf_mvm_config cfg = {CF_GD_TI, CF_GD_TJ, 0, 1};
 };
 template <int D>
 struct cf_gradd_entry<D, true> {
-    static constexpr cf_gradd_launch_fn fn[2][2] = {{&cf_gradd_launch<D, CF_ATOM_EQ, false>, &cf_gradd_launch<D, CF_ATOM_SOP, false>},
-                                                    {&cf_gradd_launch<D, CF_ATOM_EQ, true>, &cf_gradd_launch<D, CF_ATOM_SOP, true>}};
+    static constexpr cf_gradd_launch_fn fn[2][3] = {
+        {&cf_gradd_launch<D, CF_ATOM_EQ, false>, &cf_gradd_launch<D, CF_ATOM_SOP, false>, &cf_gradd_launch<D, CF_ATOM_MATERN, false>},
+        {&cf_gradd_launch<D, CF_ATOM_EQ, true>, &cf_gradd_launch<D, CF_ATOM_SOP, true>, &cf_gradd_launch<D, CF_ATOM_MATERN, true>}};
     static constexpr cf_mvm_config cfg = {CF_GD_TI, CF_GD_TJ, cf_gd_smem<D>::total, 1};
 };
 #endif // !__CUDACC_RTC__

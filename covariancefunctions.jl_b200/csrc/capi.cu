@@ -970,6 +970,7 @@ int destroy_impl(cf_gramian_s* g) {
         if (sh.yn && sh.yn != sh.xn) dev_free(sh.yn);
         dev_free(sh.xn);
         sh.a.release(); sh.y.release(); sh.partial.release(); sh.apad.release(); sh.ypad.release(); sh.at.release(); sh.sym_items.release(); sh.bsym.release(); sh.bd_t.release(); sh.bd_s.release();
+        sh.xp.release(); sh.yp.release(); sh.ap.release();
         for (auto& b : sh.cg) b.release();
         if (sh.ev0) cudaEventDestroy(sh.ev0);
         if (sh.ev1) cudaEventDestroy(sh.ev1);

@@ -276,3 +276,34 @@ def test_runtime_specialisation_unavailable_falls_back_to_interpreter_kernel():
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "fallback ok" in out.stdout, out.stderr[-2000:]
+
+
+def test_handles_return_all_device_memory(cf):
+    """create / multiply / destroy in a loop: every per-handle buffer (padded point copies of the tensor-core kernels, padded
+    weights, partial sums, transposed right-hand sides) must go back to the pool -- free device memory stays flat"""
+    import torch
+    rng = np.random.default_rng(2)
+    n, d = 30000, 16
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    a = rng.standard_normal(n)
+    A = rng.standard_normal((n, 3))
+    g = rng.standard_normal(n * d)
+
+    def cycle():
+        G = cf.gramian(cf.MaternP(2), X.T.copy())
+        G @ a
+        G @ A
+        G.close()
+        H = cf.gramian(cf.GradientKernel(cf.EQ()), X[:3000].T.copy())
+        H @ g[:3000 * d]
+        H.close()
+
+    for _ in range(3):
+        cycle()
+    torch.cuda.synchronize()
+    free0, _ = torch.cuda.mem_get_info()
+    for _ in range(12):
+        cycle()
+    torch.cuda.synchronize()
+    free1, _ = torch.cuda.mem_get_info()
+    assert free0 - free1 < 8 << 20, f"device memory shrank by {(free0 - free1) / 2**20:.1f} MiB over 12 handle lifetimes"

@@ -375,6 +375,20 @@ __device__ __forceinline__ void cf_atom_jet(double r2, const cf_atom& A, cf_tbl_
     }
 }
 
+// element u of a register array, u a run-time index: a chain of selects (register arrays cannot be indexed dynamically)
+template <int N>
+__device__ __forceinline__ double cf_select_n(const double (&a)[N], int u) {
+    double v = a[0];
+#pragma unroll
+    for (int q = 1; q < N; q++) v = (u == q) ? a[q] : v;
+    return v;
+}
+template <int N>
+__device__ __forceinline__ void cf_store_n(double (&a)[N], int u, double v) {
+#pragma unroll
+    for (int q = 0; q < N; q++) a[q] = (u == q) ? v : a[q];
+}
+
 // jets of N pairs of ONE Matern atom with p >= 2 (k' and k'' have no singular terms): every stage is issued for all N values, the
 // loops over p are uniform.  The reference's Taylor branch for r2 / l^2 < eps^(1/p) (src/stationary.jl:139-146) is evaluated
 // only by the lanes that have such an entry (coincident points) and selected per entry.
@@ -433,6 +447,47 @@ __device__ __forceinline__ void cf_matern_jet_n(const double (&r2)[N], const cf_
     }
 }
 
+// jets of N pairs of one isotropic atom, dispatching on the kind ONCE for the N values.  MaternP(p < 2) (singular k'') is
+// handled entry by entry through cf_atom_jet: the tensor-core gradient kernel never sees it, the scalar one may.
+__device__ __forceinline__ void cf_atom_jet(double r2, const cf_atom& A, cf_tbl_t tbl_lane, double& k, double& k1, double& k2);
+template <int N>
+__device__ __forceinline__ void cf_atom_jet_n(const double (&r2)[N], const cf_atom& A, cf_tbl_t tbl_lane, double (&k)[N],
+                                              double (&k1)[N], double (&k2)[N]) {
+    const int kind = A.v.kind;
+    if (kind == CF_ATOM_EQ) {
+#pragma unroll
+        for (int u = 0; u < N; u++) {
+            k[u] = cf_exp_cv(r2[u], A.v.e, tbl_lane);
+            k1[u] = A.v.e.c * k[u];
+            k2[u] = A.v.e.c * k1[u];
+        }
+    } else if (kind == CF_ATOM_MATERN && A.v.p >= 2) {
+        cf_matern_jet_n<N>(r2, A, tbl_lane, k, k1, k2);
+    } else if (kind == CF_ATOM_RQ_INT) {
+        double ib[N];
+#pragma unroll
+        for (int u = 0; u < N; u++) { ib[u] = cf_rcp(fma(r2[u], A.v.w, 1.0)); k[u] = ib[u]; }
+#pragma unroll 1
+        for (int i = 1; i < A.v.p; i++) {
+#pragma unroll
+            for (int u = 0; u < N; u++) k[u] *= ib[u];
+        }
+        const double c1 = -A.v.alpha * A.v.w, c2 = -(A.v.alpha + 1.0) * A.v.w;
+#pragma unroll
+        for (int u = 0; u < N; u++) {
+            k1[u] = c1 * k[u] * ib[u];
+            k2[u] = c2 * k1[u] * ib[u];
+        }
+    } else {
+#pragma unroll 1
+        for (int u = 0; u < N; u++) {  // rolled: one copy of the scalar code (real-power RQ, MaternP(p < 2), LINE)
+            double kk, kk1, kk2;
+            cf_atom_jet(cf_select_n<N>(r2, u), A, tbl_lane, kk, kk1, kk2);
+            cf_store_n<N>(k, u, kk); cf_store_n<N>(k1, u, kk1); cf_store_n<N>(k2, u, kk2);
+        }
+    }
+}
+
 // compile-time specialised jets for the common single-atom gradient kernels (no switch, no inlined dead paths)
 template <int KIND>
 __device__ __forceinline__ void cf_atom_jet_t(double r2, const cf_atom& A, cf_tbl_t tbl_lane, double& k, double& k1, double& k2) {
@@ -464,6 +519,36 @@ __device__ __forceinline__ void cf_sop_jet(double r2, const cf_sop_grad& P, cf_t
         sv += pv; s1 += p1; s2 += p2;
     }
     k = sv; k1 = s1; k2 = s2;
+}
+
+// the same for N pairs at a time: the program is decoded once per N values
+template <int N>
+__device__ __forceinline__ void cf_sop_jet_n(const double (&r2)[N], const cf_sop_grad& P, cf_tbl_t tbl_lane, double (&k)[N],
+                                             double (&k1)[N], double (&k2)[N]) {
+#pragma unroll
+    for (int u = 0; u < N; u++) { k[u] = 0.0; k1[u] = 0.0; k2[u] = 0.0; }
+    for (int t = 0; t < P.nterms; t++) {
+        const cf_sop_term& T = P.terms[t];
+        double pv[N], p1[N], p2[N];
+#pragma unroll
+        for (int u = 0; u < N; u++) { pv[u] = T.coef; p1[u] = 0.0; p2[u] = 0.0; }
+        for (int f = 0; f < T.nfac; f++) {
+            double av[N], a1[N], a2[N];
+            cf_atom_jet_n<N>(r2, P.atoms[T.atom[f]], tbl_lane, av, a1, a2);
+#pragma unroll 1
+            for (int q = 0; q < T.power[f]; q++) {
+#pragma unroll
+                for (int u = 0; u < N; u++) {
+                    const double nv = pv[u] * av[u];
+                    const double n1 = fma(p1[u], av[u], pv[u] * a1[u]);
+                    const double n2 = fma(p2[u], av[u], fma(2.0 * p1[u], a1[u], pv[u] * a2[u]));
+                    pv[u] = nv; p1[u] = n1; p2[u] = n2;
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < N; u++) { k[u] += pv[u]; k1[u] += p1[u]; k2[u] += p2[u]; }
+    }
 }
 
 // ---- FP32 ------------------------------------------------------------------------------------------

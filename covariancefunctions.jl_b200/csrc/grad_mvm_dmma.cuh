@@ -208,10 +208,10 @@ __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_cons
                     }
                 }
             } else {
-                // generic jets: ONE copy of the (large) jet code in a rolled loop over this lane's 16 entries.  r2 and r.a_g are parked
-                // in the entry's own two slots of the coefficient tile (nobody else touches them before the barrier), then
-                // overwritten by ca and -cw.  Sixteen inlined copies of the jet interpreter thrashed the instruction cache (1.8x slower
-                // than the scalar kernel).
+                // generic programs: 8-wide jets (the program is decoded once per 8 entries); the two row blocks go through ONE
+                // copy of the code in a rolled loop -- r2 and r.a_g are parked in the entries' own slots of the coefficient tile
+                // (nobody else touches them before the barrier) and overwritten by ca and -cw.  Sixteen inlined scalar copies of
+                // the jet interpreter thrashed the instruction cache (1.8x slower than the scalar kernel).
 #pragma unroll
                 for (int rb = 0; rb < 2; rb++) {
                     const int row = 16 * w + 8 * rb + g;
@@ -224,29 +224,33 @@ __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_cons
                     }
                 }
 #pragma unroll 1
-                for (int e16 = 0; e16 < 16; e16++) {
-                    const int rb = e16 >> 3, u = e16 & 7;
+                for (int rb = 0; rb < 2; rb++) {
                     const int row = 16 * w + 8 * rb + g;
-                    const int cl = 8 * (u >> 1) + (u & 1);  // column within the tile, without this lane's 2 t4 offset
-                    const int col = cl + 2 * t4;
-                    const double r2 = Cc[col * SC + row];
-                    const double sdot = Cc[(TJ + col) * SC + row];
-                    double kval, k1, k2;
-                    if (P.single) cf_atom_jet(r2, P.atom, tbl_lane, kval, k1, k2);
-                    else cf_sop_jet(r2, P.sop, tbl_lane, kval, k1, k2);
-                    double ca = -2.0 * k1;
-                    double cw = -4.0 * k2 * sdot;
-                    double v0 = 0.0;
-                    if constexpr (VG) {
-                        const double a0 = a0s[col];
-                        v0 = fma(kval, a0, ca * sdot);
-                        cw = fma(-ca, a0, cw);
+                    double r2[8], kv[8], k1[8], k2[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) r2[u] = Cc[(8 * (u >> 1) + 2 * t4 + (u & 1)) * SC + row];
+                    if (P.single) cf_atom_jet_n<8>(r2, P.atom, tbl_lane, kv, k1, k2);
+                    else cf_sop_jet_n<8>(r2, P.sop, tbl_lane, kv, k1, k2);
+                    double cws = 0.0, b0s = 0.0;
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const int col = 8 * (u >> 1) + 2 * t4 + (u & 1);
+                        const double sdot = Cc[(TJ + col) * SC + row];
+                        double ca = -2.0 * k1[u];
+                        double cw = -4.0 * k2[u] * sdot;
+                        if constexpr (VG) {
+                            double v0 = fma(kv[u], a08[u], ca * sdot);
+                            if (ragged && col >= cnt) v0 = 0.0;
+                            b0s += v0;
+                            cw = fma(-ca, a08[u], cw);
+                        }
+                        if (ragged && col >= cnt) { ca = 0.0; cw = 0.0; }
+                        cws += cw;
+                        Cc[col * SC + row] = ca;
+                        Cc[(TJ + col) * SC + row] = -cw;
                     }
-                    if (ragged && col >= cnt) { ca = 0.0; cw = 0.0; v0 = 0.0; }
-                    if (rb == 0) { cwsum[0] += cw; b0sum[0] += v0; }
-                    else { cwsum[1] += cw; b0sum[1] += v0; }
-                    Cc[col * SC + row] = ca;
-                    Cc[(TJ + col) * SC + row] = -cw;
+                    if (rb == 0) { cwsum[0] += cws; b0sum[0] += b0s; }
+                    else { cwsum[1] += cws; b0sum[1] += b0s; }
                 }
             }
         }

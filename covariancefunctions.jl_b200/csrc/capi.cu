@@ -253,7 +253,9 @@ int launch_mm(cf_gramian_s* g, Shard& sh, void* d_B, int64_t ldb, const void* d_
     }
     // Float64, well-scaled points, d >= 8: FP64 tensor-core kernel (gram_mm_dmma.cuh); COVFN_MM_SCALAR=1 forces the scalar one
     const bool dmma = g->dtype == CF_F64 && g->use_norms && g->entry->mm_dmma != nullptr && !env_flag("COVFN_MM_SCALAR");
-    const int ldat = dmma ? CF_MMD_SA : CF_MM_PC;
+    // Float32, well-scaled points, d >= 8: tensor cores in 3xTF32 split precision (gram_mm_tf32.cuh)
+    const bool tf32 = g->dtype == CF_F32 && g->use_norms && g->entry->mm_tf32 != nullptr && !env_flag("COVFN_MM_SCALAR");
+    const int ldat = dmma ? CF_MMD_SA : (tf32 ? CF_MMT_SA : CF_MM_PC);
     if (int rc = sh.at.ensure((size_t)g->m * ldat * es)) return rc;
     cf_mm_params P;
     std::memset(&P, 0, sizeof(P));
@@ -267,6 +269,17 @@ int launch_mm(cf_gramian_s* g, Shard& sh, void* d_B, int64_t ldb, const void* d_
         if (int rc = ensure_padded_points(g, sh, stream)) return rc;
         P.X = sh.xp.p;
         P.Y = (sh.Y != sh.X) ? sh.yp.p : sh.xp.p;
+    }
+    if (tf32) {  // the column points with the padded row stride (B fragments); the row tile is transposed inside the kernel
+        const int sx = g->entry->mm_tf32_sx;
+        if (!sh.mmd_ready) {
+            if (int rc = sh.yp.ensure((size_t)g->m * sx * 4)) return rc;
+            cf_pad_rows_f32_kernel<<<148 * 8, 256, 0, stream>>>((const float*)sh.Y, g->D, sx, g->m, (float*)sh.yp.p);
+            CF_CUDA(cudaGetLastError());
+            sh.mmd_ready = true;
+        }
+        P.X = sh.X;
+        P.Y = sh.yp.p;
     }
     const int row_tiles = (int)((nrows + CF_MM_TI - 1) / CF_MM_TI);
     cfjit::Kernel* jit = nullptr;
@@ -286,7 +299,7 @@ int launch_mm(cf_gramian_s* g, Shard& sh, void* d_B, int64_t ldb, const void* d_
             launched = cfjit::launch(jit, &P, (unsigned)row_tiles, 1, 256, (unsigned)g->entry->mm_dmma_smem, stream) == 0;
             if (!launched) jit = nullptr;
         }
-        if (!launched) CF_CUDA((dmma ? g->entry->mm_dmma : g->entry->mm[g->dtype])(P, row_tiles, stream));
+        if (!launched) CF_CUDA((dmma ? g->entry->mm_dmma : (tf32 ? g->entry->mm_tf32 : g->entry->mm[g->dtype]))(P, row_tiles, stream));
         g->last_launches += 2;
     }
     return CF_OK;
@@ -1127,7 +1140,10 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
             else if (A.v.kind == CF_ATOM_MATERN) slope = std::max(slope, std::fabs(A.tay[1]) * A.inv_l2);
             else if (A.v.kind == CF_ATOM_RQ_INT || A.v.kind == CF_ATOM_RQ_REAL) slope = std::max(slope, A.v.alpha * A.v.w);
         }
-        g->use_norms = (d >= 8) && !sqrt_atom && ((d + 2) * eps * 2.0 * max_sq * slope < bound);
+        // Float64 uses the worst-case accumulation factor (d + 2); for Float32 (tolerance 1e-5 on the result's 2-norm) the
+        // random-walk factor sqrt(d + 2) is the realistic one -- the worst case would switch the expansion off for unit-scale data
+        const double growth = dtype == CF_F64 ? (double)(d + 2) : std::sqrt((double)(d + 2));
+        g->use_norms = (d >= 8) && !sqrt_atom && (growth * eps * 2.0 * max_sq * slope < bound);
         // the derivative operators also need k'' (one more factor of the slope) and MaternP(1) has a 1/sqrt(r2) term in k''
         bool smooth2 = true;
         for (int i = 0; i < g->prog.natoms; i++)

@@ -42,6 +42,8 @@ const cf_kernel_entry entry = {
     {{cf_gradd_entry<D>::fn[0][0], cf_gradd_entry<D>::fn[0][1], cf_gradd_entry<D>::fn[0][2]},
      {cf_gradd_entry<D>::fn[1][0], cf_gradd_entry<D>::fn[1][1], cf_gradd_entry<D>::fn[1][2]}},
     cf_gradd_entry<D>::cfg,
+    cf_mmt_entry<D>::fn,
+    cf_mmt_entry<D>::sx,
     {TU::R, TU::NT, TU::TJ, TU::NS, TU::MINB},
 };
 }  // namespace

@@ -583,29 +583,93 @@ __device__ __forceinline__ float cf_atom_value_f32(float r2, float dt, const cf_
     if (kind == CF_ATOM_RQ_REAL) return cf_ex2f(-A.f_alpha * cf_lg2f(fmaf(r2, A.f_w, 1.0f)));
     return dt + A.f_sigma;
 }
+// N pairs at once, dispatching on the atom kind ONCE (uniform branch): only the code of the kind that is present runs, every
+// stage is issued for all N values.  (Per-entry dispatch made ptxas if-convert the chain: every entry executed the rsqrt /
+// lg2 / ex2 of kinds that were not there -- profiles/r1_ncu_gram_mm_tf32_c3.md.)
+template <int N>
+__device__ __forceinline__ void cf_atom_value_f32_n(const float (&r2)[N], const float (&dt)[N], const cf_atom_val& A, float (&out)[N]) {
+    switch (A.kind) {
+        case CF_ATOM_EQ:
+#pragma unroll
+            for (int u = 0; u < N; u++) out[u] = cf_ex2f(r2[u] * A.f_clog2e);
+            break;
+        case CF_ATOM_MATERN: {
+            float g[N], e[N];
+#pragma unroll
+            for (int u = 0; u < N; u++) {
+                g[u] = fminf(r2[u] * cf_rsqrtf(fmaxf(r2[u], 1e-37f)), A.f_gmax);  // sqrt(r2), 0 at r2 = 0; far points underflow to 0
+                e[u] = cf_ex2f(g[u] * A.f_clog2e);
+            }
+            const int p = A.p;
+            float mp[N];
+#pragma unroll
+            for (int u = 0; u < N; u++) mp[u] = A.f_mat[p];
+#pragma unroll 1
+            for (int i = p - 1; i >= 0; i--) {
+                const float ci = A.f_mat[i];
+#pragma unroll
+                for (int u = 0; u < N; u++) mp[u] = fmaf(mp[u], g[u], ci);
+            }
+#pragma unroll
+            for (int u = 0; u < N; u++) out[u] = (p == 0) ? e[u] : mp[u] * e[u];
+            break;
+        }
+        case CF_ATOM_RQ_INT: {
+            float ib[N];
+#pragma unroll
+            for (int u = 0; u < N; u++) { ib[u] = cf_rcpf(fmaf(r2[u], A.f_w, 1.0f)); out[u] = ib[u]; }
+#pragma unroll 1
+            for (int i = 1; i < A.p; i++) {
+#pragma unroll
+                for (int u = 0; u < N; u++) out[u] *= ib[u];
+            }
+            break;
+        }
+        case CF_ATOM_RQ_REAL:
+#pragma unroll
+            for (int u = 0; u < N; u++) out[u] = cf_ex2f(-A.f_alpha * cf_lg2f(fmaf(r2[u], A.f_w, 1.0f)));
+            break;
+        default:
+#pragma unroll
+            for (int u = 0; u < N; u++) out[u] = dt[u] + A.f_sigma;
+    }
+}
+// value = sum_t coef_t prod_f atom^pw (same structure as the Float64 interpreter: first factor initialises the product,
+// coefficient in the final FMA)
 template <int N>
 __device__ __forceinline__ void cf_sop_value_f32_n(const float (&r2)[N], const float (&dt)[N], const cf_sop_val& P, float (&val)[N]) {
 #pragma unroll
     for (int u = 0; u < N; u++) val[u] = 0.f;
-    for (int t = 0; t < P.nterms; t++) {
+    const int nt = P.nterms;
+    for (int t = 0; t < nt; t++) {
         const cf_sop_term& T = P.terms[t];
+        const float coef = (float)T.coef;
+        const int nf = T.nfac;
+        if (nf == 0) {
+#pragma unroll
+            for (int u = 0; u < N; u++) val[u] += coef;
+            continue;
+        }
         float prod[N];
+        for (int f = 0; f < nf; f++) {
+            float a[N];
+            cf_atom_value_f32_n<N>(r2, dt, P.atoms[T.atom[f]], a);
+            const int pw = T.power[f];
+            if (pw >= 2) {
+                float b[N];
 #pragma unroll
-        for (int u = 0; u < N; u++) prod[u] = (float)T.coef;
-        for (int f = 0; f < T.nfac; f++) {
-            const cf_atom_val& A = P.atoms[T.atom[f]];
-            float a[N], r[N];
+                for (int u = 0; u < N; u++) b[u] = a[u];
+#pragma unroll 1
+                for (int q = 1; q < pw; q++) {
 #pragma unroll
-            for (int u = 0; u < N; u++) { a[u] = cf_atom_value_f32<-1>(r2[u], dt[u], A); r[u] = a[u]; }
-            for (int q = 1; q < T.power[f]; q++) {
-#pragma unroll
-                for (int u = 0; u < N; u++) r[u] *= a[u];
+                    for (int u = 0; u < N; u++) a[u] *= b[u];
+                }
             }
 #pragma unroll
-            for (int u = 0; u < N; u++) prod[u] *= r[u];
+            for (int u = 0; u < N; u++) prod[u] = (f == 0) ? a[u] : prod[u] * a[u];
         }
 #pragma unroll
-        for (int u = 0; u < N; u++) val[u] += prod[u];
+        for (int u = 0; u < N; u++) val[u] = fmaf(coef, prod[u], val[u]);
     }
 }
 __device__ __forceinline__ float cf_sop_value_f32(float r2, float dt, const cf_sop_val& P) {

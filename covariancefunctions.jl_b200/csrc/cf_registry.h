@@ -7,6 +7,7 @@
 #include "gram_mm_dmma.cuh"
 #include "gram_mvm_dmma.cuh"
 #include "grad_mvm_dmma.cuh"
+#include "gram_mm_tf32.cuh"
 
 #define CF_NKINDS 4 /* EQ, MATERN, RQ_INT, SOP */
 inline int cf_kind_slot(int kind) {
@@ -33,6 +34,8 @@ struct cf_kernel_entry {
     cf_mvm_config mvm_dmma_cfg;
     cf_gradd_launch_fn grad_dmma[2][3]; // Float64 tensor-core isotropic gradient MVM: [value_gradient][0 EQ, 1 generic, 2 MaternP(p>=2)]; nullptr when unavailable
     cf_mvm_config grad_dmma_cfg;
+    cf_mm_launch_fn mm_tf32; // Float32 multi-RHS on the tensor cores in 3xTF32 (gram_mm_tf32.cuh), nullptr for D < 8
+    int mm_tf32_sx;          // row stride (floats) of its padded point copies
     int tune[5];                     // R, NT, TJ, NS, MINB of the value MVM kernel (names the instantiation for cf_jit.h)
 };
 

@@ -285,6 +285,9 @@ int launch_mm(cf_gramian_s* g, Shard& sh, void* d_B, int64_t ldb, const void* d_
     cfjit::Kernel* jit = nullptr;
     if (dmma && cfjit::wanted((double)nrows * (double)g->m))
         jit = cfjit::get_kernel(g->sop_val, "gram_mm_dmma.cuh", "gram_mm_dmma_kernel<" + std::to_string(g->D) + ">");
+    if (tf32 && cfjit::wanted((double)nrows * (double)g->m))
+        jit = cfjit::get_kernel(g->sop_val, "gram_mm_tf32.cuh", "gram_mm_tf32_kernel<" + std::to_string(g->D) + ">");
+    const unsigned jit_smem = (unsigned)(tf32 ? g->entry->mm_tf32_smem : g->entry->mm_dmma_smem);
     for (int64_t c0 = 0; c0 < nrhs; c0 += CF_MM_PC) {
         P.nrhs = (int)std::min<int64_t>(CF_MM_PC, nrhs - c0);
         const dim3 tg((unsigned)((g->m + 31) / 32), CF_MM_PC / 32), tb(32, 8);
@@ -296,7 +299,7 @@ int launch_mm(cf_gramian_s* g, Shard& sh, void* d_B, int64_t ldb, const void* d_
         P.B = (char*)d_B + c0 * ldb * es;
         bool launched = false;
         if (jit) {  // same kernel source, program structure compiled in (cf_jit.h); any failure falls back to the interpreter build
-            launched = cfjit::launch(jit, &P, (unsigned)row_tiles, 1, 256, (unsigned)g->entry->mm_dmma_smem, stream) == 0;
+            launched = cfjit::launch(jit, &P, (unsigned)row_tiles, 1, 256, jit_smem, stream) == 0;
             if (!launched) jit = nullptr;
         }
         if (!launched) CF_CUDA((dmma ? g->entry->mm_dmma : (tf32 ? g->entry->mm_tf32 : g->entry->mm[g->dtype]))(P, row_tiles, stream));

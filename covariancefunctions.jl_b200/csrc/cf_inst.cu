@@ -44,6 +44,7 @@ const cf_kernel_entry entry = {
     cf_gradd_entry<D>::cfg,
     cf_mmt_entry<D>::fn,
     cf_mmt_entry<D>::sx,
+    cf_mmt_entry<D>::smem,
     {TU::R, TU::NT, TU::TJ, TU::NS, TU::MINB},
 };
 }  // namespace

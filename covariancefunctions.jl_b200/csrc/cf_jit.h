@@ -126,36 +126,41 @@ inline std::string shape_key(const cf_sop_val& P) {
     return k;
 }
 
-// generated cf_jit_shape.h: atoms first (each distinct atom evaluated once per group of N pairs), then the terms
-inline std::string shape_source(const cf_sop_val& P) {
-    std::string s = "// generated by cf_jit.h for program structure " + shape_key(P) + "\n";
-    s += "template <int N>\n__device__ __forceinline__ void cf_sop_value_n(const double (&r2)[N], const double (&dt)[N], "
-         "const cf_sop_val& P, cf_tbl_t tbl_lane, double (&val)[N]) {\n";
-    // highest power needed of each atom decides nothing here: powers are formed per use with static exponents (the compiler
-    // shares common sub-products); an atom is evaluated once
+// generated cf_jit_shape.h: atoms first (each distinct atom evaluated once per group of N pairs), then the terms.  Part 1 is
+// the Float64 evaluator, part 2 the Float32 one (cf_math.cuh includes the header twice, after the helpers each part needs).
+inline std::string shape_source_part(const cf_sop_val& P, bool f32) {
+    const std::string T = f32 ? "float" : "double";
+    std::string s = "template <int N>\n__device__ __forceinline__ void ";
+    s += f32 ? "cf_sop_value_f32_n(const float (&r2)[N], const float (&dt)[N], const cf_sop_val& P, float (&val)[N]) {\n"
+             : "cf_sop_value_n(const double (&r2)[N], const double (&dt)[N], const cf_sop_val& P, cf_tbl_t tbl_lane, double (&val)[N]) {\n";
     for (int i = 0; i < P.natoms; i++) {
         const int kind = P.atoms[i].kind;
         const int ps = (kind == CF_ATOM_MATERN || kind == CF_ATOM_RQ_INT) ? P.atoms[i].p : 0;
-        s += "    double a" + std::to_string(i) + "[N];\n";
-        s += "    cf_atom_pow_s<N, " + std::string(kind_name(kind)) + ", " + std::to_string(ps) + ", 1>(r2, dt, P.atoms[" +
-             std::to_string(i) + "], tbl_lane, a" + std::to_string(i) + ");\n";
+        const std::string ai = "a" + std::to_string(i);
+        s += "    " + T + " " + ai + "[N];\n";
+        s += std::string("    ") + (f32 ? "cf_atom_pow_f32_s" : "cf_atom_pow_s") + "<N, " + kind_name(kind) + ", " + std::to_string(ps) +
+             ", 1>(r2, dt, P.atoms[" + std::to_string(i) + "], " + (f32 ? "" : "tbl_lane, ") + ai + ");\n";
     }
-    s += "#pragma unroll\n    for (int u = 0; u < N; u++) {\n        double v = 0.0, p;\n";
+    s += "#pragma unroll\n    for (int u = 0; u < N; u++) {\n        " + T + " v = 0, p;\n";
     for (int t = 0; t < P.nterms; t++) {
-        const cf_sop_term& T = P.terms[t];
-        const std::string coef = "P.terms[" + std::to_string(t) + "].coef";
-        if (T.nfac == 0) {
+        const cf_sop_term& Tm = P.terms[t];
+        const std::string coef = std::string(f32 ? "(float)" : "") + "P.terms[" + std::to_string(t) + "].coef";
+        if (Tm.nfac == 0) {
             s += "        v += " + coef + ";\n";
             continue;
         }
         std::string prod;
-        for (int f = 0; f < T.nfac; f++)
-            for (int q = 0; q < T.power[f]; q++) prod += (prod.empty() ? "" : " * ") + ("a" + std::to_string(T.atom[f]) + "[u]");
+        for (int f = 0; f < Tm.nfac; f++)
+            for (int q = 0; q < Tm.power[f]; q++) prod += (prod.empty() ? "" : " * ") + ("a" + std::to_string(Tm.atom[f]) + "[u]");
         s += "        p = " + prod + ";\n";
-        s += (t == 0) ? "        v = " + coef + " * p;\n" : "        v = fma(" + coef + ", p, v);\n";
+        s += (t == 0) ? "        v = " + coef + " * p;\n" : std::string("        v = ") + (f32 ? "fmaf(" : "fma(") + coef + ", p, v);\n";
     }
     s += "        val[u] = v;\n    }\n}\n";
     return s;
+}
+inline std::string shape_source(const cf_sop_val& P) {
+    return "// generated by cf_jit.h for program structure " + shape_key(P) + "\n#if CF_JIT_PART == 1\n" + shape_source_part(P, false) +
+           "#elif CF_JIT_PART == 2\n" + shape_source_part(P, true) + "#endif\n";
 }
 
 // Returns the specialised kernel for (shape of P, name_expr), compiling it on first use; nullptr if unavailable.

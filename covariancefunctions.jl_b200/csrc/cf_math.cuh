@@ -270,7 +270,9 @@ __device__ __forceinline__ void cf_atom_pow_s(const double (&r2)[N], const doubl
 // run-time specialised build (capi.cu, cf_jit.h): the generated header defines cf_sop_value_n<N> for ONE program structure --
 // atom kinds, integer parameters, powers and the term list are compile-time constants, only the coefficients and atom
 // parameters stay in the kernel arguments.  Same signature and same results as the interpreter below.
+#define CF_JIT_PART 1  // the Float64 evaluator
 #include "cf_jit_shape.h"
+#undef CF_JIT_PART
 #else
 // out = atom^pw for N pairs (pw >= 1; the common pw = 1, 2 cost no copies)
 template <int N>
@@ -634,6 +636,52 @@ __device__ __forceinline__ void cf_atom_value_f32_n(const float (&r2)[N], const 
             for (int u = 0; u < N; u++) out[u] = dt[u] + A.f_sigma;
     }
 }
+// out = atom^PW in Float32 with the atom kind, its integer parameter and the power known at compile time (run-time specialised builds)
+template <int N, int KIND, int PS, int PW>
+__device__ __forceinline__ void cf_atom_pow_f32_s(const float (&r2)[N], const float (&dt)[N], const cf_atom_val& A, float (&out)[N]) {
+    if constexpr (KIND == CF_ATOM_EQ) {
+#pragma unroll
+        for (int u = 0; u < N; u++) out[u] = cf_ex2f(r2[u] * A.f_clog2e);
+    } else if constexpr (KIND == CF_ATOM_MATERN) {
+#pragma unroll
+        for (int u = 0; u < N; u++) {
+            const float g = fminf(r2[u] * cf_rsqrtf(fmaxf(r2[u], 1e-37f)), A.f_gmax);
+            const float e = cf_ex2f(g * A.f_clog2e);
+            float mp = A.f_mat[PS];
+#pragma unroll
+            for (int i = PS - 1; i >= 0; i--) mp = fmaf(mp, g, A.f_mat[i]);
+            out[u] = (PS == 0) ? e : mp * e;
+        }
+    } else if constexpr (KIND == CF_ATOM_RQ_INT) {
+#pragma unroll
+        for (int u = 0; u < N; u++) {
+            const float ib = cf_rcpf(fmaf(r2[u], A.f_w, 1.0f));
+            float r = ib;
+#pragma unroll
+            for (int i = 1; i < PS; i++) r *= ib;
+            out[u] = r;
+        }
+    } else if constexpr (KIND == CF_ATOM_RQ_REAL) {
+#pragma unroll
+        for (int u = 0; u < N; u++) out[u] = cf_ex2f(-A.f_alpha * cf_lg2f(fmaf(r2[u], A.f_w, 1.0f)));
+    } else {
+#pragma unroll
+        for (int u = 0; u < N; u++) out[u] = dt[u] + A.f_sigma;
+    }
+    if constexpr (PW > 1) {
+#pragma unroll
+        for (int u = 0; u < N; u++) {
+            const float a = out[u];
+#pragma unroll
+            for (int q = 1; q < PW; q++) out[u] *= a;
+        }
+    }
+}
+#ifdef CF_JIT_SHAPE
+#define CF_JIT_PART 2  // the Float32 evaluator (same generated header, second part)
+#include "cf_jit_shape.h"
+#undef CF_JIT_PART
+#else
 // value = sum_t coef_t prod_f atom^pw (same structure as the Float64 interpreter: first factor initialises the product,
 // coefficient in the final FMA)
 template <int N>
@@ -672,6 +720,7 @@ __device__ __forceinline__ void cf_sop_value_f32_n(const float (&r2)[N], const f
         for (int u = 0; u < N; u++) val[u] = fmaf(coef, prod[u], val[u]);
     }
 }
+#endif // CF_JIT_SHAPE (Float32)
 __device__ __forceinline__ float cf_sop_value_f32(float r2, float dt, const cf_sop_val& P) {
     float a[1] = {r2}, b[1] = {dt}, v[1];
     cf_sop_value_f32_n<1>(a, b, P, v);

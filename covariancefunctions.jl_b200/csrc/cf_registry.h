@@ -36,6 +36,7 @@ struct cf_kernel_entry {
     cf_mvm_config grad_dmma_cfg;
     cf_mm_launch_fn mm_tf32; // Float32 multi-RHS on the tensor cores in 3xTF32 (gram_mm_tf32.cuh), nullptr for D < 8
     int mm_tf32_sx;          // row stride (floats) of its padded point copies
+    int mm_tf32_smem;        // its dynamic shared memory (run-time specialised launches)
     int tune[5];                     // R, NT, TJ, NS, MINB of the value MVM kernel (names the instantiation for cf_jit.h)
 };
 

@@ -25,7 +25,7 @@
 #define CF_MMT_SA (CF_MM_PC + 4)  // row stride of At[j][c] (floats, global and shared): 2 SA = 8 mod 32
 
 // row stride of the padded point copies (floats): smallest value >= D that is 8 mod 16 (conflict-free 8-byte fragment loads)
-constexpr int cf_mmt_sx(int D) { return (D % 16 <= 8) ? (D / 16) * 16 + 8 : (D / 16) * 16 + 24; }
+__host__ __device__ constexpr int cf_mmt_sx(int D) { return (D % 16 <= 8) ? (D / 16) * 16 + 8 : (D / 16) * 16 + 24; }
 
 template <int D>
 struct cf_mmt_layout {
@@ -284,11 +284,11 @@ cudaError_t cf_mmt_launch(const cf_mm_params& P, int row_tiles, cudaStream_t str
 template <int D, bool OK = (D >= 8)>
 struct cf_mmt_entry {
     static constexpr cf_mm_launch_fn fn = nullptr;
-    static constexpr int sx = 0;
+    static constexpr int sx = 0, smem = 0;
 };
 template <int D>
 struct cf_mmt_entry<D, true> {
     static constexpr cf_mm_launch_fn fn = &cf_mmt_launch<D>;
-    static constexpr int sx = cf_mmt_sx(D);
+    static constexpr int sx = cf_mmt_sx(D), smem = cf_mmt_layout<D>::total;
 };
 #endif // !__CUDACC_RTC__

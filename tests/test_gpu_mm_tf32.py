@@ -80,3 +80,29 @@ def test_tf32_symmetric_row_range_and_nan_overwrite(cf, O):
     G.set_row_range(130, 777)
     part = G @ A
     assert part.shape == (647, p) and relerr(part, B[130:777]) < 1e-6
+
+
+def test_tf32_runtime_specialised_program(cf, O):
+    """COVFN_JIT=1: the Float32 evaluator of the program is generated too (csrc/cf_jit.h, part 2 of cf_jit_shape.h)"""
+    rng = np.random.default_rng(63)
+    n, m, d, p = 300, 260, 16, 7
+    X = (rng.standard_normal((n, d)) / np.sqrt(d)).astype(np.float32)
+    Y = (rng.standard_normal((m, d)) / np.sqrt(d)).astype(np.float32)
+    A = rng.standard_normal((m, p)).astype(np.float32)
+    before = cf.jit_stats()
+    os.environ["COVFN_JIT"] = "1"
+    try:
+        for name, k in _kernels(cf).items():
+            G = cf.gramian(k, X.T.copy(), Y.T.copy())
+            Bj = G @ A
+            os.environ["COVFN_JIT"] = "0"
+            Bi = G @ A
+            os.environ["COVFN_JIT"] = "1"
+            truth = O.mul_mat(k.program(), X.astype(np.float64), A.astype(np.float64), Y=Y.astype(np.float64))
+            assert relerr(Bj.astype(np.float64), truth) < TOL32, name
+            assert relerr(Bj, Bi) < 2e-6, name
+    finally:
+        del os.environ["COVFN_JIT"]
+    after = cf.jit_stats()
+    assert after["failures"] == before["failures"]
+    assert after["compiled"] + after["cache_hits"] > before["compiled"] + before["cache_hits"]

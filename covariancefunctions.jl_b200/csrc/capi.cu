@@ -235,6 +235,8 @@ int ensure_padded_points(cf_gramian_s* g, Shard& sh, cudaStream_t stream) {
     return CF_OK;
 }
 
+int ensure_padded_points_f32(cf_gramian_s* g, Shard& sh, cudaStream_t stream);
+
 static bool env_flag(const char* name) {
     const char* e = std::getenv(name);
     return e && std::atoi(e) != 0;
@@ -271,13 +273,7 @@ int launch_mm(cf_gramian_s* g, Shard& sh, void* d_B, int64_t ldb, const void* d_
         P.Y = (sh.Y != sh.X) ? sh.yp.p : sh.xp.p;
     }
     if (tf32) {  // the column points with the padded row stride (B fragments); the row tile is transposed inside the kernel
-        const int sx = g->entry->mm_tf32_sx;
-        if (!sh.mmd_ready) {
-            if (int rc = sh.yp.ensure((size_t)g->m * sx * 4)) return rc;
-            cf_pad_rows_f32_kernel<<<148 * 8, 256, 0, stream>>>((const float*)sh.Y, g->D, sx, g->m, (float*)sh.yp.p);
-            CF_CUDA(cudaGetLastError());
-            sh.mmd_ready = true;
-        }
+        if (int rc = ensure_padded_points_f32(g, sh, stream)) return rc;
         P.X = sh.X;
         P.Y = sh.yp.p;
     }
@@ -769,6 +765,59 @@ int launch_mvm_dmma(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin
     return CF_OK;
 }
 
+// padded Float32 copy of the column points for the 3xTF32 kernels (B fragments), built once per shard
+int ensure_padded_points_f32(cf_gramian_s* g, Shard& sh, cudaStream_t stream) {
+    if (sh.mmd_ready) return CF_OK;
+    const int sx = g->entry->mm_tf32_sx;
+    if (int rc = sh.yp.ensure((size_t)g->m * sx * 4)) return rc;
+    cf_pad_rows_f32_kernel<<<148 * 8, 256, 0, stream>>>((const float*)sh.Y, g->D, sx, g->m, (float*)sh.yp.p);
+    CF_CUDA(cudaGetLastError());
+    sh.mmd_ready = true;
+    return CF_OK;
+}
+
+int launch_mvm_tf32(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const void* d_a, double alpha, double beta,
+                    cudaStream_t stream, const cf_peer_out* peers) {
+    const int64_t nrows = sh.r1 - sh.r0;
+    const cf_mvm_config& cfg = g->entry->mvm_tf32_cfg;
+    const int slot = cf_kind_slot(g->kind);
+    if (int rc = ensure_padded_points_f32(g, sh, stream)) return rc;
+    Plan pl = make_plan(nrows, g->m, cfg, sh.ctx->sms);
+    cf_mvm_params P;
+    std::memset(&P, 0, sizeof(P));
+    P.X = sh.X; P.Y = sh.yp.p; P.xn = sh.xn; P.yn = sh.yn; P.a = d_a;
+    P.sop = g->sop_val;
+    P.row0 = sh.r0; P.nrows = nrows; P.m = g->m;
+    P.cols_per_chunk = pl.cols_per_chunk;
+    P.alpha = alpha * g->coef; P.beta = beta;
+    P.use_tma = (((uintptr_t)d_a) % 16 == 0) ? 1 : 0;
+    if (g->prog.single) P.atom = g->prog.atoms[g->prog.terms[0].fac[0].atom].v;
+    P.direct = (pl.chunks == 1) ? 1 : 0;
+    P.peers = *peers;
+    if (P.direct) {
+        P.out = d_y; P.yin = d_yin;
+    } else {
+        if (int rc = sh.partial.ensure((size_t)pl.chunks * nrows * sizeof(double))) return rc;
+        P.out = sh.partial.p;
+    }
+    bool launched = false;
+    if (g->kind == CF_ATOM_SOP && cfjit::wanted((double)nrows * (double)g->m)) {
+        const std::string name = "gram_mvm_tf32_kernel<" + std::to_string(g->D) + ", " + std::to_string((int)CF_ATOM_SOP) + ">";
+        if (cfjit::Kernel* jit = cfjit::get_kernel(g->sop_val, "gram_mvm_tf32.cuh", name))
+            launched = cfjit::launch(jit, &P, (unsigned)pl.row_tiles, (unsigned)pl.chunks, 256, (unsigned)cfg.smem_bytes, stream) == 0;
+    }
+    if (!launched) CF_CUDA(g->entry->mvm_tf32[slot](P, dim3(pl.row_tiles, pl.chunks), stream));
+    g->last_launches++;
+    if (!P.direct) {
+        const int blocks = (int)std::min<int64_t>((nrows + 255) / 256, 4096);
+        gram_reduce_partials<float><<<blocks, 256, 0, stream>>>((const double*)sh.partial.p, pl.chunks, nrows, (float*)d_y, (const float*)d_yin,
+                                                                 alpha * g->coef, beta, *peers);
+        CF_CUDA(cudaGetLastError());
+        g->last_launches++;
+    }
+    return CF_OK;
+}
+
 int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const void* d_a, double alpha, double beta,
                cudaStream_t stream, const cf_peer_out* peers) {
     cf_peer_out no_peers;
@@ -791,6 +840,9 @@ int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const v
     const int slot = cf_kind_slot(g->kind);
     const bool dmma = dt == CF_F64 && g->use_norms && g->entry->mvm_dmma[slot] != nullptr && !env_flag("COVFN_MVM_SCALAR");
     if (dmma) return launch_mvm_dmma(g, sh, (double*)d_y, (const double*)d_yin, (const double*)d_a, alpha, beta, stream, peers);
+    // the Float32 counterpart: distance GEMM in 3xTF32 (gram_mvm_tf32.cuh)
+    if (dt == CF_F32 && g->use_norms && g->entry->mvm_tf32[slot] != nullptr && !env_flag("COVFN_MVM_SCALAR"))
+        return launch_mvm_tf32(g, sh, d_y, d_yin, d_a, alpha, beta, stream, peers);
     Plan pl = make_plan(nrows, g->m, cfg, sh.ctx->sms);
     cf_mvm_params P;
     std::memset(&P, 0, sizeof(P));

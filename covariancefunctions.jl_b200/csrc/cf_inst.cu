@@ -45,6 +45,8 @@ const cf_kernel_entry entry = {
     cf_mmt_entry<D>::fn,
     cf_mmt_entry<D>::sx,
     cf_mmt_entry<D>::smem,
+    {cf_mvt_entry<D>::fn[0], cf_mvt_entry<D>::fn[1], cf_mvt_entry<D>::fn[2], cf_mvt_entry<D>::fn[3]},
+    cf_mvt_entry<D>::cfg,
     {TU::R, TU::NT, TU::TJ, TU::NS, TU::MINB},
 };
 }  // namespace

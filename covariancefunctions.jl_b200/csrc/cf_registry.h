@@ -8,6 +8,7 @@
 #include "gram_mvm_dmma.cuh"
 #include "grad_mvm_dmma.cuh"
 #include "gram_mm_tf32.cuh"
+#include "gram_mvm_tf32.cuh"
 
 #define CF_NKINDS 4 /* EQ, MATERN, RQ_INT, SOP */
 inline int cf_kind_slot(int kind) {
@@ -37,6 +38,8 @@ struct cf_kernel_entry {
     cf_mm_launch_fn mm_tf32; // Float32 multi-RHS on the tensor cores in 3xTF32 (gram_mm_tf32.cuh), nullptr for D < 8
     int mm_tf32_sx;          // row stride (floats) of its padded point copies
     int mm_tf32_smem;        // its dynamic shared memory (run-time specialised launches)
+    cf_mvm_launch_fn mvm_tf32[CF_NKINDS]; // Float32 value MVM with the distance GEMM in 3xTF32 (gram_mvm_tf32.cuh), nullptr for D < 8
+    cf_mvm_config mvm_tf32_cfg;
     int tune[5];                     // R, NT, TJ, NS, MINB of the value MVM kernel (names the instantiation for cf_jit.h)
 };
 

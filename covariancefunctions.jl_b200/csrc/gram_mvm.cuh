@@ -124,6 +124,7 @@ __device__ __forceinline__ void cf_rows_value(const T (&x)[R][D], const T (&yj)[
         }
     } else {
         if constexpr (KIND == CF_ATOM_SOP) cf_sop_value_f32_n<R>(r2, dt, sop, kv);
+        else if constexpr (KIND == CF_ATOM_MATERN || KIND == CF_ATOM_RQ_INT) cf_atom_value_f32_n<R>(r2, dt, atom, kv); // one loop over p for R values
         else {
 #pragma unroll
             for (int r = 0; r < R; r++) kv[r] = cf_atom_value_f32<KIND>(r2[r], dt[r], atom);

@@ -127,3 +127,36 @@ def test_short_length_scales_disable_the_norm_expansion(cf, O):
         G2 = cf.gramian(k, X.T.copy())          # points scaled with the length scale: the expansion is safe again
         assert relerr(G2 @ a, O.mul_vec(k.program(), X, a)) < TOL64
         assert relerr(G2 @ A, O.mul_mat(k.program(), X, A)) < TOL64
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (1, 40), (5, 3), (129, 33)])
+def test_tensor_core_kernels_tiny_shapes(cf, O, shape):
+    """single point, fewer columns than one tile, one row past a tile boundary: every tensor-core kernel family
+    (value MVM, multi-RHS, gradient, value-gradient; Float64 and Float32)"""
+    n, m = shape
+    d = 16
+    rng = np.random.default_rng(1000 + 7 * n + m)
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    Y = rng.standard_normal((m, d)) / np.sqrt(d)
+    a = rng.standard_normal(m)
+    A = rng.standard_normal((m, 3))
+    k = cf.MaternP(2)
+    os.environ["COVFN_GRAD_DMMA"] = "1"
+    try:
+        G = cf.gramian(k, X.T.copy(), Y.T.copy())
+        assert relerr(G @ a, O.mul_vec(k.program(), X, a, Y=Y)) < TOL64
+        assert relerr(G @ A, O.mul_mat(k.program(), X, A, Y=Y)) < TOL64
+        ag = rng.standard_normal(m * d)
+        Gg = cf.gramian(cf.GradientKernel(k), X.T.copy(), Y.T.copy())
+        assert relerr(Gg @ ag, O.gradient_mul(k.program(), X, ag, Y=Y)) < TOL64
+        av = rng.standard_normal(m * (d + 1))
+        Gv = cf.gramian(cf.ValueGradientKernel(k), X.T.copy(), Y.T.copy())
+        assert relerr(Gv @ av, O.derivative_mul(k.program(), X, av, Y=Y, trait="isotropic", value_gradient=True)) < TOL64
+    finally:
+        del os.environ["COVFN_GRAD_DMMA"]
+    Xf, Yf = X.astype(np.float32), Y.astype(np.float32)
+    Gf = cf.gramian(k, Xf.T.copy(), Yf.T.copy())
+    t64 = O.mul_vec(k.program(), Xf.astype(np.float64), a.astype(np.float32).astype(np.float64), Y=Yf.astype(np.float64))
+    assert relerr((Gf @ a.astype(np.float32)).astype(np.float64), t64) < 1e-5
+    T64 = O.mul_mat(k.program(), Xf.astype(np.float64), A.astype(np.float32).astype(np.float64), Y=Yf.astype(np.float64))
+    assert relerr((Gf @ A.astype(np.float32)).astype(np.float64), T64) < 1e-5

@@ -1476,7 +1476,7 @@ int cf_jit_stats(int* compiled, int* cache_hits, int* failures, double* compile_
     cfjit::State& st = cfjit::state();
     std::lock_guard<std::mutex> lk(st.mu);
     if (compiled) *compiled = st.stats.compiled;
-    if (cache_hits) *cache_hits = st.stats.hits;
+    if (cache_hits) *cache_hits = st.stats.hits + st.stats.disk_hits;  // in-process and on-disk cache
     if (failures) *failures = st.stats.failures;
     if (compile_seconds) *compile_seconds = st.stats.compile_seconds;
     return CF_OK;

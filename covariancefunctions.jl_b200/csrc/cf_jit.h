@@ -16,8 +16,12 @@
 #include <dlfcn.h>
 #include <nvrtc.h>
 
+#include <sys/stat.h>
+#include <unistd.h>
+
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
 #include <map>
 #include <mutex>
 #include <string>
@@ -54,7 +58,7 @@ struct Kernel {
 };
 
 struct Stats {
-    int compiled = 0, hits = 0, failures = 0;
+    int compiled = 0, hits = 0, failures = 0, disk_hits = 0;
     double compile_seconds = 0.0;
 };
 
@@ -163,6 +167,60 @@ inline std::string shape_source(const cf_sop_val& P) {
            "#elif CF_JIT_PART == 2\n" + shape_source_part(P, true) + "#endif\n";
 }
 
+// ---- on-disk cache of compiled cubins: $COVFN_JIT_CACHE or ~/.cache/covfn_b200 (COVFN_JIT_CACHE=off disables) ------------------
+// The file name hashes the kernel name, the program structure and a stamp of this library build (the embedded headers change
+// with it), so a stale cubin can never be picked up; files are written to a temporary name and renamed.
+inline uint64_t fnv1a(const std::string& s, uint64_t h = 1469598103934665603ull) {
+    for (unsigned char c : s) { h ^= c; h *= 1099511628211ull; }
+    return h;
+}
+inline std::string cache_path(const std::string& key) {
+    const char* e = std::getenv("COVFN_JIT_CACHE");
+    std::string dir;
+    if (e && std::string(e) == "off") return "";
+    if (e && *e) dir = e;
+    else if (const char* h = std::getenv("HOME")) dir = std::string(h) + "/.cache/covfn_b200";
+    else return "";
+    ::mkdir((dir.substr(0, dir.rfind('/'))).c_str(), 0755);
+    ::mkdir(dir.c_str(), 0755);
+    uint64_t h = fnv1a(key);
+    for (int i = 0; i < cf_jit_num_headers; i++) h = fnv1a(cf_jit_header_srcs[i], h);  // build stamp: the embedded sources
+    char name[64];
+    std::snprintf(name, sizeof(name), "/%016llx.cubin", (unsigned long long)h);
+    return dir + name;
+}
+inline bool cache_read(const std::string& path, std::vector<char>& out, std::string& lowered) {
+    if (path.empty()) return false;
+    std::ifstream f(path, std::ios::binary);
+    if (!f) return false;
+    uint32_t nl = 0;
+    uint64_t nb = 0;
+    f.read(reinterpret_cast<char*>(&nl), 4);
+    f.read(reinterpret_cast<char*>(&nb), 8);
+    if (!f || nl == 0 || nl > 4096 || nb == 0 || nb > (1ull << 30)) return false;
+    lowered.resize(nl);
+    out.resize(nb);
+    f.read(&lowered[0], nl);
+    f.read(out.data(), (std::streamsize)nb);
+    return (bool)f;
+}
+inline void cache_write(const std::string& path, const std::vector<char>& cubin, const std::string& lowered) {
+    if (path.empty()) return;
+    const std::string tmp = path + "." + std::to_string((long)::getpid()) + ".tmp";
+    {
+        std::ofstream f(tmp, std::ios::binary);
+        if (!f) return;
+        const uint32_t nl = (uint32_t)lowered.size();
+        const uint64_t nb = cubin.size();
+        f.write(reinterpret_cast<const char*>(&nl), 4);
+        f.write(reinterpret_cast<const char*>(&nb), 8);
+        f.write(lowered.data(), nl);
+        f.write(cubin.data(), (std::streamsize)nb);
+        if (!f) { ::unlink(tmp.c_str()); return; }
+    }
+    if (::rename(tmp.c_str(), path.c_str()) != 0) ::unlink(tmp.c_str());
+}
+
 // Returns the specialised kernel for (shape of P, name_expr), compiling it on first use; nullptr if unavailable.
 inline Kernel* get_kernel(const cf_sop_val& P, const std::string& entry_header, const std::string& name_expr) {
     State& st = state();
@@ -181,6 +239,22 @@ inline Kernel* get_kernel(const cf_sop_val& P, const std::string& entry_header, 
     }
     Api& a = st.api;
     const bool verbose = std::getenv("COVFN_JIT_VERBOSE") != nullptr;
+    const std::string disk = cache_path(key);
+    {
+        std::vector<char> cubin0;
+        std::string lowered0;
+        CUlibrary lib0 = nullptr;
+        CUkernel kern0 = nullptr;
+        if (cache_read(disk, cubin0, lowered0) &&
+            a.LibraryLoadData(&lib0, cubin0.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == CUDA_SUCCESS &&
+            a.LibraryGetKernel(&kern0, lib0, lowered0.c_str()) == CUDA_SUCCESS) {
+            st.stats.disk_hits++;
+            if (verbose) std::fprintf(stderr, "[covfn_b200] specialised %s loaded from %s\n", key.c_str(), disk.c_str());
+            slot = new Kernel();
+            slot->k = kern0;
+            return slot;
+        }
+    }
     const std::string shape = shape_source(P);
     const std::string main_src = "#include \"" + entry_header + "\"\n";
     std::vector<const char*> names(cf_jit_header_names, cf_jit_header_names + cf_jit_num_headers);
@@ -221,6 +295,7 @@ inline Kernel* get_kernel(const cf_sop_val& P, const std::string& entry_header, 
              a.LibraryLoadData(&lib, cubin.data(), nullptr, nullptr, 0, nullptr, nullptr, 0) == CUDA_SUCCESS &&
              a.LibraryGetKernel(&kern, lib, lowered) == CUDA_SUCCESS;
     }
+    const std::string lowered_name = (ok && lowered) ? lowered : "";  // owned by the program: copy before destroying it
     a.DestroyProgram(&prog);
     clock_gettime(CLOCK_MONOTONIC, &t1);
     if (!ok) {
@@ -228,6 +303,7 @@ inline Kernel* get_kernel(const cf_sop_val& P, const std::string& entry_header, 
         st.stats.failures++;
         return nullptr;
     }
+    cache_write(disk, cubin, lowered_name);
     const double secs = (t1.tv_sec - t0.tv_sec) + 1e-9 * (t1.tv_nsec - t0.tv_nsec);
     st.stats.compiled++;
     st.stats.compile_seconds += secs;

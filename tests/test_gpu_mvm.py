@@ -307,3 +307,29 @@ def test_handles_return_all_device_memory(cf):
     torch.cuda.synchronize()
     free1, _ = torch.cuda.mem_get_info()
     assert free0 - free1 < 8 << 20, f"device memory shrank by {(free0 - free1) / 2**20:.1f} MiB over 12 handle lifetimes"
+
+
+def test_runtime_specialisation_disk_cache(tmp_path):
+    """a second process finds the compiled cubin in $COVFN_JIT_CACHE: no compilation, one cache hit, same result"""
+    import os
+    import subprocess
+    import sys
+    code = (
+        "import numpy as np, covfn_b200 as cf\n"
+        "rng = np.random.default_rng(3)\n"
+        "X = rng.standard_normal((500, 3)); a = rng.standard_normal(500)\n"
+        "k = 0.25 * cf.EQ() + cf.MaternP(3) * cf.RQ(2)\n"
+        "b = cf.gramian(k, X.T.copy()) @ a\n"
+        "s = cf.jit_stats()\n"
+        "print('STATS', s['compiled'], s['cache_hits'], s['failures'], repr(float(np.linalg.norm(b))))\n")
+    env = dict(os.environ, COVFN_JIT="1", COVFN_JIT_CACHE=str(tmp_path))
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for _ in range(2):
+        out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, out.stderr[-2000:]
+        outs.append([l for l in out.stdout.splitlines() if l.startswith("STATS")][0].split())
+    assert outs[0][1:4] == ["1", "0", "0"], outs[0]      # first process compiles
+    assert outs[1][1:4] == ["0", "1", "0"], outs[1]      # second process loads the cubin from disk
+    assert outs[0][4] == outs[1][4]                       # bit-identical result
+    assert any(f.endswith(".cubin") for f in os.listdir(tmp_path))

@@ -8,6 +8,11 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 
+# hermetic tests: the run-time specialised kernels are compiled in every test process unless a test opts in to the on-disk
+# cubin cache (tests/test_gpu_mvm.py::test_runtime_specialisation_disk_cache points it at a temporary directory)
+os.environ.setdefault("COVFN_JIT_CACHE", "off")
+
+
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 

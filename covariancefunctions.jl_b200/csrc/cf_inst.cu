@@ -30,8 +30,9 @@ const cf_kernel_entry entry = {
       &cf_grad_launch<D, CF_ATOM_SOP, CF_GRAD_DOT, true, TU::GR, TU::GNT, TU::GTJ, TU::NS, TU::GMINB>}},
     {{TU::GNT * TU::GR, TU::GTJ, cf_grad_smem<D, TU::GTJ, TU::NS, false>::total, TU::GMINB},
      {TU::GNT * TU::GR, TU::GTJ, cf_grad_smem<D, TU::GTJ, TU::NS, true>::total, TU::GMINB}},
-    // fp32: 512 threads (+15 %).  fp64: 256 threads; the 512-thread form (x_i in shared memory, 122 registers, no spills) measured
-    // the same 0.98 s at config 3, so the extra warps are not what limits it -- kept selectable for the next tuning round.
+    // scalar multi-RHS kernels (d < 8, ill-scaled points, COVFN_MM_SCALAR): fp32 at 512 threads (+15 %), fp64 at 256 threads with the
+    // x tile in shared memory and 8-wide program evaluation.  Both are bound by shared-memory operand delivery; well-scaled
+    // points with d >= 8 go to the tensor-core kernels below (DMMA for fp64, 3xTF32 for fp32).
     {&cf_mm_launch<float, D, 512>, &cf_mm_launch<double, D, 256>},
     cf_mmd_entry<D>::fn,
     cf_mmd_entry<D>::smem,

@@ -369,6 +369,11 @@ def main():
         # (profiles/r1_ncu_mvm_eq_c2_n1048576.md): 33.90 MB + 0.76 MB per launch; only known for the 1-GPU c2 shape
         "traffic": 34653184 if (args.config == "c2" and world == 1) else None,
         "kernel_ms": kernel_ms, "flops_per_pair": 2 * slots,
+        # `frac` uses SURVEY.md 8d's fixed reference instruction sequence (exp = 16 slots, distance = 2 d), so a kernel with a
+        # cheaper exp (9 FP64 instructions here) or a tensor-core distance can exceed 1; the counter-level view is in profiles/
+        "note": "reference-slot accounting (implementation independent); executed FP64 instructions per pair for c2: 15 of the "
+                "23 slots -> the FP64 pipe itself is at frac * 15 / 23 of the probe peak (ncu: 78.8 % pipe-active)",
+        "fp64_instr_frac": (achieved_tflops / peak_tflops) * 15.0 / 23.0 if args.config == "c2" else None,
         "peak_source": "cf_peak_probe DFMA microbenchmark in this run (MEASURED_PEAKS.json has no FP64 entry); "
                        "nominal 64 DFMA/clk/SM x 148 SMs x 1.965 GHz = 37.2 TFLOP/s",
         "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,

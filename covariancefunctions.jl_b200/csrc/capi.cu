@@ -912,9 +912,10 @@ int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, co
         const bool eq = g->prog.single && g->prog.atoms[g->prog.terms[0].fac[0].atom].v.kind == CF_ATOM_EQ;
         const bool matern = g->prog.single && g->prog.atoms[g->prog.terms[0].fac[0].atom].v.kind == CF_ATOM_MATERN &&
                             g->prog.atoms[g->prog.terms[0].fac[0].atom].v.p >= 2;
-        cf_gradd_launch_fn fn = g->entry->grad_dmma[vg][eq ? 0 : (matern ? 2 : 1)];
+        const bool dot = g->prog.dotproduct != 0;  // nothing cancels in the dot-product form: no scale check needed
+        cf_gradd_launch_fn fn = g->entry->grad_dmma[vg][dot ? 3 : (eq ? 0 : (matern ? 2 : 1))];
         // (below ~2^22 blocks the extra preparation launches cost more than the tensor cores save)
-        if (!g->prog.dotproduct && g->use_norms_grad && fn &&
+        if ((dot || g->use_norms_grad) && fn &&
             ((double)nrows * (double)g->m >= 4194304.0 || env_flag("COVFN_GRAD_DMMA")) && !env_flag("COVFN_GRAD_SCALAR")) {
             if (int rc = ensure_padded_points(g, sh, stream)) return rc;
             const int sx = (D % 8 == 4) ? D : D + 4;

@@ -40,8 +40,8 @@ const cf_kernel_entry entry = {
      &cf_sym_launch<D, CF_ATOM_RQ_INT, TU::R, TU::NT, TU::TJ, TU::NS, 1>, &cf_sym_launch<D, CF_ATOM_SOP, TU::R, TU::NT, TU::TJ, TU::NS, 1>},
     {cf_mvd_entry<D>::fn[0], cf_mvd_entry<D>::fn[1], cf_mvd_entry<D>::fn[2], cf_mvd_entry<D>::fn[3]},
     cf_mvd_entry<D>::cfg,
-    {{cf_gradd_entry<D>::fn[0][0], cf_gradd_entry<D>::fn[0][1], cf_gradd_entry<D>::fn[0][2]},
-     {cf_gradd_entry<D>::fn[1][0], cf_gradd_entry<D>::fn[1][1], cf_gradd_entry<D>::fn[1][2]}},
+    {{cf_gradd_entry<D>::fn[0][0], cf_gradd_entry<D>::fn[0][1], cf_gradd_entry<D>::fn[0][2], cf_gradd_entry<D>::fn[0][3]},
+     {cf_gradd_entry<D>::fn[1][0], cf_gradd_entry<D>::fn[1][1], cf_gradd_entry<D>::fn[1][2], cf_gradd_entry<D>::fn[1][3]}},
     cf_gradd_entry<D>::cfg,
     cf_mmt_entry<D>::fn,
     cf_mmt_entry<D>::sx,

@@ -33,7 +33,7 @@ struct cf_kernel_entry {
     cf_sym_launch_fn sym[CF_NKINDS]; // Float64 symmetric variant, [kind slot]
     cf_mvm_launch_fn mvm_dmma[CF_NKINDS]; // Float64 tensor-core value MVM (gram_mvm_dmma.cuh), nullptr when unavailable for D
     cf_mvm_config mvm_dmma_cfg;
-    cf_gradd_launch_fn grad_dmma[2][3]; // Float64 tensor-core isotropic gradient MVM: [value_gradient][0 EQ, 1 generic, 2 MaternP(p>=2)]; nullptr when unavailable
+    cf_gradd_launch_fn grad_dmma[2][4]; // Float64 tensor-core gradient MVM: [value_gradient][0 EQ, 1 generic isotropic, 2 MaternP(p>=2), 3 dot product]; nullptr when unavailable
     cf_mvm_config grad_dmma_cfg;
     cf_mm_launch_fn mm_tf32; // Float32 multi-RHS on the tensor cores in 3xTF32 (gram_mm_tf32.cuh), nullptr for D < 8
     int mm_tf32_sx;          // row stride (floats) of its padded point copies

@@ -51,7 +51,10 @@ static __global__ void cf_rowdot_kernel(const double* __restrict__ Y, const doub
 
 // VG = true: ValueGradientKernel, blocks (d+1) x (d+1) with entry 0 the value observation (reference src/gradient.jl:442-463):
 //   b_g += ca a_g + cw r with cw = -4 k2 (r.a_g) + 2 k1 a_0,   b_0 += k a_0 - 2 k1 (r.a_g)   -- two more per-entry FMAs and a row sum
-template <int D, int KIND, bool VG>
+// MODE = CF_GRAD_DOT: DotProductInput programs (reference src/gradient.jl:109-115): the variable is t = x.y (GEMM 1 as it is, no
+//   norms, nothing to cancel), s = x_i.a_g (GEMM 2 as it is), b_g += k1 a_g + (k2 s + k1 a_0) y,  b_0 += k a_0 + k1 s
+//   -> [Ca | Cw] . [A; Y] with ca = k1, cw = k2 s (+ k1 a_0), no row-sum term.
+template <int D, int KIND, bool VG, int MODE = CF_GRAD_ISO>
 __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_constant__ cf_gradd_params PP) {
     using S = cf_gd_smem<D>;
     constexpr int SX = S::sx, SC = CF_GD_SC, NTB = 256, TJ = CF_GD_TJ, TI = CF_GD_TI, NS = CF_GD_NS, NCB = D / 8;
@@ -218,9 +221,14 @@ __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_cons
 #pragma unroll
                     for (int u = 0; u < 8; u++) {
                         const int col = 8 * (u >> 1) + 2 * t4 + (u & 1);
-                        const double v = fma(-2.0, c[rb][u >> 1][u & 1], xnorm[rb] + yn8[u]);
-                        Cc[col * SC + row] = (__double2hiint(v) < 0) ? 0.0 : v;
-                        Cc[(TJ + col) * SC + row] = p[rb][u >> 1][u & 1] - q8[u];
+                        if constexpr (MODE == CF_GRAD_DOT) {
+                            Cc[col * SC + row] = c[rb][u >> 1][u & 1];
+                            Cc[(TJ + col) * SC + row] = p[rb][u >> 1][u & 1];
+                        } else {
+                            const double v = fma(-2.0, c[rb][u >> 1][u & 1], xnorm[rb] + yn8[u]);
+                            Cc[col * SC + row] = (__double2hiint(v) < 0) ? 0.0 : v;
+                            Cc[(TJ + col) * SC + row] = p[rb][u >> 1][u & 1] - q8[u];
+                        }
                     }
                 }
 #pragma unroll 1
@@ -236,18 +244,19 @@ __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_cons
                     for (int u = 0; u < 8; u++) {
                         const int col = 8 * (u >> 1) + 2 * t4 + (u & 1);
                         const double sdot = Cc[(TJ + col) * SC + row];
-                        double ca = -2.0 * k1[u];
-                        double cw = -4.0 * k2[u] * sdot;
+                        double ca, cw;
+                        if constexpr (MODE == CF_GRAD_DOT) { ca = k1[u]; cw = k2[u] * sdot; }
+                        else { ca = -2.0 * k1[u]; cw = -4.0 * k2[u] * sdot; }
                         if constexpr (VG) {
                             double v0 = fma(kv[u], a08[u], ca * sdot);
                             if (ragged && col >= cnt) v0 = 0.0;
                             b0s += v0;
-                            cw = fma(-ca, a08[u], cw);
+                            cw = (MODE == CF_GRAD_DOT) ? fma(ca, a08[u], cw) : fma(-ca, a08[u], cw);
                         }
                         if (ragged && col >= cnt) { ca = 0.0; cw = 0.0; }
                         cws += cw;
                         Cc[col * SC + row] = ca;
-                        Cc[(TJ + col) * SC + row] = -cw;
+                        Cc[(TJ + col) * SC + row] = (MODE == CF_GRAD_DOT) ? cw : -cw;
                     }
                     if (rb == 0) { cwsum[0] += cws; b0sum[0] += b0s; }
                     else { cwsum[1] += cws; b0sum[1] += b0s; }
@@ -323,7 +332,7 @@ __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_cons
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 const int cidx = 8 * cb + 2 * t4 + e;
-                o[cidx] = coef * fma(Xs[row * SX + cidx], cwsum[rb], out[rb][cb][e]);
+                o[cidx] = (MODE == CF_GRAD_DOT) ? coef * out[rb][cb][e] : coef * fma(Xs[row * SX + cidx], cwsum[rb], out[rb][cb][e]);
             }
         if (VG && t4 == 0) P.partial0[(int64_t)blockIdx.y * P.nrows + (i - P.row0)] = coef * b0sum[rb];
     }
@@ -331,10 +340,10 @@ __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_cons
 
 #ifndef __CUDACC_RTC__ // host side
 typedef cudaError_t (*cf_gradd_launch_fn)(const cf_gradd_params& P, dim3 grid, cudaStream_t stream);
-template <int D, int KIND, bool VG>
+template <int D, int KIND, bool VG, int MODE = CF_GRAD_ISO>
 cudaError_t cf_gradd_launch(const cf_gradd_params& P, dim3 grid, cudaStream_t stream) {
     using S = cf_gd_smem<D>;
-    auto kern = grad_mvm_dmma_kernel<D, KIND, VG>;
+    auto kern = grad_mvm_dmma_kernel<D, KIND, VG, MODE>;
     static bool configured[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -350,15 +359,17 @@ cudaError_t cf_gradd_launch(const cf_gradd_params& P, dim3 grid, cudaStream_t st
 // registry hook: padded dimensions that are multiples of 8 (output fragments are 8 coordinates wide)
 template <int D, bool OK = (D >= 8 && D % 8 == 0)>
 struct cf_gradd_entry {
-    // [value_gradient][0 EQ specialised, 1 generic isotropic, 2 single MaternP(p >= 2)]
-    static constexpr cf_gradd_launch_fn fn[2][3] = {{nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr}};
+    // [value_gradient][0 EQ specialised, 1 generic isotropic, 2 single MaternP(p >= 2), 3 dot-product programs]
+    static constexpr cf_gradd_launch_fn fn[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};
     static constexpr cf_mvm_config cfg = {CF_GD_TI, CF_GD_TJ, 0, 1};
 };
 template <int D>
 struct cf_gradd_entry<D, true> {
-    static constexpr cf_gradd_launch_fn fn[2][3] = {
-        {&cf_gradd_launch<D, CF_ATOM_EQ, false>, &cf_gradd_launch<D, CF_ATOM_SOP, false>, &cf_gradd_launch<D, CF_ATOM_MATERN, false>},
-        {&cf_gradd_launch<D, CF_ATOM_EQ, true>, &cf_gradd_launch<D, CF_ATOM_SOP, true>, &cf_gradd_launch<D, CF_ATOM_MATERN, true>}};
+    static constexpr cf_gradd_launch_fn fn[2][4] = {
+        {&cf_gradd_launch<D, CF_ATOM_EQ, false>, &cf_gradd_launch<D, CF_ATOM_SOP, false>, &cf_gradd_launch<D, CF_ATOM_MATERN, false>,
+         &cf_gradd_launch<D, CF_ATOM_SOP, false, CF_GRAD_DOT>},
+        {&cf_gradd_launch<D, CF_ATOM_EQ, true>, &cf_gradd_launch<D, CF_ATOM_SOP, true>, &cf_gradd_launch<D, CF_ATOM_MATERN, true>,
+         &cf_gradd_launch<D, CF_ATOM_SOP, true, CF_GRAD_DOT>}};
     static constexpr cf_mvm_config cfg = {CF_GD_TI, CF_GD_TJ, cf_gd_smem<D>::total, 1};
 };
 #endif // !__CUDACC_RTC__

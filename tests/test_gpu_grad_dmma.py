@@ -125,3 +125,26 @@ def test_value_gradient_dmma(cf, O, d):
     b = b0.copy()
     cf.mul_(b, G, v, -0.7, 0.4)
     assert relerr(b, O.derivative_mul(k.program(), Xs, v, trait="isotropic", value_gradient=True, alpha=-0.7, beta=0.4, y0=b0)) < TOL64
+
+
+@pytest.mark.parametrize("d", [8, 16, 32])
+def test_dot_product_programs_on_tensor_cores(cf, O, d):
+    """DotProductInput kernels (reference src/gradient.jl:109-115): t = x.y and s = x.a_g are GEMMs as they are, nothing cancels,
+    so the tensor-core kernel is used whatever the scale of the points"""
+    rng = np.random.default_rng(700 + d)
+    n, m = 170, 290
+    X = rng.standard_normal((n, d))  # deliberately not scaled by 1/sqrt(d)
+    Y = rng.standard_normal((m, d))
+    for name, k in {"dot2": cf.Dot() ** 2, "poly3": (cf.Dot() + 1.0) ** 3, "line_plus_dot2": 0.5 * cf.Dot() ** 2 + cf.Dot() + 0.3}.items():
+        for vg in (False, True):
+            K = cf.ValueGradientKernel(k) if vg else cf.GradientKernel(k)
+            bs = d + (1 if vg else 0)
+            a = rng.standard_normal(m * bs)
+            G = cf.gramian(K, X.T.copy(), Y.T.copy())
+            b = G @ a
+            ref = O.derivative_mul(k.program(), X, a, Y=Y, trait="dot", value_gradient=vg)
+            assert relerr(b, ref) < TOL64, (d, name, vg)
+            bsc = _scalar(lambda: G @ a)
+            assert relerr(b, bsc) < 1e-13, (d, name, vg)
+            if name == "dot2" and not vg:
+                assert not np.array_equal(b, bsc), "expected the tensor-core kernel"

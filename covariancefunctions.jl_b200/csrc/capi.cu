@@ -223,7 +223,7 @@ int launch_dense(cf_gramian_s* g, Shard& sh, void* d_M, int64_t ld, int64_t j0, 
 // point copies with the row stride (= 4 mod 8 doubles) the DMMA kernels read fragments from, built once per shard
 int ensure_padded_points(cf_gramian_s* g, Shard& sh, cudaStream_t stream) {
     if (sh.mmd_ready) return CF_OK;
-    const int sx = (g->D % 8 == 4) ? g->D : g->D + 4;
+    const int sx = (g->D % 8 == 4) ? g->D + 8 : g->D + 4;  // cf_mmd_smem<D>::sx
     if (int rc = sh.xp.ensure((size_t)g->n * sx * 8)) return rc;
     cf_pad_rows_kernel<<<148 * 8, 256, 0, stream>>>((const double*)sh.X, g->D, sx, g->n, (double*)sh.xp.p);
     if (sh.Y != sh.X) {
@@ -918,7 +918,7 @@ int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, co
         if ((dot || g->use_norms_grad) && fn &&
             ((double)nrows * (double)g->m >= 4194304.0 || env_flag("COVFN_GRAD_DMMA")) && !env_flag("COVFN_GRAD_SCALAR")) {
             if (int rc = ensure_padded_points(g, sh, stream)) return rc;
-            const int sx = (D % 8 == 4) ? D : D + 4;
+            const int sx = (D % 8 == 4) ? D + 8 : D + 4;  // cf_mmd_smem<D>::sx
             const cf_mvm_config& cfgd = g->entry->grad_dmma_cfg;
             Plan pl = make_plan(nrows, g->m, cfgd, sh.ctx->sms);
             // padded gradient weights, then q_j = y_j . a_j, then the value weights (ValueGradient): all 16-byte aligned TMA sources

@@ -1,5 +1,5 @@
 // grad_mvm_dmma.cuh -- K5d: isotropic GradientKernel O(n^2 d) matrix-vector product with every d-dependent operation on the
-// FP64 tensor cores (DMMA m8n8k4).  Float64, padded D in {8, 16, 24, 32}, well-scaled points (same host check as K1d / K4d).
+// FP64 tensor cores (DMMA m8n8k4).  Float64, padded D in {8, 12, 16, 24, 32}, well-scaled points (same host check as K1d / K4d).
 //
 // Replaces blockmul!(y, G::Gramian, x, alpha, beta) (reference src/gramian.jl:241-253) with the lazy
 // IsotropicGradientKernelElement product (reference src/gradient.jl:86-92)
@@ -57,7 +57,7 @@ static __global__ void cf_rowdot_kernel(const double* __restrict__ Y, const doub
 template <int D, int KIND, bool VG, int MODE = CF_GRAD_ISO>
 __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_constant__ cf_gradd_params PP) {
     using S = cf_gd_smem<D>;
-    constexpr int SX = S::sx, SC = CF_GD_SC, NTB = 256, TJ = CF_GD_TJ, TI = CF_GD_TI, NS = CF_GD_NS, NCB = D / 8;
+    constexpr int SX = S::sx, SC = CF_GD_SC, NTB = 256, TJ = CF_GD_TJ, TI = CF_GD_TI, NS = CF_GD_NS, NCB = (D + 7) / 8;
     const cf_grad_params& P = PP.g;
     extern __shared__ __align__(128) unsigned char smem[];
     double* tbl = reinterpret_cast<double*>(smem);
@@ -332,7 +332,7 @@ __global__ void __launch_bounds__(256, 1) grad_mvm_dmma_kernel(const __grid_cons
 #pragma unroll
             for (int e = 0; e < 2; e++) {
                 const int cidx = 8 * cb + 2 * t4 + e;
-                o[cidx] = (MODE == CF_GRAD_DOT) ? coef * out[rb][cb][e] : coef * fma(Xs[row * SX + cidx], cwsum[rb], out[rb][cb][e]);
+                if (cidx < D) o[cidx] = (MODE == CF_GRAD_DOT) ? coef * out[rb][cb][e] : coef * fma(Xs[row * SX + cidx], cwsum[rb], out[rb][cb][e]);
             }
         if (VG && t4 == 0) P.partial0[(int64_t)blockIdx.y * P.nrows + (i - P.row0)] = coef * b0sum[rb];
     }
@@ -356,8 +356,8 @@ cudaError_t cf_gradd_launch(const cf_gradd_params& P, dim3 grid, cudaStream_t st
     return cudaGetLastError();
 }
 
-// registry hook: padded dimensions that are multiples of 8 (output fragments are 8 coordinates wide)
-template <int D, bool OK = (D >= 8 && D % 8 == 0)>
+// registry hook: padded dimensions >= 8 that are multiples of 4 (D = 12: the second 8-wide output block is half padding)
+template <int D, bool OK = (D >= 8 && D % 4 == 0)>
 struct cf_gradd_entry {
     // [value_gradient][0 EQ specialised, 1 generic isotropic, 2 single MaternP(p >= 2), 3 dot-product programs]
     static constexpr cf_gradd_launch_fn fn[2][4] = {{nullptr, nullptr, nullptr, nullptr}, {nullptr, nullptr, nullptr, nullptr}};

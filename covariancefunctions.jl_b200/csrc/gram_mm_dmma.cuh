@@ -22,7 +22,8 @@
 
 template <int D>
 struct cf_mmd_smem {
-    static constexpr int sx = (D % 8 == 4) ? D : D + 4;  // row stride of the padded point copies
+    // row stride of the padded point copies: = 4 (mod 8) and >= the next multiple of 8 (the gradient kernel reads 8-wide column blocks)
+    static constexpr int sx = (D % 8 == 4) ? D + 8 : D + 4;
     static constexpr int tbl_bytes = CF_EXP_TBL_DOUBLES * 8;
     static constexpr int bar_bytes = 128;
     static constexpr int ks_bytes = CF_MM_TJ * CF_MMD_SK * 8;

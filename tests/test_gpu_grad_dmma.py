@@ -1,4 +1,4 @@
-"""Parity of the Float64 tensor-core isotropic gradient-kernel MVM (csrc/grad_mvm_dmma.cuh, padded D in {8, 16, 24, 32},
+"""Parity of the Float64 tensor-core isotropic gradient-kernel MVM (csrc/grad_mvm_dmma.cuh, padded D in {8, 12, 16, 24, 32},
 well-scaled points) against the oracle and against the scalar kernel K5 it replaces.  Reference semantics:
 blockmul!(y, G::Gramian, x, alpha, beta) src/gramian.jl:241-253 with mul!(b, ::IsotropicGradientKernelElement, a, alpha, beta)
 src/gradient.jl:86-92; the shapes follow test/gradient.jl:29-52 (lazy operator vs dense matrix, 5-argument mul!)."""
@@ -44,7 +44,7 @@ def _kernels(cf):
     }
 
 
-@pytest.mark.parametrize("d", [8, 16, 24, 32])
+@pytest.mark.parametrize("d", [8, 11, 12, 16, 24, 32])
 def test_grad_dmma_dims_ragged_rectangular(cf, O, d):
     rng = np.random.default_rng(300 + d)
     n, m = 203, 301  # neither a multiple of the 128-row / 32-column tiles
@@ -98,7 +98,7 @@ def test_grad_dmma_dense_operator_and_symmetry(cf, O):
     assert abs(u @ (G @ v) - v @ (G @ u)) < 1e-12 * np.linalg.norm(u) * np.linalg.norm(v) * np.linalg.norm(M, 2)
 
 
-@pytest.mark.parametrize("d", [8, 16, 32])
+@pytest.mark.parametrize("d", [8, 10, 16, 32])
 def test_value_gradient_dmma(cf, O, d):
     """ValueGradientKernel blocks (d+1) x (d+1) (reference src/gradient.jl:400-474) on the tensor-core kernel"""
     rng = np.random.default_rng(400 + d)
@@ -127,7 +127,7 @@ def test_value_gradient_dmma(cf, O, d):
     assert relerr(b, O.derivative_mul(k.program(), Xs, v, trait="isotropic", value_gradient=True, alpha=-0.7, beta=0.4, y0=b0)) < TOL64
 
 
-@pytest.mark.parametrize("d", [8, 16, 32])
+@pytest.mark.parametrize("d", [8, 12, 16, 32])
 def test_dot_product_programs_on_tensor_cores(cf, O, d):
     """DotProductInput kernels (reference src/gradient.jl:109-115): t = x.y and s = x.a_g are GEMMs as they are, nothing cancels,
     so the tensor-core kernel is used whatever the scale of the points"""

@@ -12,6 +12,6 @@ from ._lib import (CovFnError, CudaError, DimensionMismatch, DomainError, Unsupp
 from .kernels import (ARD, EQ, RQ, AbstractKernel, Constant, Dot, DotProductInput, Exp, Exponential, ExponentiatedQuadratic,
                       GenericInput, GradientKernel, IsotropicInput, IsotropicKernel, Lengthscale, Line, Matern, MaternP,
                       Poly, Polynomial, Power, Product, RationalQuadratic, Sum, ValueGradientKernel, input_trait)
-from .gramian import Diagonal, Gramian, I, LazyMatrixSum, gramian, jit_stats, mul_, peak_probe
+from .gramian import Diagonal, Gramian, I, LazyMatrixSum, gramian, jit_check, jit_stats, mul_, peak_probe
 
 __all__ = [n for n in dir() if not n.startswith("_")]

@@ -77,6 +77,7 @@ SYMBOLS = {
     "cf_last_timing": (_int, [_vp, C.POINTER(C.c_float), C.POINTER(_int)]),
     "cf_peak_probe": (_int, [_int, _int, C.POINTER(_dbl), C.POINTER(C.c_float)]),
     "cf_jit_stats": (_int, [C.POINTER(_int), C.POINTER(_int), C.POINTER(_int), C.POINTER(_dbl)]),
+    "cf_jit_check": (_int, [C.POINTER(KNode), _int, _int, _int, C.c_char_p, _int]),
 }
 
 _lib = None

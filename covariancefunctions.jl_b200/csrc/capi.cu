@@ -1475,6 +1475,48 @@ int cf_peak_probe(int kind, int iters, double* lane_ops_per_s, float* ms) {
     return peak_probe_impl(kind, iters, lane_ops_per_s, ms);
 }
 
+int cf_jit_check(const cf_knode_t* prog, int nnodes, int d, int which, char* log, int loglen) {
+    if (log && loglen > 0) log[0] = 0;
+    cf_program lowered;
+    cf_sop_val sop_val;
+    try {
+        lowered = cf::lower(prog, nnodes);
+        cf::to_sop_val(lowered, sop_val);
+    } catch (const cf::LowerError& e) {
+        return fail(e.code, "cf_jit_check: %s", e.msg.c_str());
+    } catch (...) {
+        return fail(CF_ERR_INTERNAL, "cf_jit_check: unexpected failure while lowering the kernel program");
+    }
+    const cf_kernel_entry* entry = find_entry(d);
+    if (!entry) return fail(CF_ERR_UNSUPPORTED, "cf_jit_check: d = %d > 32 has no specialised kernels", d);
+    const int D = entry->D;
+    const int* tu = entry->tune;
+    const std::string sD = std::to_string(D), sop = std::to_string((int)CF_ATOM_SOP);
+    std::string header, name;
+    switch (which) {
+        case 0:
+            header = "gram_mvm.cuh";
+            name = "gram_mvm_kernel<double, " + sD + ", " + sop + ", " + std::to_string(tu[0]) + ", " + std::to_string(tu[1]) + ", " +
+                   std::to_string(tu[2]) + ", " + std::to_string(tu[3]) + ", " + std::to_string(tu[4]) + ">";
+            break;
+        case 1: header = "gram_mm_dmma.cuh"; name = "gram_mm_dmma_kernel<" + sD + ">"; break;
+        case 2: header = "gram_mvm_dmma.cuh"; name = "gram_mvm_dmma_kernel<" + sD + ", " + sop + ">"; break;
+        case 3: header = "gram_mm_tf32.cuh"; name = "gram_mm_tf32_kernel<" + sD + ">"; break;
+        case 4: header = "gram_mvm_tf32.cuh"; name = "gram_mvm_tf32_kernel<" + sD + ", " + sop + ">"; break;
+        default: return fail(CF_ERR_BAD_ARGUMENT, "cf_jit_check: which must be 0..4");
+    }
+    if (which >= 1 && (D < 8 || (which <= 2 && D % 4 != 0))) return fail(CF_ERR_UNSUPPORTED, "cf_jit_check: no tensor-core kernel for D = %d", D);
+    std::string text;
+    size_t nb = 0;
+    const int rc = cfjit::compile_only(sop_val, header, name, text, &nb);
+    if (log && loglen > 0) {
+        std::snprintf(log, (size_t)loglen, "%s", text.c_str());
+    }
+    if (rc == 1) return fail(CF_ERR_UNSUPPORTED, "cf_jit_check: NVRTC is not available (%s)", text.c_str());
+    if (rc != 0) return fail(CF_ERR_INTERNAL, "cf_jit_check: compilation of %s failed", name.c_str());
+    return CF_OK;
+}
+
 int cf_jit_stats(int* compiled, int* cache_hits, int* failures, double* compile_seconds) {
     cfjit::State& st = cfjit::state();
     std::lock_guard<std::mutex> lk(st.mu);

@@ -33,7 +33,7 @@
 namespace cfjit {
 
 struct Api {
-    bool tried = false, ok = false;
+    bool tried = false, ok = false, nvrtc_tried = false, nvrtc_ok = false;
     std::string why;
     nvrtcResult (*CreateProgram)(nvrtcProgram*, const char*, const char*, int, const char* const*, const char* const*) = nullptr;
     nvrtcResult (*DestroyProgram)(nvrtcProgram*) = nullptr;
@@ -79,9 +79,11 @@ bool sym(void* h, const char* name, F& out) {
     return out != nullptr;
 }
 
-inline bool load_api(Api& a) {
-    if (a.tried) return a.ok;
-    a.tried = true;
+// NVRTC alone is enough to COMPILE a specialisation (cf_jit_check, also on a machine without a GPU); loading and launching
+// additionally needs the driver
+inline bool load_nvrtc(Api& a) {
+    if (a.nvrtc_tried) return a.nvrtc_ok;
+    a.nvrtc_tried = true;
     if (std::getenv("COVFN_JIT_TEST_NO_NVRTC")) { a.why = "disabled for testing"; return false; }  // exercises the fallback path
     void* hn = nullptr;
     std::vector<std::string> cands;
@@ -90,18 +92,25 @@ inline bool load_api(Api& a) {
     for (const auto& c : cands)
         if ((hn = dlopen(c.c_str(), RTLD_NOW | RTLD_LOCAL))) break;
     if (!hn) { a.why = "libnvrtc not found"; return false; }
+    a.nvrtc_ok = sym(hn, "nvrtcCreateProgram", a.CreateProgram) && sym(hn, "nvrtcDestroyProgram", a.DestroyProgram) &&
+                 sym(hn, "nvrtcCompileProgram", a.CompileProgram) && sym(hn, "nvrtcGetProgramLogSize", a.GetProgramLogSize) &&
+                 sym(hn, "nvrtcGetProgramLog", a.GetProgramLog) && sym(hn, "nvrtcGetCUBINSize", a.GetCUBINSize) &&
+                 sym(hn, "nvrtcGetCUBIN", a.GetCUBIN) && sym(hn, "nvrtcAddNameExpression", a.AddNameExpression) &&
+                 sym(hn, "nvrtcGetLoweredName", a.GetLoweredName);
+    if (!a.nvrtc_ok) a.why = "missing NVRTC entry points";
+    return a.nvrtc_ok;
+}
+inline bool load_api(Api& a) {
+    if (a.tried) return a.ok;
+    a.tried = true;
+    if (!load_nvrtc(a)) return false;
     void* hc = dlopen("libcuda.so.1", RTLD_NOW | RTLD_LOCAL);
     if (!hc) { a.why = "libcuda.so.1 not found"; return false; }
-    bool ok = sym(hn, "nvrtcCreateProgram", a.CreateProgram) && sym(hn, "nvrtcDestroyProgram", a.DestroyProgram) &&
-              sym(hn, "nvrtcCompileProgram", a.CompileProgram) && sym(hn, "nvrtcGetProgramLogSize", a.GetProgramLogSize) &&
-              sym(hn, "nvrtcGetProgramLog", a.GetProgramLog) && sym(hn, "nvrtcGetCUBINSize", a.GetCUBINSize) &&
-              sym(hn, "nvrtcGetCUBIN", a.GetCUBIN) && sym(hn, "nvrtcAddNameExpression", a.AddNameExpression) &&
-              sym(hn, "nvrtcGetLoweredName", a.GetLoweredName) && sym(hc, "cuLibraryLoadData", a.LibraryLoadData) &&
-              sym(hc, "cuLibraryGetKernel", a.LibraryGetKernel) && sym(hc, "cuKernelSetAttribute", a.KernelSetAttribute) &&
-              sym(hc, "cuLaunchKernel", a.LaunchKernel) && sym(hc, "cuDeviceGet", a.DeviceGet);
-    if (!ok) a.why = "missing NVRTC / driver entry points";
-    a.ok = ok;
-    return ok;
+    a.ok = sym(hc, "cuLibraryLoadData", a.LibraryLoadData) && sym(hc, "cuLibraryGetKernel", a.LibraryGetKernel) &&
+           sym(hc, "cuKernelSetAttribute", a.KernelSetAttribute) && sym(hc, "cuLaunchKernel", a.LaunchKernel) &&
+           sym(hc, "cuDeviceGet", a.DeviceGet);
+    if (!a.ok) a.why = "missing driver entry points";
+    return a.ok;
 }
 
 inline const char* kind_name(int kind) {
@@ -219,6 +228,40 @@ inline void cache_write(const std::string& path, const std::vector<char>& cubin,
         if (!f) { ::unlink(tmp.c_str()); return; }
     }
     if (::rename(tmp.c_str(), path.c_str()) != 0) ::unlink(tmp.c_str());
+}
+
+// Compile (only) the specialisation of `name_expr` from `entry_header` for the structure of P; returns 0 on success, 1 if NVRTC is
+// unavailable, 2 on a compilation error.  `log` receives the NVRTC log or the reason.
+inline int compile_only(const cf_sop_val& P, const std::string& entry_header, const std::string& name_expr, std::string& log,
+                        size_t* cubin_bytes) {
+    State& st = state();
+    std::lock_guard<std::mutex> lk(st.mu);
+    if (!load_nvrtc(st.api)) { log = st.api.why; return 1; }
+    Api& a = st.api;
+    const std::string shape = shape_source(P);
+    const std::string main_src = "#include \"" + entry_header + "\"\n";
+    std::vector<const char*> names(cf_jit_header_names, cf_jit_header_names + cf_jit_num_headers);
+    std::vector<const char*> srcs(cf_jit_header_srcs, cf_jit_header_srcs + cf_jit_num_headers);
+    names.push_back("cf_jit_shape.h");
+    srcs.push_back(shape.c_str());
+    nvrtcProgram prog = nullptr;
+    if (a.CreateProgram(&prog, main_src.c_str(), "cf_jit.cu", (int)names.size(), srcs.data(), names.data()) != NVRTC_SUCCESS) {
+        log = "nvrtcCreateProgram failed";
+        return 2;
+    }
+    a.AddNameExpression(prog, name_expr.c_str());
+    const char* opts[] = {"--gpu-architecture=sm_100a", "-std=c++17", "-lineinfo", "-DCF_JIT_SHAPE=1"};
+    const nvrtcResult rc = a.CompileProgram(prog, 4, opts);
+    size_t n = 0;
+    a.GetProgramLogSize(prog, &n);
+    log.assign(n, ' ');
+    if (n) a.GetProgramLog(prog, &log[0]);
+    size_t nb = 0;
+    if (rc == NVRTC_SUCCESS) a.GetCUBINSize(prog, &nb);
+    if (cubin_bytes) *cubin_bytes = nb;
+    a.DestroyProgram(&prog);
+    if (rc != NVRTC_SUCCESS) log += "\n--- generated cf_jit_shape.h ---\n" + shape;
+    return rc == NVRTC_SUCCESS && nb > 0 ? 0 : 2;
 }
 
 // Returns the specialised kernel for (shape of P, name_expr), compiling it on first use; nullptr if unavailable.

@@ -341,3 +341,18 @@ def jit_stats():
     c, h, f, t = C.c_int(), C.c_int(), C.c_int(), C.c_double()
     check(lib().cf_jit_stats(C.byref(c), C.byref(h), C.byref(f), C.byref(t)))
     return {"compiled": c.value, "cache_hits": h.value, "failures": f.value, "compile_seconds": t.value}
+
+
+JIT_KERNELS = {"mvm": 0, "mm_dmma": 1, "mvm_dmma": 2, "mm_tf32": 3, "mvm_tf32": 4}
+
+
+def jit_check(kernel, d: int, which: str = "mvm"):
+    """Compile (only) the run-time specialisation of one device kernel for `kernel`'s program -- works without a GPU (NVRTC
+    cross-compiles for sm_100a).  Returns the NVRTC log; raises if the generated code does not build."""
+    prog = kernel.program()
+    arr = (KNode * len(prog))()
+    for i, (op, ip, fp) in enumerate(prog):
+        arr[i].op, arr[i].iparam, arr[i].fparam = op, ip, fp
+    buf = C.create_string_buffer(1 << 16)
+    check(lib().cf_jit_check(arr, len(prog), int(d), JIT_KERNELS[which], buf, len(buf)))
+    return buf.value.decode(errors="replace")

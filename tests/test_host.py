@@ -167,3 +167,27 @@ def test_float32_gramian_eltype(cf):
     X = np.zeros((3, 5), dtype=np.float32)
     assert cf.gramian(cf.EQ(), X).eltype == np.float32  # promote(Union{}, Float32) (src/gramian.jl:30-33)
     assert cf.gramian(cf.EQ(), X.astype(np.float64)).eltype == np.float64
+
+
+def test_runtime_specialisations_compile_without_a_gpu():
+    """the generated evaluators (csrc/cf_jit.h) must build with NVRTC for sm_100a for every kernel family that can be
+    specialised, Float64 and Float32 -- checked here on the CPU, through the C ABI (cf_jit_check); the GPU tests then
+    check that they compute the right numbers"""
+    import covfn_b200 as cf
+    from covfn_b200._lib import UnsupportedKernel
+
+    programs = {
+        "config3": 0.5 * cf.RQ(2) + cf.Dot() ** 2,
+        "matern_times_rq_plus_const": cf.MaternP(3) * cf.RQ(1.5) + cf.Lengthscale(cf.EQ(), 0.7) + 0.25,
+        "poly_of_sum": (cf.EQ() + cf.Exp()) ** 2 + (cf.Dot() + 1.0) ** 3,
+    }
+    try:
+        cf.jit_check(cf.EQ(), 3, "mvm")
+    except UnsupportedKernel as e:  # no libnvrtc on this machine: nothing to check
+        pytest.skip(str(e))
+    for name, k in programs.items():
+        cf.jit_check(k, 3, "mvm")                 # K1, d = 3 (R = 4)
+        for which in ("mm_dmma", "mvm_dmma", "mm_tf32", "mvm_tf32"):
+            cf.jit_check(k, 16, which)
+    with pytest.raises(UnsupportedKernel):
+        cf.jit_check(cf.EQ(), 3, "mm_dmma")       # no tensor-core kernel below d = 8

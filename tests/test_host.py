@@ -191,3 +191,23 @@ def test_runtime_specialisations_compile_without_a_gpu():
             cf.jit_check(k, 16, which)
     with pytest.raises(UnsupportedKernel):
         cf.jit_check(cf.EQ(), 3, "mm_dmma")       # no tensor-core kernel below d = 8
+
+
+def test_program_limits_are_reported_not_truncated():
+    """the C++ lowering (csrc/cf_lower.h) runs on the host: programs beyond the by-value limits (8 terms, 6 atoms, 4 factors)
+    must come back as CF_ERR_UNSUPPORTED so that the Julia shim falls through to the reference method"""
+    import covfn_b200 as cf
+    from covfn_b200._lib import UnsupportedKernel
+
+    try:
+        cf.jit_check(cf.EQ(), 3, "mvm")
+    except UnsupportedKernel as e:
+        pytest.skip(str(e))
+    too_many_terms = (cf.EQ() + cf.RQ(1) + cf.MaternP(2) + cf.Lengthscale(cf.EQ(), 0.5)) ** 3  # 20 terms after expansion
+    with pytest.raises(UnsupportedKernel):
+        cf.jit_check(too_many_terms, 3, "mvm")
+    too_many_atoms = sum((cf.Lengthscale(cf.EQ(), 0.1 * (i + 1)) for i in range(1, 8)), cf.EQ())  # 8 distinct atoms
+    with pytest.raises(UnsupportedKernel):
+        cf.jit_check(too_many_atoms, 3, "mvm")
+    ok = cf.jit_check((cf.EQ() + cf.RQ(2)) ** 2 + 0.5, 3, "mvm")  # 4 terms, 2 atoms: fine
+    assert isinstance(ok, str)

@@ -945,7 +945,15 @@ int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, co
             P.coef = g->coef_grad;
             if (g->prog.single) P.atom = g->prog.atoms[g->prog.terms[0].fac[0].atom];
             PP.xn = (const double*)sh.xn; PP.yn = (const double*)sh.yn; PP.q = ap + q_off;
-            CF_CUDA(fn(PP, dim3(pl.row_tiles, pl.chunks), stream));
+            bool launched = false;
+            if (!g->prog.single && cfjit::wanted((double)nrows * (double)g->m * (double)D)) {
+                // composite derivative program: the same kernel with the jets' product rule generated for this structure (cf_jit.h)
+                const std::string name = "grad_mvm_dmma_kernel<" + std::to_string(D) + ", " + std::to_string((int)CF_ATOM_SOP) + ", " +
+                                         (vg ? "true" : "false") + ", " + std::to_string(dot ? CF_GRAD_DOT : CF_GRAD_ISO) + ">";
+                if (cfjit::Kernel* jit = cfjit::get_kernel(g->sop_val, "grad_mvm_dmma.cuh", name, &g->sop_grad))
+                    launched = cfjit::launch(jit, &PP, (unsigned)pl.row_tiles, (unsigned)pl.chunks, 256, (unsigned)cfgd.smem_bytes, stream) == 0;
+            }
+            if (!launched) CF_CUDA(fn(PP, dim3(pl.row_tiles, pl.chunks), stream));
             const int blocks = (int)std::min<int64_t>((nrows * bs + 255) / 256, 8192);
             grad_reduce_partials<<<blocks, 256, 0, stream>>>((const double*)sh.partial.p, P.partial0, pl.chunks, nrows, D, d, vg, d_y, d_yin,
                                                              alpha, beta, *peers);
@@ -1503,12 +1511,19 @@ int cf_jit_check(const cf_knode_t* prog, int nnodes, int d, int which, char* log
         case 2: header = "gram_mvm_dmma.cuh"; name = "gram_mvm_dmma_kernel<" + sD + ", " + sop + ">"; break;
         case 3: header = "gram_mm_tf32.cuh"; name = "gram_mm_tf32_kernel<" + sD + ">"; break;
         case 4: header = "gram_mvm_tf32.cuh"; name = "gram_mvm_tf32_kernel<" + sD + ", " + sop + ">"; break;
-        default: return fail(CF_ERR_BAD_ARGUMENT, "cf_jit_check: which must be 0..4");
+        case 5: header = "grad_mvm_dmma.cuh"; name = "grad_mvm_dmma_kernel<" + sD + ", " + sop + ", false, 0>"; break;
+        default: return fail(CF_ERR_BAD_ARGUMENT, "cf_jit_check: which must be 0..5");
+    }
+    cf_sop_grad sop_grad;
+    const bool want_grad = which == 5;
+    if (want_grad) {
+        if (!cf::to_sop_grad(lowered, sop_grad) || !lowered.isotropic)
+            return fail(CF_ERR_UNSUPPORTED, "cf_jit_check: the program has no isotropic derivative form within the device limits");
     }
     if (which >= 1 && (D < 8 || (which <= 2 && D % 4 != 0))) return fail(CF_ERR_UNSUPPORTED, "cf_jit_check: no tensor-core kernel for D = %d", D);
     std::string text;
     size_t nb = 0;
-    const int rc = cfjit::compile_only(sop_val, header, name, text, &nb);
+    const int rc = cfjit::compile_only(sop_val, header, name, text, &nb, want_grad ? &sop_grad : nullptr);
     if (log && loglen > 0) {
         std::snprintf(log, (size_t)loglen, "%s", text.c_str());
     }

@@ -171,9 +171,54 @@ inline std::string shape_source_part(const cf_sop_val& P, bool f32) {
     s += "        val[u] = v;\n    }\n}\n";
     return s;
 }
-inline std::string shape_source(const cf_sop_val& P) {
-    return "// generated by cf_jit.h for program structure " + shape_key(P) + "\n#if CF_JIT_PART == 1\n" + shape_source_part(P, false) +
-           "#elif CF_JIT_PART == 2\n" + shape_source_part(P, true) + "#endif\n";
+// structure of a derivative program (same encoding as shape_key)
+inline std::string shape_key_grad(const cf_sop_grad& P) {
+    std::string k = "G";
+    for (int i = 0; i < P.natoms; i++) {
+        const int kind = P.atoms[i].v.kind;
+        const int ps = (kind == CF_ATOM_MATERN || kind == CF_ATOM_RQ_INT) ? P.atoms[i].v.p : 0;
+        k += std::to_string(kind) + "." + std::to_string(ps) + ",";
+    }
+    k += "T";
+    for (int t = 0; t < P.nterms; t++) {
+        for (int f = 0; f < P.terms[t].nfac; f++) k += std::to_string(P.terms[t].atom[f]) + "^" + std::to_string(P.terms[t].power[f]) + "*";
+        k += "+";
+    }
+    return k;
+}
+// part 3: jets (k, k', k'') of the derivative program by the product rule, atoms first; G == nullptr: declaration only
+inline std::string shape_source_jets(const cf_sop_grad* G) {
+    const std::string sig = "template <int N>\n__device__ __forceinline__ void cf_sop_jet_n(const double (&r2)[N], const cf_sop_grad& P, "
+                            "cf_tbl_t tbl_lane, double (&k)[N], double (&k1)[N], double (&k2)[N])";
+    if (!G) return sig + ";\n";
+    std::string s = sig + " {\n";
+    for (int i = 0; i < G->natoms; i++) {
+        const int kind = G->atoms[i].v.kind;
+        const int ps = (kind == CF_ATOM_MATERN || kind == CF_ATOM_RQ_INT) ? G->atoms[i].v.p : 0;
+        const std::string id = std::to_string(i);
+        s += "    double v" + id + "[N], d" + id + "[N], e" + id + "[N];\n";
+        s += "    cf_atom_jet_s<N, " + std::string(kind_name(kind)) + ", " + std::to_string(ps) + ">(r2, P.atoms[" + id + "], tbl_lane, v" + id +
+             ", d" + id + ", e" + id + ");\n";
+    }
+    s += "#pragma unroll\n    for (int u = 0; u < N; u++) {\n        double sv = 0.0, s1 = 0.0, s2 = 0.0, pv, p1, p2, nv, n1, n2;\n";
+    for (int t = 0; t < G->nterms; t++) {
+        const cf_sop_term& T = G->terms[t];
+        s += "        pv = P.terms[" + std::to_string(t) + "].coef; p1 = 0.0; p2 = 0.0;\n";
+        for (int f = 0; f < T.nfac; f++)
+            for (int q = 0; q < T.power[f]; q++) {
+                const std::string a = std::to_string(T.atom[f]);
+                s += "        nv = pv * v" + a + "[u]; n1 = fma(p1, v" + a + "[u], pv * d" + a + "[u]); n2 = fma(p2, v" + a + "[u], fma(2.0 * p1, d" + a +
+                     "[u], pv * e" + a + "[u])); pv = nv; p1 = n1; p2 = n2;\n";
+            }
+        s += "        sv += pv; s1 += p1; s2 += p2;\n";
+    }
+    s += "        k[u] = sv; k1[u] = s1; k2[u] = s2;\n    }\n}\n";
+    return s;
+}
+inline std::string shape_source(const cf_sop_val& P, const cf_sop_grad* G = nullptr) {
+    return "// generated by cf_jit.h for program structure " + shape_key(P) + (G ? " " + shape_key_grad(*G) : std::string()) +
+           "\n#if CF_JIT_PART == 1\n" + shape_source_part(P, false) + "#elif CF_JIT_PART == 2\n" + shape_source_part(P, true) +
+           "#elif CF_JIT_PART == 3\n" + shape_source_jets(G) + "#endif\n";
 }
 
 // ---- on-disk cache of compiled cubins: $COVFN_JIT_CACHE or ~/.cache/covfn_b200 (COVFN_JIT_CACHE=off disables) ------------------
@@ -233,12 +278,12 @@ inline void cache_write(const std::string& path, const std::vector<char>& cubin,
 // Compile (only) the specialisation of `name_expr` from `entry_header` for the structure of P; returns 0 on success, 1 if NVRTC is
 // unavailable, 2 on a compilation error.  `log` receives the NVRTC log or the reason.
 inline int compile_only(const cf_sop_val& P, const std::string& entry_header, const std::string& name_expr, std::string& log,
-                        size_t* cubin_bytes) {
+                        size_t* cubin_bytes, const cf_sop_grad* G = nullptr) {
     State& st = state();
     std::lock_guard<std::mutex> lk(st.mu);
     if (!load_nvrtc(st.api)) { log = st.api.why; return 1; }
     Api& a = st.api;
-    const std::string shape = shape_source(P);
+    const std::string shape = shape_source(P, G);
     const std::string main_src = "#include \"" + entry_header + "\"\n";
     std::vector<const char*> names(cf_jit_header_names, cf_jit_header_names + cf_jit_num_headers);
     std::vector<const char*> srcs(cf_jit_header_srcs, cf_jit_header_srcs + cf_jit_num_headers);
@@ -265,10 +310,11 @@ inline int compile_only(const cf_sop_val& P, const std::string& entry_header, co
 }
 
 // Returns the specialised kernel for (shape of P, name_expr), compiling it on first use; nullptr if unavailable.
-inline Kernel* get_kernel(const cf_sop_val& P, const std::string& entry_header, const std::string& name_expr) {
+inline Kernel* get_kernel(const cf_sop_val& P, const std::string& entry_header, const std::string& name_expr,
+                          const cf_sop_grad* G = nullptr) {
     State& st = state();
     std::lock_guard<std::mutex> lk(st.mu);
-    const std::string key = name_expr + "|" + shape_key(P);
+    const std::string key = name_expr + "|" + shape_key(P) + (G ? "|" + shape_key_grad(*G) : std::string());
     auto it = st.cache.find(key);
     if (it != st.cache.end()) {
         if (it->second) st.stats.hits++;
@@ -298,7 +344,7 @@ inline Kernel* get_kernel(const cf_sop_val& P, const std::string& entry_header, 
             return slot;
         }
     }
-    const std::string shape = shape_source(P);
+    const std::string shape = shape_source(P, G);
     const std::string main_src = "#include \"" + entry_header + "\"\n";
     std::vector<const char*> names(cf_jit_header_names, cf_jit_header_names + cf_jit_num_headers);
     std::vector<const char*> srcs(cf_jit_header_srcs, cf_jit_header_srcs + cf_jit_num_headers);

@@ -523,6 +523,41 @@ __device__ __forceinline__ void cf_sop_jet(double r2, const cf_sop_grad& P, cf_t
     k = sv; k1 = s1; k2 = s2;
 }
 
+// jets of N pairs of one atom whose kind (and integer parameter) is a compile-time constant (run-time specialised builds)
+template <int N, int KIND, int PS>
+__device__ __forceinline__ void cf_atom_jet_s(const double (&r2)[N], const cf_atom& A, cf_tbl_t tbl_lane, double (&k)[N],
+                                              double (&k1)[N], double (&k2)[N]) {
+    if constexpr (KIND == CF_ATOM_EQ) {
+#pragma unroll
+        for (int u = 0; u < N; u++) {
+            k[u] = cf_exp_cv(r2[u], A.v.e, tbl_lane);
+            k1[u] = A.v.e.c * k[u];
+            k2[u] = A.v.e.c * k1[u];
+        }
+    } else if constexpr (KIND == CF_ATOM_MATERN && PS >= 2) {
+        cf_matern_jet_n<N>(r2, A, tbl_lane, k, k1, k2);
+    } else if constexpr (KIND == CF_ATOM_RQ_INT) {
+        const double c1 = -A.v.alpha * A.v.w, c2 = -(A.v.alpha + 1.0) * A.v.w;
+#pragma unroll
+        for (int u = 0; u < N; u++) {
+            const double ib = cf_rcp(fma(r2[u], A.v.w, 1.0));
+            double kk = ib;
+#pragma unroll
+            for (int i = 1; i < PS; i++) kk *= ib;
+            k[u] = kk;
+            k1[u] = c1 * kk * ib;
+            k2[u] = c2 * k1[u] * ib;
+        }
+    } else {
+        cf_atom_jet_n<N>(r2, A, tbl_lane, k, k1, k2);  // real-power RQ, MaternP(p < 2), LINE: the generic N-wide form
+    }
+}
+
+#ifdef CF_JIT_SHAPE
+#define CF_JIT_PART 3  // the jets of the derivative program (or only a declaration when the specialised kernel has none)
+#include "cf_jit_shape.h"
+#undef CF_JIT_PART
+#else
 // the same for N pairs at a time: the program is decoded once per N values
 template <int N>
 __device__ __forceinline__ void cf_sop_jet_n(const double (&r2)[N], const cf_sop_grad& P, cf_tbl_t tbl_lane, double (&k)[N],
@@ -552,6 +587,7 @@ __device__ __forceinline__ void cf_sop_jet_n(const double (&r2)[N], const cf_sop
         for (int u = 0; u < N; u++) { k[u] += pv[u]; k1[u] += p1[u]; k2[u] += p2[u]; }
     }
 }
+#endif // CF_JIT_SHAPE (jets)
 
 // ---- FP32 ------------------------------------------------------------------------------------------
 __device__ __forceinline__ float cf_ex2f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }

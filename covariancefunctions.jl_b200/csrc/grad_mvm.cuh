@@ -204,6 +204,7 @@ __global__ void cf_pad_points(const T* __restrict__ src, int64_t lds, int d, T* 
     }
 }
 
+#ifndef __CUDACC_RTC__ // host side: not part of run-time specialised builds
 typedef cudaError_t (*cf_grad_launch_fn)(const cf_grad_params& P, dim3 grid, cudaStream_t stream);
 
 template <int D, int KIND, int MODE, bool VG, int R, int NT, int TJ, int NS, int MINB>
@@ -221,3 +222,4 @@ cudaError_t cf_grad_launch(const cf_grad_params& P, dim3 grid, cudaStream_t stre
     kern<<<grid, NT, S::total, stream>>>(P);
     return cudaGetLastError();
 }
+#endif // !__CUDACC_RTC__

@@ -148,3 +148,40 @@ def test_dot_product_programs_on_tensor_cores(cf, O, d):
             assert relerr(b, bsc) < 1e-13, (d, name, vg)
             if name == "dot2" and not vg:
                 assert not np.array_equal(b, bsc), "expected the tensor-core kernel"
+
+
+def test_runtime_specialised_jets(cf, O):
+    """COVFN_JIT=1: composite derivative programs get their product-rule jets generated (csrc/cf_jit.h part 3) and compiled
+    into the tensor-core gradient kernel; specialised == interpreted == oracle, GradientKernel and ValueGradientKernel"""
+    rng = np.random.default_rng(801)
+    n, m, d = 210, 330, 16
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    Y = rng.standard_normal((m, d)) / np.sqrt(d)
+    programs = {
+        "eq_plus_rq": cf.EQ() + 0.5 * cf.RQ(2),
+        "eq_times_matern3": 0.7 * cf.EQ() * cf.MaternP(3),
+        "square_of_sum": (cf.Lengthscale(cf.EQ(), 1.4) + cf.RQ(1)) ** 2,
+        "rq_real_plus_matern": cf.RQ(1.7) + cf.MaternP(2),
+    }
+    before = cf.jit_stats()
+    for name, k in programs.items():
+        for vg in (False, True):
+            K = cf.ValueGradientKernel(k) if vg else cf.GradientKernel(k)
+            bs = d + (1 if vg else 0)
+            a = rng.standard_normal(m * bs)
+            G = cf.gramian(K, X.T.copy(), Y.T.copy())
+            os.environ["COVFN_JIT"] = "1"
+            try:
+                bj = G @ a
+            finally:
+                os.environ["COVFN_JIT"] = "0"
+            try:
+                bi = G @ a
+            finally:
+                del os.environ["COVFN_JIT"]
+            ref = O.derivative_mul(k.program(), X, a, Y=Y, trait="isotropic", value_gradient=vg)
+            assert relerr(bj, ref) < TOL64, (name, vg)
+            assert relerr(bj, bi) < 1e-13, (name, vg)
+    after = cf.jit_stats()
+    assert after["failures"] == before["failures"]
+    assert after["compiled"] - before["compiled"] >= len(programs)

@@ -191,6 +191,9 @@ def test_runtime_specialisations_compile_without_a_gpu():
             cf.jit_check(k, 16, which)
     with pytest.raises(UnsupportedKernel):
         cf.jit_check(cf.EQ(), 3, "mm_dmma")       # no tensor-core kernel below d = 8
+    # derivative programs: generated jets (product rule) for the tensor-core gradient kernel
+    cf.jit_check(cf.EQ() + 0.5 * cf.RQ(2) * cf.MaternP(3), 16, "grad_dmma")
+    cf.jit_check(cf.Lengthscale(cf.MaternP(2), 0.7) ** 2 + cf.RQ(1.5), 8, "grad_dmma")
 
 
 def test_program_limits_are_reported_not_truncated():

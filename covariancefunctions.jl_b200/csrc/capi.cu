@@ -83,7 +83,14 @@ int get_ctx(int dev, DeviceCtx** out) {
         CF_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     }
     double tbl[CF_EXP_TBL];
-    for (int j = 0; j < CF_EXP_TBL; j++) tbl[j] = (double)exp2l((long double)j / CF_EXP_TBL);
+    for (int j = 0; j < CF_EXP_TBL; j++) {
+        // 2^(j/256) correctly rounded, with (j << 12) subtracted from its high word: cf_exp_cv adds kk << 12 = (k << 20) + (j << 12)
+        // to the high word, which then holds the exponent of 2^k 2^(j/256) (one integer instruction instead of mask + add)
+        union { double d; uint64_t u; } v;
+        v.d = (double)exp2l((long double)j / CF_EXP_TBL);
+        v.u -= (uint64_t)j << (32 + 20 - CF_EXP_TBL_BITS);
+        tbl[j] = v.d;
+    }
     CF_CUDA(cudaMalloc(&c.exp2_tbl, sizeof(tbl)));
     CF_CUDA(cudaMemcpy(c.exp2_tbl, tbl, sizeof(tbl), cudaMemcpyHostToDevice));
     g_ctx.reserve(64);
@@ -138,6 +145,7 @@ struct cf_gramian_s {
     bool symmetric = false;
     bool use_norms = false; // multi-RHS kernel may use r2 = |x|^2 + |y|^2 - 2 x.y (well-scaled data, d >= 8)
     bool use_norms_grad = false; // ... and so may the isotropic gradient operator (stricter: needs k'')
+    bool eq_fast = false;   // single EQ atom, any d: norm expansion error < 1e-13 and |c| (|x| + |y|)^2 < 600 (gram_mvm_eq.cuh)
     int64_t row_begin = 0, row_end = 0;
     cf_program prog;
     cf_sop_val sop_val;    // parameter-resident program for the value kernels
@@ -843,10 +851,12 @@ int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const v
     // the Float32 counterpart: distance GEMM in 3xTF32 (gram_mvm_tf32.cuh)
     if (dt == CF_F32 && g->use_norms && g->entry->mvm_tf32[slot] != nullptr && !env_flag("COVFN_MVM_SCALAR"))
         return launch_mvm_tf32(g, sh, d_y, d_yin, d_a, alpha, beta, stream, peers);
-    Plan pl = make_plan(nrows, g->m, cfg, sh.ctx->sms);
+    // single EQ atom on well-scaled Float64 points, small d: exponent formed in the scaled domain (gram_mvm_eq.cuh)
+    const bool eqf = g->eq_fast && g->entry->mvm_eq != nullptr && !env_flag("COVFN_MVM_SCALAR");
+    Plan pl = make_plan(nrows, g->m, eqf ? g->entry->mvm_eq_cfg : cfg, sh.ctx->sms);
     cf_mvm_params P;
     std::memset(&P, 0, sizeof(P));
-    P.X = sh.X; P.Y = sh.Y; P.a = d_a;
+    P.X = sh.X; P.Y = sh.Y; P.a = d_a; P.xn = sh.xn; P.yn = sh.yn;
     P.exp2_tbl = sh.ctx->exp2_tbl;
     P.sop = g->sop_val;
     P.row0 = sh.r0; P.nrows = nrows; P.m = g->m;
@@ -854,6 +864,11 @@ int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const v
     P.alpha = alpha * g->coef; P.beta = beta;
     P.use_tma = (((uintptr_t)d_a) % 16 == 0) ? 1 : 0;
     if (g->prog.single) P.atom = g->prog.atoms[g->prog.terms[0].fac[0].atom].v;
+    if (eqf) {
+        const long double lam = 0.693147180559945309417232121458176568L / 256.0L;
+        P.eqc[0] = (double)lam; P.eqc[1] = (double)(lam * lam / 2); P.eqc[2] = (double)(lam * lam * lam / 6);
+        P.eqc[3] = (double)(lam * lam * lam * lam / 24);
+    }
     P.direct = (pl.chunks == 1) ? 1 : 0;
     P.peers = *peers;
     if (P.direct) {
@@ -874,7 +889,7 @@ int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const v
             launched = cfjit::launch(jit, &P, (unsigned)pl.row_tiles, (unsigned)pl.chunks, (unsigned)tu[1], (unsigned)cfg.smem_bytes, stream) == 0;
     }
     if (!launched) {
-        cf_mvm_launch_fn fn = g->entry->mvm[dt][cf_kind_slot(g->kind)];
+        cf_mvm_launch_fn fn = eqf ? g->entry->mvm_eq : g->entry->mvm[dt][cf_kind_slot(g->kind)];
         CF_CUDA(fn(P, dim3(pl.row_tiles, pl.chunks), stream));
     }
     g->last_launches++;
@@ -1215,6 +1230,10 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
         for (int i = 0; i < g->prog.natoms; i++)
             if (g->prog.atoms[i].v.kind == CF_ATOM_MATERN && g->prog.atoms[i].v.p < 2) smooth2 = false;
         g->use_norms_grad = g->use_norms && smooth2 && (growth * eps * 2.0 * max_sq * slope * slope < bound);
+        // the scaled-domain EQ kernel (gram_mvm_eq.cuh) has no clamp: besides the cancellation bound, the exponent of the
+        // farthest pair, |c| (|x| + |y|)^2 <= 4 |c| max|x|^2, must stay clear of the 2^-1022 underflow (ln 2^-1022 = -708)
+        g->eq_fast = dtype == CF_F64 && g->kind == CF_ATOM_EQ && (growth * eps * 2.0 * max_sq * slope < bound) &&
+                     (4.0 * max_sq * slope < 600.0);
     }
     (void)es;
     split_rows(g);

@@ -40,10 +40,10 @@ __device__ __forceinline__ void cf_fill_exp_table(double* tbl, const double* __r
 
 // exp(c*v), v >= 0 (c < 0 folded into the constants).  tbl_lane = table + (lane & 15).
 // The SM issues one instruction per cycle per sub-partition and an FP64 instruction holds the dispatch port for two
-// (measured: cycles = 2 * #FP64 + #other, profiles/), so the non-FP64 work is kept to 6 instructions per call:
+// (measured: cycles = 2 * #FP64 + #other, profiles/), so the non-FP64 work is kept to 5 instructions per call:
 // the clamp of v is ONE integer min on the high word (v >= 0, so integer order of high words == floating-point
 // order; the clamped value lies within 2^-20 relative of E.vmax, where the result is ~1e-304, i.e. 0), the table
-// address is AND + multiply-add, the 2^k scaling is AND + multiply-add on the high word.
+// address is AND + multiply-add, the 2^k scaling is one multiply-add on the high word of the (pre-compensated) table entry.
 __device__ __forceinline__ double cf_exp_cv(double v, const cf_exp_consts& E, cf_tbl_t tbl_lane) {
     v = __hiloint2double(min(__double2hiint(v), E.vmax_hi), __double2loint(v));
     double t = fma(v, E.c1, CF_MAGIC);
@@ -64,11 +64,13 @@ __device__ __forceinline__ double cf_exp_cv(double v, const cf_exp_consts& E, cf
     double tj;
     asm("mad.lo.s32 %0, %1, 128, %2;" : "=r"(off) : "r"(kk & (CF_EXP_TBL - 1)), "r"((int)tbl_lane));
     asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(off)); // table is written once, before the first barrier
-    double tu = tj * u;
-    double e = fma(tu, p, tj); // tj * (1 + u p)
+    // 2^k scaling in ONE integer instruction: the table stores 2^(j/256) with (j << 12) already subtracted from its high word, so that
+    // adding kk << 12 = (k << 20) + (j << 12) leaves exactly k in the exponent field (capi.cu get_ctx builds the table)
     int hi;
-    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(hi) : "r"(kk & ~(CF_EXP_TBL - 1)), "r"(0x100000 >> CF_EXP_TBL_BITS), "r"(__double2hiint(e)));
-    return __hiloint2double(hi, __double2loint(e));
+    asm("mad.lo.s32 %0, %1, %2, %3;" : "=r"(hi) : "r"(kk), "r"(0x100000 >> CF_EXP_TBL_BITS), "r"(__double2hiint(tj)));
+    const double s = __hiloint2double(hi, __double2loint(tj)); // 2^k 2^(j/256)
+    const double su = s * u;
+    return fma(su, p, s); // s * (1 + u p)
 }
 
 // sqrt(v) for v >= 0; v below 2^-1007 (incl. 0 and subnormals) returns ~2^-504 (i.e. 0 for our purposes).

@@ -47,6 +47,7 @@ struct cf_mvm_params {
     cf_peer_out peers;    // direct mode: also store the finished rows into these peer vectors
     const void* xn;       // squared norms of the rows / columns (tensor-core variant gram_mvm_dmma.cuh only; X, Y then point at
     const void* yn;       // the point copies with the padded row stride)
+    double eqc[4];        // gram_mvm_eq.cuh: polynomial constants of exp(f ln2 / 32768) (constant-bank operands)
 };
 
 // ---- mbarrier / TMA 1-D bulk copy wrappers (PTX ISA: cp.async.bulk, mbarrier) ------------------------------

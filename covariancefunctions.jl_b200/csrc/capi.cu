@@ -1025,7 +1025,7 @@ int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, co
 // upload one point set: raw d x n (leading dimension ld) -> padded AoS on the device, squared norms, finiteness check.
 // No host-side packing: one 2-D copy, one pad kernel (only when D != d) and one validation/norm kernel.
 int upload_points(int dtype, const void* H, int64_t ld, int64_t n, int d, int D, void** dX, void** dN, Buf& scratch,
-                  double* flags_dev, cudaStream_t st) {
+                  double* flags_dev, cudaStream_t st, const double* ard_scale_dev = nullptr) {
     const size_t es = esize(dtype);
     CF_CUDA(dev_alloc(dX, std::max<size_t>(16, (size_t)n * D * es)));
     CF_CUDA(dev_alloc(dN, std::max<size_t>(16, (size_t)n * es)));
@@ -1044,6 +1044,12 @@ int upload_points(int dtype, const void* H, int64_t ld, int64_t n, int d, int D,
         const int blocks = (int)std::min<int64_t>((n * D + 255) / 256, 8192);
         if (dtype == CF_F64) cf_pad_points<double><<<blocks, 256, 0, st>>>((const double*)scratch.p, d, d, (double*)*dX, D, n);
         else cf_pad_points<float><<<blocks, 256, 0, st>>>((const float*)scratch.p, d, d, (float*)*dX, D, n);
+        CF_CUDA(cudaGetLastError());
+    }
+    if (ard_scale_dev) {  // ARD: the metric is applied to the device copy of the points (1/sqrt(l_c) per coordinate)
+        const int sb = (int)std::min<int64_t>((n * D + 255) / 256, 8192);
+        if (dtype == CF_F64) cf_scale_coords_kernel<double><<<sb, 256, 0, st>>>((double*)*dX, D, d, n, ard_scale_dev);
+        else cf_scale_coords_kernel<float><<<sb, 256, 0, st>>>((float*)*dX, D, d, n, ard_scale_dev);
         CF_CUDA(cudaGetLastError());
     }
     const int nb = (int)std::min<int64_t>((n + 255) / 256, 4096);
@@ -1113,8 +1119,9 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
     cf_sop_val sop_val;
     cf_sop_grad sop_grad;
     bool grad_ok = false;
+    std::vector<double> ard;  // ARD length scales l_c (empty: none)
     try {
-        lowered = cf::lower(prog, nnodes);
+        lowered = cf::lower(prog, nnodes, &ard);
         cf::to_sop_val(lowered, sop_val);
         grad_ok = cf::to_sop_grad(lowered, sop_grad);
     } catch (const cf::LowerError& e) {
@@ -1122,6 +1129,9 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
     } catch (...) {
         return fail(CF_ERR_INTERNAL, "cf_gramian_create: unexpected failure while lowering the kernel program");
     }
+    if (!ard.empty() && (int)ard.size() != d)
+        return fail(CF_ERR_DIMENSION, "cf_gramian_create: ARD has %d length scales, the points have dimension %d", (int)ard.size(), d);
+    for (double& l : ard) l = 1.0 / std::sqrt(l);  // coordinate scale
     const cf_kernel_entry* entry = find_entry(d);  // nullptr for d > 32: tiled contraction kernels (bigd.cuh), Float64 only
     if (!entry && dtype != CF_F64) return fail(CF_ERR_UNSUPPORTED, "cf_gramian_create: d = %d > 32 is supported in Float64 only", d);
     if (d > (1 << 20)) return fail(CF_ERR_UNSUPPORTED, "cf_gramian_create: d = %d is too large", d);
@@ -1183,15 +1193,21 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
             double* flags = nullptr;
             CF_CREATE_CUDA(dev_alloc((void**)&flags, 16));
             CF_CREATE_CUDA(cudaMemsetAsync(flags, 0, 16, sh.stream));
-            rc = upload_points(dtype, X, ldx, n, d, g->D, &sh.X, &sh.xn, sh.apad, flags, sh.stream);
+            double* ard_dev = nullptr;
+            if (!ard.empty()) {
+                CF_CREATE_CUDA(dev_alloc((void**)&ard_dev, ard.size() * sizeof(double)));
+                CF_CREATE_CUDA(cudaMemcpyAsync(ard_dev, ard.data(), ard.size() * sizeof(double), cudaMemcpyHostToDevice, sh.stream));
+            }
+            rc = upload_points(dtype, X, ldx, n, d, g->D, &sh.X, &sh.xn, sh.apad, flags, sh.stream, ard_dev);
             if (!rc) {
-                if (Y) rc = upload_points(dtype, Y, ldy, m, d, g->D, &sh.Y, &sh.yn, sh.apad, flags, sh.stream);
+                if (Y) rc = upload_points(dtype, Y, ldy, m, d, g->D, &sh.Y, &sh.yn, sh.apad, flags, sh.stream, ard_dev);
                 else { sh.Y = sh.X; sh.yn = sh.xn; }
             }
             unsigned long long hflags[2] = {0, 0};
             if (!rc && cudaMemcpyAsync(hflags, flags, 16, cudaMemcpyDeviceToHost, sh.stream) != cudaSuccess) rc = fail(CF_ERR_CUDA, "flag copy failed");
             if (!rc && cudaStreamSynchronize(sh.stream) != cudaSuccess) rc = fail(CF_ERR_CUDA, "upload failed: %s", cudaGetErrorString(cudaGetLastError()));
             dev_free(flags);
+            dev_free(ard_dev);
             if (!rc && hflags[0] != 0) rc = fail(CF_ERR_NONFINITE, "%llu point coordinates are not finite (NaN or Inf)", hflags[0]);
             if (rc) { destroy_impl(g); return rc; }
             double ms;
@@ -1507,7 +1523,8 @@ int cf_jit_check(const cf_knode_t* prog, int nnodes, int d, int which, char* log
     cf_program lowered;
     cf_sop_val sop_val;
     try {
-        lowered = cf::lower(prog, nnodes);
+        std::vector<double> ard;
+        lowered = cf::lower(prog, nnodes, &ard);
         cf::to_sop_val(lowered, sop_val);
     } catch (const cf::LowerError& e) {
         return fail(e.code, "cf_jit_check: %s", e.msg.c_str());

@@ -109,6 +109,16 @@ __global__ void cf_transpose_rhs(const T* __restrict__ A, int64_t lda, int64_t m
 
 // squared norms of padded points + validation: flags[0] += number of non-finite coordinates,
 // flags[1] = max squared norm (bit pattern of a non-negative double: integer order == floating-point order)
+// ARD metric (reference src/transformation.jl:42-45): coordinate c of every point times scale[c] = 1/sqrt(l_c), in place,
+// on the padded device copy (padding columns stay 0)
+template <typename T>
+__global__ void cf_scale_coords_kernel(T* __restrict__ X, int D, int d, int64_t n, const double* __restrict__ scale) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n * D; q += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(q % D);
+        if (c < d) X[q] = (T)((double)X[q] * scale[c]);
+    }
+}
+
 template <typename T>
 __global__ void cf_sqnorm_validate_kernel(const T* __restrict__ X, int D, int64_t n, T* __restrict__ out, double* flags) {
     unsigned long long bad = 0;

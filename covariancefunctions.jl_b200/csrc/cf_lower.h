@@ -39,6 +39,7 @@ struct HExpr {
     double cval = 0;
     bool is_iso_leaf = false;    // isotropic leaf (possibly under Lengthscale): atom index below
     int atom = -1;
+    bool is_ardscale = false;    // an ARDSCALE entry waiting for its ARD node (cval = l_c)
 };
 
 inline long double lfact(int n) { long double f = 1; for (int i = 2; i <= n; i++) f *= i; return f; }
@@ -138,12 +139,16 @@ inline cf_atom zero_atom() {
 
 }  // namespace detail
 
-// Lower a postfix program.  Throws LowerError.
-inline cf_program lower(const cf_knode_t* prog, int nnodes) {
+// Lower a postfix program.  Throws LowerError.  ard (may be NULL -> ARD programs are rejected) receives the per-dimension
+// length scales l_c of the program's ARD node, empty if there is none; the caller applies them to the points (1/sqrt(l_c)).
+inline cf_program lower(const cf_knode_t* prog, int nnodes, std::vector<double>* ard = nullptr) {
     using namespace detail;
     if (!prog || nnodes <= 0) throw LowerError{CF_ERR_BAD_ARGUMENT, "empty kernel program"};
     std::vector<cf_atom> atoms;
     std::vector<HExpr> st;
+    std::vector<double> ard_l;       // the one ARD metric of the program
+    std::vector<char> atom_in_ard;   // per atom: sits under the ARD node
+    if (ard) ard->clear();
     auto add_atom = [&](const cf_atom& A) {
         if ((int)atoms.size() >= CF_MAX_TERMS) throw LowerError{CF_ERR_UNSUPPORTED, "too many distinct base kernels"};
         atoms.push_back(A);
@@ -223,6 +228,8 @@ inline cf_program lower(const cf_knode_t* prog, int nnodes) {
                 if (k < 1 || k > (int)st.size()) throw LowerError{CF_ERR_BAD_ARGUMENT, "malformed program: Sum/Product arity"};
                 std::vector<HExpr> args(st.end() - k, st.end());
                 st.resize(st.size() - k);
+                for (auto& a : args)
+                    if (a.is_ardscale) throw LowerError{CF_ERR_BAD_ARGUMENT, "malformed program: ARDSCALE outside ARD"};
                 HExpr out;
                 if (nd.op == CF_OP_SUM) {
                     // Line: Dot() + sigma  (mercer.jl:12) -> one atom
@@ -259,12 +266,49 @@ inline cf_program lower(const cf_knode_t* prog, int nnodes) {
                 st.push_back(out);
                 break;
             }
+            case CF_OP_ARDSCALE: {
+                if (!(nd.fparam > 0) || !std::isfinite(nd.fparam)) throw LowerError{CF_ERR_DOMAIN, "ARD: length scale is non-positive"};
+                HExpr e;
+                e.is_ardscale = true;
+                e.cval = nd.fparam;
+                st.push_back(e);
+                break;
+            }
+            case CF_OP_ARD: {
+                const int k = nd.iparam;
+                if (k < 1 || k + 1 > (int)st.size()) throw LowerError{CF_ERR_BAD_ARGUMENT, "malformed program: ARD arity"};
+                std::vector<double> l(k);
+                for (int q = 0; q < k; q++) {
+                    const HExpr& e = st[st.size() - k + q];
+                    if (!e.is_ardscale) throw LowerError{CF_ERR_BAD_ARGUMENT, "malformed program: ARD expects ARDSCALE entries"};
+                    l[q] = e.cval;
+                }
+                st.resize(st.size() - k);
+                HExpr child = st.back();
+                st.pop_back();
+                if (child.is_ardscale) throw LowerError{CF_ERR_BAD_ARGUMENT, "malformed program: ARD without a kernel"};
+                if (!ard) throw LowerError{CF_ERR_UNSUPPORTED, "ARD kernels are not supported by this entry point"};
+                if (!ard_l.empty() && ard_l != l)
+                    throw LowerError{CF_ERR_UNSUPPORTED, "two ARD kernels with different length scales in one program"};
+                ard_l = l;
+                atom_in_ard.resize(atoms.size(), 0);
+                for (auto& tt : child.terms)
+                    for (auto& f : tt.fac) {
+                        if (atoms[f.atom].v.kind == CF_ATOM_LINE)   // Normed calls k(n2(tau)): k must be a function of r2
+                            throw LowerError{CF_ERR_UNSUPPORTED, "ARD must wrap an isotropic kernel"};
+                        atom_in_ard[f.atom] = 1;
+                    }
+                child.is_plain_dot = child.is_const = child.is_iso_leaf = false;
+                st.push_back(child);
+                break;
+            }
             case CF_OP_POW: {
                 if (st.empty()) throw LowerError{CF_ERR_BAD_ARGUMENT, "malformed program: Power without operand"};
                 const int p = nd.iparam;
                 if (p < 0) throw LowerError{CF_ERR_UNSUPPORTED, "negative kernel powers are not supported"};
                 HExpr base = st.back();
                 st.pop_back();
+                if (base.is_ardscale) throw LowerError{CF_ERR_BAD_ARGUMENT, "malformed program: ARDSCALE outside ARD"};
                 HExpr out;
                 if (p == 0) {
                     out.terms.push_back(HTerm{1.0, {}});
@@ -302,6 +346,7 @@ inline cf_program lower(const cf_knode_t* prog, int nnodes) {
     }
     if (st.size() != 1) throw LowerError{CF_ERR_BAD_ARGUMENT, "malformed program: stack does not reduce to one kernel"};
     const HExpr& root = st[0];
+    if (root.is_ardscale) throw LowerError{CF_ERR_BAD_ARGUMENT, "malformed program: ARDSCALE outside ARD"};
     cf_program P;
     std::memset(&P, 0, sizeof(P));
     if ((int)root.terms.size() > CF_MAX_TERMS) throw LowerError{CF_ERR_UNSUPPORTED, "kernel expands to too many terms"};
@@ -333,6 +378,17 @@ inline cf_program lower(const cf_knode_t* prog, int nnodes) {
         else { P.needs_r2 = 1; P.dotproduct = 0; }
     }
     if (!any) P.dotproduct = 0; // all-constant programs count as isotropic (reference src/properties.jl:49-50)
+    if (!ard_l.empty()) {
+        // the metric is applied to the points, so every atom that is used must see it: r2-atoms outside the ARD node or x.y atoms
+        // would be evaluated on the wrong coordinates
+        atom_in_ard.resize(atoms.size(), 0);
+        for (int a = 0; a < P.natoms; a++)
+            if (used[a] && !atom_in_ard[a])
+                throw LowerError{CF_ERR_UNSUPPORTED, "ARD: every base kernel of the program must be wrapped by the same ARD"};
+        P.isotropic = 0;  // Normed <: StationaryKernel (reference src/transformation.jl:25): not IsotropicInput, no derivative operators
+        P.dotproduct = 0;
+        *ard = ard_l;
+    }
     P.single = (P.nterms == 1 && P.terms[0].nfac == 1 && P.terms[0].fac[0].power == 1) ? 1 : 0;
     return P;
 }

@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from ._lib import CF_F32, CF_F64, DimensionMismatch, KNode, UnsupportedKernel, check, lib
-from .kernels import ARD, AbstractKernel, Dot, DotProductInput, GradientKernel, IsotropicInput
+from .kernels import AbstractKernel, Dot, DotProductInput, GradientKernel, IsotropicInput
 
 
 def _points(x, dtype=None):
@@ -194,13 +194,6 @@ class Gramian:
 
 def gramian(k, x, y=None):
     """gramian(k, x[, y]) (src/gramian.jl:144-159).  GradientKernel -> lazy block Gramian (src/gramian.jl:120-123)."""
-    if isinstance(k, ARD):  # pre-scale the data, then the inner isotropic kernel (cf. src/transformation.jl:83-95)
-        xs = _points(x)
-        if xs.shape[1] != k.l.size:
-            raise DimensionMismatch(f"ARD has {k.l.size} length scales, the points have dimension {xs.shape[1]}")
-        ys = None if (y is None or y is x) else _points(y, xs.dtype)
-        sc = k.scale().astype(xs.dtype)
-        return Gramian(k.k, xs * sc, None if ys is None else ys * sc, _rows_are_points=True)
     if not isinstance(k, (AbstractKernel, GradientKernel)):
         # gramian(x, y) = Gramian(Dot(), x, y) (src/gramian.jl:23,150-151)
         return Gramian(Dot(), k, x)

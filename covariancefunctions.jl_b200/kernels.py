@@ -16,7 +16,7 @@ import numpy as np
 from ._lib import DomainError, UnsupportedKernel
 
 # cf_op numbering (include/covfn_b200.h)
-OP_EQ, OP_EXP, OP_RQ, OP_MATERNP, OP_DOT, OP_CONST, OP_SUM, OP_PROD, OP_POW, OP_LENGTHSCALE = range(1, 11)
+OP_EQ, OP_EXP, OP_RQ, OP_MATERNP, OP_DOT, OP_CONST, OP_SUM, OP_PROD, OP_POW, OP_LENGTHSCALE, OP_ARDSCALE, OP_ARD = range(1, 13)
 
 
 # ---- input traits (properties.jl:31-37) ---------------------------------------------------------------------------
@@ -431,10 +431,10 @@ class ValueGradientKernel(GradientKernel):
         return f"ValueGradientKernel({self.k!r})"
 
 
-class ARD:
-    """ARD(k, l::AbstractVector) (transformation.jl:42-45): Normed(k, tau -> sum(tau_c^2 / l_c)).  Lowered by pre-scaling
-    the points with 1/sqrt(l_c) when the Gramian is built -- the reference itself pre-transforms the data for its
-    input-scaling kernels (transformation.jl:83-95) -- after which the isotropic kernel k runs unchanged.
+class ARD(AbstractKernel):
+    """ARD(k, l::AbstractVector) (transformation.jl:42-45): Normed(k, tau -> enorm2(Diagonal(inv.(l)), tau)), i.e.
+    k(sum_c tau_c^2 / l_c), a StationaryKernel (transformation.jl:25).  Lowered to the ABI's ARD node
+    (<k> ARDSCALE(l_1) ... ARDSCALE(l_d) ARD(d)); the library applies the metric to the points on the device.
     ARD(k, l::Real) is Lengthscale(k, l) (transformation.jl:46)."""
 
     def __new__(cls, k, l):
@@ -443,20 +443,24 @@ class ARD:
         return super().__new__(cls)
 
     def __init__(self, k, l):
-        if not isinstance(k, IsotropicKernel):
-            raise TypeError("ARD(k::IsotropicKernel, l)")
+        if not isinstance(k, AbstractKernel):
+            raise TypeError("ARD(k, l): k must be a kernel")
         l = np.asarray(l, dtype=np.float64)
         if not np.all(l > 0):
             raise DomainError(f"l = {l} is non-positive")
         self.k, self.l = k, l
+        self.eltype = k.eltype
 
-    def __call__(self, x, y):
-        x, y = np.asarray(x, dtype=np.float64), np.asarray(y, dtype=np.float64)
+    def _of_pair(self, x, y):
         tau = x - y
-        return self.k._of_scalar(float(np.sum(tau * tau / self.l)))
+        return self.k._of_scalar(float(np.sum(tau * (1.0 / self.l) * tau)))
 
-    def scale(self):
-        return 1.0 / np.sqrt(self.l)
+    def _of_scalar(self, t):  # (m::Normed)(tau) = m.k(m.n2(tau)) (transformation.jl:38)
+        tau = np.atleast_1d(np.asarray(t, dtype=np.float64))
+        return self.k._of_scalar(float(np.sum(tau * (1.0 / self.l) * tau)))
+
+    def program(self):
+        return self.k.program() + [(OP_ARDSCALE, 0, float(lc)) for lc in self.l] + [(OP_ARD, int(self.l.size), 0.0)]
 
     def __repr__(self):
         return f"ARD({self.k!r}, {self.l.tolist()})"

@@ -61,6 +61,14 @@ typedef enum { CF_F32 = 0, CF_F64 = 1 } cf_dtype;
  *   PROD      product of iparam children          algebra.jl:17
  *   POW       child ^ iparam (Int power)          algebra.jl:62
  *   LENGTHSCALE  child(r2 / l^2), child isotropic leaf   transformation.jl:19   fparam=l
+ *   ARDSCALE  pushes one length-scale entry l_c                                  fparam=l_c
+ *   ARD       pops iparam = d ARDSCALE entries and one isotropic child k: k(sum_c (x_c - y_c)^2 / l_c), i.e.
+ *             ARD(k, l::AbstractVector) = Normed(k, tau -> enorm2(Diagonal(inv.(l)), tau))   transformation.jl:25-45, util.jl:52
+ *             (postfix: <child nodes> ARDSCALE(l_1) ... ARDSCALE(l_d) ARD(d)).  The library applies the metric by scaling the
+ *             point coordinates with 1/sqrt(l_c) on the device while uploading them (as the reference pre-transforms the data of
+ *             its input-scaling kernels, transformation.jl:83-95), so every r2-kernel of the program must sit under ONE ARD with
+ *             ONE l and the program may not contain DOT; anything else is CF_ERR_UNSUPPORTED (the reference method runs).
+ *             ARD programs have the StationaryInput trait: no derivative operators (the reference uses its generic fallback).
  */
 typedef enum {
     CF_OP_EQ = 1,
@@ -72,7 +80,9 @@ typedef enum {
     CF_OP_SUM = 7,
     CF_OP_PROD = 8,
     CF_OP_POW = 9,
-    CF_OP_LENGTHSCALE = 10
+    CF_OP_LENGTHSCALE = 10,
+    CF_OP_ARDSCALE = 11,
+    CF_OP_ARD = 12
 } cf_op;
 
 typedef struct {

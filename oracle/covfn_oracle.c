@@ -36,7 +36,7 @@ typedef struct {
 
 enum {
     OP_EQ = 1, OP_EXP = 2, OP_RQ = 3, OP_MATERNP = 4, OP_DOT = 5, OP_CONST = 6,
-    OP_SUM = 7, OP_PROD = 8, OP_POW = 9, OP_LENGTHSCALE = 10
+    OP_SUM = 7, OP_PROD = 8, OP_POW = 9, OP_LENGTHSCALE = 10, OP_ARDSCALE = 11, OP_ARD = 12
 };
 
 #define ORC_MAXSTACK 64
@@ -169,13 +169,48 @@ static num eval_iso_leaf(const orc_knode_t* nd, num r2) {
 }
 static int is_iso_leaf(int op) { return op == OP_EQ || op == OP_EXP || op == OP_RQ || op == OP_MATERNP; }
 
+/* ARD(k, l) = Normed(k, tau -> enorm2(Diagonal(inv.(l)), tau))            reference src/transformation.jl:25-45
+ * (m::Normed)(x, y) = m.k(m.n2(difference(x, y)));  enorm2(A, x) = dot(x, A, x)       src/transformation.jl:38-39, src/util.jl:52
+ * LinearAlgebra.dot(x, D::Diagonal, y) sums conj(x_c) * d_c * y_c = (tau_c * (1 / l_c)) * tau_c, sequentially for short vectors;
+ * inv.(l) is Float64, so the squared norm is Float64 whatever the data type. */
+static num ard_norm2(int d, const double* x, const double* y, int f64, const orc_knode_t* scales) {
+    num val = mk(0, 1);
+    for (int c = 0; c < d; c++) {
+        num tau = mk(x[c] - y[c], f64);
+        num invl = mk(1.0 / scales[c].fparam, 1);
+        val = n_add(val, n_mul(n_mul(tau, invl), tau));
+    }
+    return val;
+}
+/* postfix layout: <child nodes> ARDSCALE(l_1) ... ARDSCALE(l_d) ARD(d).  For the leaf at index t, the ARDSCALE block of the ARD
+ * node whose child subtree contains t, or NULL. */
+static int node_arity(const orc_knode_t* nd) {
+    switch (nd->op) {
+        case OP_SUM: case OP_PROD: return nd->iparam;
+        case OP_POW: case OP_LENGTHSCALE: return 1;
+        case OP_ARD: return nd->iparam + 1;
+        default: return 0;
+    }
+}
+static const orc_knode_t* ard_scales_for(const orc_knode_t* prog, int nnodes, int t) {
+    for (int u = t + 1; u < nnodes; u++) {
+        if (prog[u].op != OP_ARD) continue;
+        int k = prog[u].iparam, root = u - k - 1, need = 1, i = root;
+        while (need > 0 && i >= 0) { need += node_arity(&prog[i]) - 1; i--; }
+        if (t > i && t <= root) return &prog[u - k];
+    }
+    return NULL;
+}
+
 static num kernel_eval(const orc_knode_t* prog, int nnodes, int d, const double* x, const double* y, int f64) {
     num st[ORC_MAXSTACK];
-    int sp = 0;
+    int sp = 0, has_ard = 0;
+    for (int t = 0; t < nnodes; t++) has_ard |= (prog[t].op == OP_ARD);
     for (int t = 0; t < nnodes; t++) {
         const orc_knode_t* nd = &prog[t];
         if (is_iso_leaf(nd->op)) {
-            num r2 = euclidean2(d, x, y, f64);
+            const orc_knode_t* sc = has_ard ? ard_scales_for(prog, nnodes, t) : NULL;
+            num r2 = sc ? ard_norm2(d, x, y, f64, sc) : euclidean2(d, x, y, f64);
             /* Lengthscale wrappers directly above the leaf: k(r2 / l^2), outermost first */
             int u = t + 1, nls = 0;
             while (u < nnodes && prog[u].op == OP_LENGTHSCALE) { u++; nls++; }
@@ -199,6 +234,8 @@ static num kernel_eval(const orc_knode_t* prog, int nnodes, int d, const double*
             st[sp++] = acc;
         } else if (nd->op == OP_POW) {
             st[sp - 1] = n_powi(st[sp - 1], nd->iparam);
+        } else if (nd->op == OP_ARDSCALE || nd->op == OP_ARD) {
+            /* the metric was applied at the leaves; the child's value stays on the stack */
         } else {
             return mk(NAN, 1);
         }
@@ -705,6 +742,8 @@ static long double truth_eval(const orc_knode_t* prog, int nnodes, int d, const 
         const orc_knode_t* nd = &prog[t];
         if (is_iso_leaf(nd->op)) {
             long double s = r2;
+            const orc_knode_t* sc = ard_scales_for(prog, nnodes, t);
+            if (sc) { s = 0; for (int c = 0; c < d; c++) { long double tt = (long double)x[c] - y[c]; s += tt * tt / (long double)sc[c].fparam; } }
             int u = t + 1, nls = 0;
             while (u < nnodes && prog[u].op == OP_LENGTHSCALE) { u++; nls++; }
             for (int w = t + nls; w > t; w--) s /= (long double)prog[w].fparam * prog[w].fparam;
@@ -718,6 +757,7 @@ static long double truth_eval(const orc_knode_t* prog, int nnodes, int d, const 
             for (int q = 1; q < k; q++) acc = (nd->op == OP_SUM) ? acc + st[sp - k + q] : acc * st[sp - k + q];
             sp -= k; st[sp++] = acc;
         } else if (nd->op == OP_POW) st[sp - 1] = powl(st[sp - 1], nd->iparam);
+        else if (nd->op == OP_ARDSCALE || nd->op == OP_ARD) { /* applied at the leaves */ }
         else return NAN;
     }
     return st[0];

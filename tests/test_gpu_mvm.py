@@ -208,20 +208,44 @@ def test_row_range(cf, O):
     assert np.array_equal(np.concatenate(parts), full)  # sharding does not change a single bit
 
 
-def test_ard_lengthscales(cf):
-    # ARD(k, l) = Normed(k, tau -> sum(tau^2 / l)) (src/transformation.jl:42-45, test/stationary.jl:132-154)
+def test_ard_lengthscales(cf, O):
+    """ARD(k, l) = Normed(k, tau -> sum(tau^2 / l)) (src/transformation.jl:42-45, test/stationary.jl:132-154): the ARD node of the
+    C ABI (metric applied to the points on the device) against the oracle's restatement of enorm2(Diagonal(inv.(l)), x - y)."""
     rng = np.random.default_rng(17)
-    n, m, d = 60, 45, 3
-    X, Y = rng.standard_normal((n, d)), rng.standard_normal((m, d))
-    a = rng.standard_normal(m)
-    l = np.exp(rng.standard_normal(d))
-    for k in (cf.EQ(), cf.MaternP(2), cf.RQ(2)):
-        kard = cf.ARD(k, l)
-        G = cf.gramian(kard, X.T.copy(), Y.T.copy())
-        M = np.array([[kard(X[i], Y[j]) for j in range(m)] for i in range(n)])
-        assert relerr(G @ a, M @ a) < 1e-12
-        assert relerr(G.Matrix(), M) < 1e-13
+    n, m = 260, 145
+    for d in (2, 3, 5, 11):
+        X, Y = rng.standard_normal((n, d)), rng.standard_normal((m, d))
+        a = rng.standard_normal(m)
+        A = rng.standard_normal((m, 3))
+        l = np.exp(rng.standard_normal(d))
+        for k in (cf.EQ(), cf.MaternP(2), cf.RQ(2), cf.Exp(), 0.5 * cf.EQ() + cf.MaternP(1) * cf.RQ(1.5)):
+            kard = cf.ARD(k, l)
+            prog = kard.program()
+            G = cf.gramian(kard, X.T.copy(), Y.T.copy())
+            assert relerr(G @ a, O.mul_vec(prog, X, a, Y=Y)) < TOL64
+            assert relerr(G @ A, O.mul_mat(prog, X, A, Y=Y)) < TOL64
+            assert relerr(G.Matrix(), O.matrix(prog, X, Y)) < 1e-13
+            assert abs(G[3, 7] - kard(X[3], Y[7])) < 1e-13
+            # symmetric case and a leading constant outside the ARD node
+            Gs = cf.gramian(2.5 * kard, X.T.copy())
+            assert relerr(Gs @ a[:1].repeat(n), O.mul_vec((2.5 * kard).program(), X, a[:1].repeat(n))) < TOL64
+    # Float32 data
+    X32 = rng.standard_normal((200, 3)).astype(np.float32)
+    a32 = rng.standard_normal(200).astype(np.float32)
+    k32 = cf.ARD(cf.EQ(), [0.5, 2.0, 1.3])
+    assert relerr(cf.gramian(k32, X32.T.copy()) @ a32, O.mul_vec(k32.program(), X32, a32, dtype=np.float32)) < 1e-5
     assert isinstance(cf.ARD(cf.EQ(), 2.0), cf.Lengthscale)  # ARD(k, l::Real) = Lengthscale(k, l)
+    # one metric per program; no derivative operators (Normed is a StationaryKernel)
+    with pytest.raises(cf.DimensionMismatch):
+        cf.gramian(cf.ARD(cf.EQ(), [1.0, 2.0]), X.T.copy()).handle()
+    with pytest.raises(cf.UnsupportedKernel):
+        cf.gramian(cf.ARD(cf.EQ(), l) + cf.MaternP(2), X.T.copy()).handle()
+    with pytest.raises(cf.UnsupportedKernel):
+        cf.gramian(cf.ARD(cf.EQ(), l) + cf.Dot(), X.T.copy()).handle()
+    with pytest.raises(cf.UnsupportedKernel):
+        cf.gramian(cf.ARD(cf.EQ(), l) * cf.ARD(cf.RQ(2), 2 * l), X.T.copy()).handle()
+    Gsame = cf.gramian(cf.ARD(cf.EQ(), l) * cf.ARD(cf.RQ(2), l), X.T.copy())  # the same metric twice is one pre-scaling
+    assert relerr(Gsame @ a[:1].repeat(n), O.mul_vec((cf.ARD(cf.EQ(), l) * cf.ARD(cf.RQ(2), l)).program(), X, a[:1].repeat(n))) < TOL64
 
 
 def test_runtime_specialised_mvm_matches_interpreter(cf, O):

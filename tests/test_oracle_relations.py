@@ -178,6 +178,36 @@ def test_lengthscale_semantics(cf, O):
             assert O.getindex(cf.Lengthscale(k, l).program(), x, 0, x, 1) == pytest.approx(k(r2 / l**2), rel=1e-13)
 
 
+def test_ard_semantics(cf, O):
+    """test/stationary.jl:132-154: ARD(k, l) with l = 1 is k; n2(x - y) = sum((x - y)^2 / l); kl(x, y) ~ k(x .* w, y .* w) with
+    w = sqrt(1 / l).  The oracle's ARD node restates enorm2(Diagonal(inv.(l)), difference(x, y)) (src/transformation.jl:38-45)."""
+    rng = np.random.default_rng(66)
+    for d in (2, 3, 5):
+        x = rng.standard_normal((2, d))
+        k = cf.EQ()
+        assert O.getindex(cf.ARD(k, np.ones(d)).program(), x, 0, x, 1) == pytest.approx(O.getindex(k.program(), x, 0, x, 1), rel=1e-15)
+        c = 2.0
+        r2 = float(np.sum((x[0] - x[1]) ** 2))
+        assert O.getindex(cf.ARD(k, c**2 * np.ones(d)).program(), x, 0, x, 1) == pytest.approx(k(r2 / c**2), rel=1e-14)
+        l = np.exp(rng.standard_normal(d))
+        w = np.sqrt(1 / l)
+        for k in (cf.EQ(), cf.Exp(), cf.RQ(1.0), cf.MaternP(2), 0.5 * cf.EQ() + cf.MaternP(1) * cf.RQ(2)):
+            kl = cf.ARD(k, l)
+            got = O.getindex(kl.program(), x, 0, x, 1)
+            assert got == pytest.approx(O.getindex(k.program(), x * w, 0, x * w, 1), rel=1e-13)
+            assert got == pytest.approx(kl(x[0], x[1]), rel=1e-13)                       # the mirror's own formula
+            assert got == pytest.approx(O.truth_getindex(kl.program(), x[0], x[1]), rel=1e-13)
+        # a constant outside the ARD node, and a Lengthscale inside it
+        kk = 3.0 * cf.ARD(cf.Lengthscale(cf.MaternP(2), 0.7), l)
+        s2 = float(np.sum((x[0] - x[1]) ** 2 / l))
+        assert O.getindex(kk.program(), x, 0, x, 1) == pytest.approx(3.0 * cf.MaternP(2)(s2 / 0.49), rel=1e-13)
+    # lazy vs dense (test/gramian.jl:56-72) with the ARD kernel
+    X = rng.standard_normal((40, 3))
+    a = rng.standard_normal(40)
+    kl = cf.ARD(cf.MaternP(2), [0.5, 2.0, 1.1])
+    assert np.allclose(O.mul_vec(kl.program(), X, a), O.matrix(kl.program(), X) @ a, rtol=1e-13, atol=1e-14)
+
+
 def mp_hessian_block(kfun, x, y):
     """d x d block  d/dx d/dy^T k(x, y) by high-precision central differences (the 'generic AD fallback' comparator,
     reference src/gradient.jl:27-42, test/gradient.jl:37-45)"""

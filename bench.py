@@ -1,7 +1,12 @@
 #!/usr/bin/env python
 """bench.py -- lazy-Gramian MVM throughput (BASELINE.json metric) on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c1|c3|c4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config c2|c1|c3|c4|c5] [--dtype f64|f32] [--spmd]
+
+--config c5 is BASELINE.json configs[4]: conjugate gradients on (K + sigma^2 I) x = y, K = gramian(MaternP(2), x), d = 8,
+n = 2^19, a fixed number of iterations (--cg-iters, default 20); a step is one whole solve through cf_cg_solve.  Under torchrun
+every rank owns a row block and the library gathers the product with NCCL once per iteration (csrc/cf_comm.h); with --spmd ONE
+process drives --gpus devices (cf_init) and the all-gather is fused into the producing kernels' epilogues (NVLink peer stores).
 
 A "step" is one pass of the hot path: one `mul!(b, K, a)` with K = gramian(EQ(), x), d = 3, n = 2^20, Float64
 (BASELINE.json configs[1]).  Rows of K are sharded as contiguous blocks over the ranks (one process per GPU under
@@ -49,6 +54,9 @@ def workload(name):
     if name == "c4":
         return dict(kernel=cf.EQ(), kname="GradientKernel(EQ)", d=16, n=65536, nrhs=1, gradient=True,
                     desc="GradientKernel(EQ) MVM, d=16, n=65536, Float64 (configs[3])")
+    if name == "c5":
+        return dict(kernel=cf.MaternP(2), kname="MaternP(2)", d=8, n=1 << 19, nrhs=1, gradient=False, cg=True, sigma2=1e-2,
+                    desc="CG on (K + sigma^2 I) x = y, K = gramian(MaternP(2), x), d=8, n=2^19, sigma^2=1e-2, Float64 (configs[4])")
     if name == "x1":  # not a BASELINE config: composite-kernel MVM used to measure the interpreter vs run-time specialisation
         return dict(kernel=0.5 * cf.EQ() + cf.MaternP(2) * cf.RQ(2), kname="1/2*EQ+MaternP(2)*RQ(2)", d=3, n=262144, nrhs=1,
                     gradient=False, desc="composite-kernel Gramian MVM, d=3, n=262144, Float64 (auxiliary)")
@@ -138,15 +146,16 @@ def cpu_port_rate(w, X, a, target_s=12.0, threads=None):
     O.set_num_threads(threads or os.cpu_count() or 1)  # torchrun exports OMP_NUM_THREADS=1; the CPU arm uses every host core
     prog = w["kernel"].program()
     n = w["n"]
+    dt = X.dtype.type
 
     def run(rows):
         t0 = time.perf_counter()
         if w["gradient"]:
             O.gradient_mul(prog, X, a, rows=(0, rows))
         elif w["nrhs"] == 1:
-            O.mul_vec(prog, X, a, rows=(0, rows))
+            O.mul_vec(prog, X, a, rows=(0, rows), dtype=dt)
         else:
-            O.mul_mat(prog, X, a, rows=(0, rows))  # reference loop order: entry re-evaluated per RHS column
+            O.mul_mat(prog, X, a, rows=(0, rows), dtype=dt)  # reference loop order: entry re-evaluated per RHS column
         return time.perf_counter() - t0
 
     nt = O.num_threads()
@@ -158,6 +167,41 @@ def cpu_port_rate(w, X, a, target_s=12.0, threads=None):
     return rows * float(n) / t, rows, t, nt
 
 
+def oracle_rows(w, X, a, rows, dtype):
+    """the reference's product restricted to `rows` (oracle as the checker, outside every timed region)"""
+    from oracle import oracle as O
+
+    O.build()
+    O.set_num_threads(os.cpu_count() or 1)
+    prog = w["kernel"].program()
+    if w["gradient"]:
+        return O.gradient_mul(prog, X, a, rows=rows)
+    if w["nrhs"] == 1:
+        return O.mul_vec(prog, X, a, rows=rows, dtype=dtype)
+    return O.mul_mat(prog, X, a, rows=rows, dtype=dtype)
+
+
+def recorded_ncu(config, dtype):
+    """per-config counters of the dominant kernel from the committed ncu pass (profiles/r2_ncu_metrics.json, written by
+    bench_aux/record_ncu_metrics.py from `ncu --set full` captures of this same command's kernels); None if not recorded"""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r2_ncu_metrics.json")))
+        return rec.get(f"{config}:{dtype}")
+    except Exception:
+        return None
+
+
+def load_peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        return {}
+
+
+CPU_NOTE = ("C/OpenMP restatement of the reference loop (oracle/: src/gramian.jl:78-99, 241-253); Julia is not installed here or on "
+            "the GPU box (profiles/r2_julia_probe.txt), so the reference binary cannot run")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -165,6 +209,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="c2")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--spmd", action="store_true", help="c5 only: ONE process drives --gpus devices (cf_init, fused peer-store gather)")
+    ap.add_argument("--cg-iters", type=int, default=20)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.warmup < 3:
@@ -174,44 +221,47 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     w = workload(args.config)
+    w.setdefault("cg", False)
+    if os.environ.get("CF_BENCH_N"):  # development only: a smaller n (the JSON line then names it in config.n)
+        w["n"] = int(os.environ["CF_BENCH_N"])
+        w["desc"] += f" [n overridden to {w['n']}]"
     n, d = w["n"], w["d"]
-    pairs_per_step = float(n) * float(n)
+    npdt = np.float64 if args.dtype == "f64" else np.float32
     unit = "kernel-pair evaluations/s"
     metric = "Gramian MVM kernel-evals/s"
-    cfg = {"workload": w["desc"], "kernel": w["kname"], "d": d, "n": n, "nrhs": w["nrhs"],
-           "sharding": f"contiguous row blocks over {world} rank(s), x and a replicated, all-gather of b per step" if world > 1
-           else "single GPU", "l2": "256 MiB L2 flush (memset) between timed steps, inside the timed region"}
+    ngpus = args.gpus if args.spmd else world
+    cfg = {"workload": w["desc"] + (" [Float32 variant]" if args.dtype == "f32" else ""), "kernel": w["kname"], "d": d, "n": n, "nrhs": w["nrhs"],
+           "sharding": (f"ONE process, rows sharded inside the library over {ngpus} device(s) (cf_init), all-gather fused into the kernel epilogues (peer stores)"
+                        if args.spmd else
+                        f"contiguous row blocks over {world} rank(s), x and a replicated, all-gather of b per product" if world > 1 else "single GPU"),
+           "l2": "256 MiB L2 flush (memset) between timed steps, inside the timed region"}
 
     # ------------------------------------------------------------------------------------------------ reference arm
     if args.impl == "reference":
         if rank != 0:
             return
         X, a = make_inputs(w)
+        X, a = X.astype(npdt), a.astype(npdt)
         rate0, rows, _, nt = cpu_port_rate(w, X, a, target_s=6.0)
-        from oracle import oracle as O
-
-        prog = w["kernel"].program()
         times = []
         for it in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            if w["gradient"]:
-                O.gradient_mul(prog, X, a, rows=(0, rows))
-            elif w["nrhs"] == 1:
-                O.mul_vec(prog, X, a, rows=(0, rows))
-            else:
-                O.mul_mat(prog, X, a, rows=(0, rows))
+            oracle_rows(w, X, a, (0, rows), npdt)
             if it >= args.warmup:
                 times.append(time.perf_counter() - t0)
         t = float(np.mean(times))
         value = rows * float(n) / t
-        sample = f"rows 0..{rows} of the n={n} row MVM ({rows * float(n):.3g} pairs per step), all {n} columns"
+        products = (args.cg_iters + 1) if w["cg"] else 1
+        sample = f"rows 0..{rows} of the n={n} row product ({rows * float(n):.3g} pairs per timed sample), all {n} columns"
         print(json.dumps({
             "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": t * 1e3 * (n / rows), "higher_is_better": True, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+            "warmup": args.warmup, "ms_per_step": t * 1e3 * (n / rows) * products, "ms_per_step_is_extrapolated": True,
+            "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": args.dtype, "data": "synthetic", "config": cfg,
             "cpu_baseline": {"value": value, "unit": unit, "cores": nt, "kind": "port", "sample": sample,
-                             "note": "C/OpenMP restatement of reference src/gramian.jl:78-87 (Julia is not installed; "
-                                     "the reference binary cannot run here). ms_per_step is extrapolated to all n rows."},
+                             "note": CPU_NOTE + ". Each timed step is the row sample; ms_per_step is EXTRAPOLATED linearly to all n rows"
+                                     + (f" and {products} products of the CG solve" if w["cg"] else "")
+                                     + " (so it does not fit the driver's clock around this run by construction)."},
             "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         }))
         return
@@ -231,8 +281,16 @@ def main():
         dist = dist_mod
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
+    if w["cg"]:
+        return run_cg(args, w, cfg, rank, world, local_rank, dev, dist, metric, unit)
+    if args.spmd:
+        raise SystemExit("--spmd applies to --config c5")
 
     X, a_host = make_inputs(w)
+    X, a_host = X.astype(npdt), a_host.astype(npdt)
+    pairs_per_step = float(n) * float(n)
+    tdt = torch.float64 if args.dtype == "f64" else torch.float32
+    es = 8 if args.dtype == "f64" else 4
     blk = d if w["gradient"] else 1
     k = cf.GradientKernel(w["kernel"]) if w["gradient"] else w["kernel"]
     r0, r1 = n * rank // world, n * (rank + 1) // world
@@ -240,19 +298,21 @@ def main():
     G.handle()
     nrhs = w["nrhs"]
     a_dev = torch.from_numpy(np.ascontiguousarray(a_host.T if nrhs > 1 else a_host)).to(dev)  # column-major m x nrhs
-    b_full = torch.empty((nrhs, n * blk) if nrhs > 1 else (n * blk,), dtype=torch.float64, device=dev)
-    b_loc = torch.empty((nrhs, (r1 - r0) * blk) if nrhs > 1 else ((r1 - r0) * blk,), dtype=torch.float64, device=dev)
+    b_full = torch.empty((nrhs, n * blk) if nrhs > 1 else (n * blk,), dtype=tdt, device=dev)
+    b_loc = torch.empty((nrhs, (r1 - r0) * blk) if nrhs > 1 else ((r1 - r0) * blk,), dtype=tdt, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     stream = torch.cuda.current_stream()
+    parts = [torch.empty((nrhs, (n * (r + 1) // world - n * r // world) * blk), dtype=tdt, device=dev) for r in range(world)] if nrhs > 1 else None
 
     def step_device():
         flush.zero_()
         G.mul_device(b_loc.data_ptr(), a_dev.data_ptr(), nrhs=nrhs, ldy=(r1 - r0) * blk, ldx=n * blk, stream=stream.cuda_stream)
         if dist is not None:
-            if nrhs == 1:
+            if nrhs == 1 and n % world == 0:
                 dist.all_gather_into_tensor(b_full, b_loc)
+            elif nrhs == 1:
+                dist.all_gather([b_full[(n * r // world) * blk:(n * (r + 1) // world) * blk] for r in range(world)], b_loc)
             else:
-                parts = [torch.empty_like(b_loc) for _ in range(world)]
                 dist.all_gather(parts, b_loc)
         return b_loc
 
@@ -283,6 +343,27 @@ def main():
     ms_per_step = total_ms / args.steps
     value = pairs_per_step / (ms_per_step * 1e-3)
 
+    # parity spot check, outside the timed region: rows spanning the first and the last rank boundary (or the middle of the
+    # matrix on one GPU) of the gathered product against the reference restatement
+    parity = None
+    if rank == 0:
+        full = (b_full if world > 1 and nrhs == 1 else (torch.cat(parts, dim=1) if world > 1 else b_loc)).cpu().numpy()
+        full = full.T if nrhs > 1 else full
+        bounds = sorted({n * 1 // world, n * (world - 1) // world} - {0, n}) if world > 1 else [n // 2]
+        half = 16 if nrhs > 1 else 32
+        worst, checked = 0.0, []
+        for bnd in bounds:
+            rws = (max(0, bnd - half), min(n, bnd + half))
+            ref = oracle_rows(w, X, a_host, rws, npdt)
+            got = full[rws[0] * blk:rws[1] * blk]
+            err = float(np.linalg.norm(np.asarray(got, dtype=np.float64) - ref) / np.linalg.norm(ref))
+            worst = max(worst, err)
+            checked.append(list(rws))
+        tol = 1e-12 if args.dtype == "f64" else 1e-5
+        parity = {"rows": checked, "rel_2norm_err_vs_oracle": worst, "tolerance": tol, "ok": bool(worst < tol)}
+        if not parity["ok"]:
+            raise SystemExit(f"bench.py: parity spot check failed: {parity}")
+
     # dominant kernel alone (CUDA events recorded by the library on the launch stream, around the kernel + its reduction)
     for _ in range(args.steps):
         G.mul_device(b_loc.data_ptr(), a_dev.data_ptr(), nrhs=nrhs, ldy=(r1 - r0) * blk, ldx=n * blk)  # library stream, blocking
@@ -291,20 +372,22 @@ def main():
     kernel_ms = float(np.mean(kern_ms))
     launches_per_step = launches
 
-    # opt-in symmetric variant (each unordered pair evaluated once; NOT the headline: see include/covfn_b200.h CF_OPT_SYMMETRIC)
+    # the symmetric variant (each unordered pair evaluated once) and the plain one, reported side by side
     sym = None
-    if world == 1 and nrhs == 1 and not w["gradient"]:
-        G.set_symmetric(True)
-        ts = []
-        for _ in range(1 + min(args.steps, 3)):
-            G.mul_device(b_loc.data_ptr(), a_dev.data_ptr())
-            ts.append(G.last_timing()[0])
+    if world == 1 and nrhs == 1 and not w["gradient"] and args.dtype == "f64":
+        out_sym = {}
+        for on in (True, False):
+            G.set_symmetric(on)
+            ts = []
+            for _ in range(1 + min(args.steps, 3)):
+                G.mul_device(b_loc.data_ptr(), a_dev.data_ptr())
+                ts.append(G.last_timing()[0])
+            out_sym[on] = float(np.mean(ts[1:]))
         G.set_symmetric(False)
-        sym_ms = float(np.mean(ts[1:]))
-        sym = {"ms_per_step": sym_ms, "mvm_equivalent_pairs_per_s": pairs_per_step / (sym_ms * 1e-3),
-               "evaluated_pairs_per_s": 0.5 * pairs_per_step / (sym_ms * 1e-3),
-               "note": "cf_gramian_set_option(CF_OPT_SYMMETRIC): K = K^T, every unordered pair evaluated once and used for b_i and "
-                       "b_j; column half accumulated with fp64 atomics (not bit-reproducible), off by default, not used for `value`"}
+        sym = {"ms_per_step": out_sym[True], "mvm_equivalent_pairs_per_s": pairs_per_step / (out_sym[True] * 1e-3),
+               "evaluated_pairs_per_s": 0.5 * pairs_per_step / (out_sym[True] * 1e-3), "all_pairs_ms_per_step": out_sym[False],
+               "note": "cf_gramian_set_option(CF_OPT_SYMMETRIC): K = K^T, every unordered pair evaluated once and used for b_i and b_j; "
+                       "`value` above counts the n*m entries the reference evaluates and is measured with this option OFF"}
 
     # end to end through the public host API, pinned host buffers, X uploaded every step
     a_pin = torch.from_numpy(np.ascontiguousarray(a_host.T if nrhs > 1 else a_host)).pin_memory()
@@ -314,16 +397,10 @@ def main():
     XT = X.T  # d x n, column-major (columns are points): the layout of a Julia Matrix passed to gramian(k, X)
 
     def step_e2e():
-        t_a = time.perf_counter()
         Ge = cf.gramian(k, XT).set_row_range(r0, r1)  # create: uploads X (reference: gramian(k, x) is O(1) lazy)
         Ge.handle()
-        t_b = time.perf_counter()
         cf.mul_(b_np, Ge, a_np)
-        t_c = time.perf_counter()
         Ge.close()
-        if os.environ.get("CF_BENCH_DEBUG"):
-            print(f"[e2e] create {1e3 * (t_b - t_a):.1f} ms, mul_ {1e3 * (t_c - t_b):.1f} ms, close {1e3 * (time.perf_counter() - t_c):.1f} ms",
-                  file=sys.stderr)
 
     step_e2e()
     barrier()
@@ -331,10 +408,7 @@ def main():
     e2e_steps = max(2, min(args.steps, 3))
     for _ in range(e2e_steps):
         step_e2e()
-    t_loop = time.perf_counter()
     barrier()
-    if os.environ.get("CF_BENCH_DEBUG"):
-        print(f"[e2e] loop {1e3 * (t_loop - t0):.1f} ms, barrier {1e3 * (time.perf_counter() - t_loop):.1f} ms", file=sys.stderr)
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     if dist is not None:
         tt = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
@@ -342,67 +416,233 @@ def main():
         e2e_s = float(tt.item())
     e2e_value = pairs_per_step / e2e_s
     h2d = X.nbytes + a_host.nbytes
-    d2h = b_loc.numel() * 8
+    d2h = b_loc.numel() * es
 
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
 
-    # roofline of the dominant kernel against the DFMA peak measured now
-    peak_lane_ops, _ = cf.peak_probe("dfma", 1 << 15)
-    slots = SLOTS[args.config]
-    my_pairs = float(r1 - r0) * float(n)
-    achieved_tflops = 2.0 * slots * my_pairs / (kernel_ms * 1e-3) / 1e12
-    peak_tflops = 2.0 * peak_lane_ops / 1e12
-    alg_bytes = X.nbytes + a_host.nbytes + (r1 - r0) * blk * 8 * nrhs
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    roofline = {
-        "bound": "fp64_fma_pipe", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
-        "frac": achieved_tflops / peak_tflops,
-        # dram__bytes_read.sum + dram__bytes_write.sum of this kernel, one ncu --set full capture at this workload
-        # (profiles/r1_ncu_mvm_eq_c2_n1048576.md): 33.90 MB + 0.76 MB per launch; only known for the 1-GPU c2 shape
-        "traffic": 34653184 if (args.config == "c2" and world == 1) else None,
-        "kernel_ms": kernel_ms, "flops_per_pair": 2 * slots,
-        # `frac` uses SURVEY.md 8d's fixed reference instruction sequence (exp = 16 slots, distance = 2 d), so a kernel with a
-        # cheaper exp (9 FP64 instructions here) or a tensor-core distance can exceed 1; the counter-level view is in profiles/
-        "note": "reference-slot accounting (implementation independent); executed FP64 instructions per pair for c2: 15 of the "
-                "23 slots -> the FP64 pipe itself is at frac * 15 / 23 of the probe peak (ncu: 78.8 % pipe-active)",
-        "fp64_instr_frac": (achieved_tflops / peak_tflops) * 15.0 / 23.0 if args.config == "c2" else None,
-        "peak_source": "cf_peak_probe DFMA microbenchmark in this run (MEASURED_PEAKS.json has no FP64 entry); "
-                       "nominal 64 DFMA/clk/SM x 148 SMs x 1.965 GHz = 37.2 TFLOP/s",
-        "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
-                "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
-                "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"},
-    }
     out = {
         "metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.dtype,
         "data": "synthetic", "config": cfg, "clocks": sampler.result(),
         "e2e": {"value": e2e_value, "unit": unit, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": e2e_s * 1e3,
                 "note": "gramian(k, X) handle creation (packs and uploads X) + mul_(b, G, a) with pinned host a, b, every step"},
         "gpu_launches": int(launches_per_step) * args.steps,
-        "roofline": roofline,
-        "pct_of_fp64_peak": 100.0 * achieved_tflops / peak_tflops,
+        "roofline": roofline_block(cf, args, w, world, kernel_ms, float(r1 - r0) * float(n), X.nbytes + a_host.nbytes + (r1 - r0) * blk * es * nrhs),
+        "parity_check": parity,
     }
+    out["pct_of_fp64_peak" if args.dtype == "f64" else "pct_of_fp32_peak"] = 100.0 * out["roofline"]["frac"]
     if sym is not None:
         out["symmetric_variant"] = sym
     if world == 1 and not args.no_cpu_baseline:
         rate, rows, secs, nt = cpu_port_rate(w, X, a_host, target_s=12.0)
         out["cpu_baseline"] = {
             "value": rate, "unit": unit, "cores": nt, "kind": "port",
-            "sample": f"rows 0..{rows} of the same n={n} MVM ({rows * float(n):.3g} pairs, {secs:.1f} s)",
-            "note": "C/OpenMP restatement of reference src/gramian.jl:78-87 (oracle/); Julia absent, reference binary not runnable; "
-                    "README.md:37-38 publishes 4.59e8 pairs/s for MaternP(2), d=3, n=16384 on unstated hardware",
+            "sample": f"rows 0..{rows} of the same n={n} product ({rows * float(n):.3g} pairs, {secs:.1f} s)",
+            "note": CPU_NOTE + "; README.md:37-38 publishes 4.59e8 pairs/s for MaternP(2), d=3, n=16384 on unstated hardware",
         }
     print(json.dumps(out))
     if dist is not None:
+        dist.destroy_process_group()
+
+
+def roofline_block(cf, args, w, world, kernel_ms, my_pairs, alg_bytes):
+    """FP64 (or FP32) FMA-pipe roofline of the dominant kernel.  `achieved` follows SURVEY.md section 8d: the fixed reference
+    instruction sequence (slots per pair x 2 flops) over the measured kernel time; `peak` is the FMA rate measured in this run by
+    cf_peak_probe (MEASURED_PEAKS.json has no FP64 / FP32 entry).  Because the reference sequence charges 16 slots for an exp
+    that costs 8-9 FP64 instructions here and 2 d for a distance that costs d, `frac` can exceed 1: it compares WORK, not pipe
+    occupancy.  The occupancy view -- FP64 pipe cycles active, DRAM bytes -- comes from the ncu pass recorded for this config
+    (profiles/r2_ncu_metrics.json) and is reported beside it."""
+    slots = SLOTS[args.config]
+    f64 = args.dtype == "f64"
+    peak_lane_ops, _ = cf.peak_probe("dfma" if f64 else "ffma", 1 << 15)
+    achieved_tflops = 2.0 * slots * my_pairs / (kernel_ms * 1e-3) / 1e12
+    peak_tflops = 2.0 * peak_lane_ops / 1e12
+    peaks = load_peaks()
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    rec = recorded_ncu(args.config, args.dtype) if world == 1 else None
+    sm_mhz = peaks.get("sm_max_mhz", 1965.0)
+    rl = {
+        "bound": "fp64_fma_pipe" if f64 else "fp32_fma_pipe", "achieved": achieved_tflops, "peak": peak_tflops, "unit": "TFLOP/s",
+        "frac": achieved_tflops / peak_tflops,
+        "traffic": (rec or {}).get("dram_bytes"),
+        "kernel_ms": kernel_ms, "flops_per_pair": 2 * slots,
+        "fp64_pipe_active": (rec or {}).get("fp64_pipe_active_pct"),
+        "issue_active": (rec or {}).get("issue_active_pct"),
+        "ncu_source": (rec or {}).get("source"),
+        "peak_lane_fma_per_clk_per_sm": peak_lane_ops / 148.0 / (sm_mhz * 1e6),
+        "note": "frac = reference-slot work (SURVEY.md 8d) / measured FMA peak: implementation independent, can exceed 1 when the kernel "
+                "needs fewer instructions than the reference sequence (EQ d=3: 12 FP64 instructions per pair against 23 slots); "
+                "fp64_pipe_active is the occupancy figure (ncu sm__pipe_fp64_cycles_active of the recorded pass)",
+        "peak_source": "cf_peak_probe FMA microbenchmark in this run (two-register operand form: bench_aux/micro/fp64_issue_probe.cu); "
+                       "MEASURED_PEAKS.json has no FP64/FP32 FMA entry; nominal 64 DFMA/clk/SM x 148 SMs x 1.965 GHz = 37.2 TFLOP/s",
+        "hbm": {"algorithmic_bytes": alg_bytes, "achieved_gbs": alg_bytes / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                "frac": alg_bytes / (kernel_ms * 1e-3) / 1e9 / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"},
+    }
+    if not f64:
+        mufu, _ = cf.peak_probe("mufu", 1 << 15)
+        rl["mufu_peak_lane_ops_per_s"] = mufu
+    return rl
+
+
+def run_cg(args, w, cfg, rank, world, local_rank, dev, dist, metric, unit):
+    """BASELINE config 5: a step is ONE conjugate-gradient solve of --cg-iters iterations through cf_cg_solve (iterates stay on
+    the device(s)); pairs per step = (iterations + 1) n^2 (one operator product per iteration plus the initial residual)."""
+    import torch
+
+    import covfn_b200 as cf
+    from covfn_b200 import distributed as D
+
+    n, d = w["n"], w["d"]
+    sigma2 = w["sigma2"]
+    rng = np.random.Generator(np.random.Philox(0xC0F00005))
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    y = rng.standard_normal(n)
+    iters = args.cg_iters
+    products = iters + 1
+    pairs_per_step = products * float(n) * float(n)
+    ngpus = args.gpus if args.spmd else world
+    if args.spmd:
+        if world != 1:
+            raise SystemExit("--spmd is a single-process mode: do not launch it under torchrun")
+        cf.init(list(range(args.gpus)))
+    elif world > 1:
+        D.comm_init_from_torch()
+    r0, r1 = (0, n) if args.spmd else (n * rank // world, n * (rank + 1) // world)
+    XT = X.T
+
+    def make():
+        G = cf.gramian(w["kernel"], XT)
+        if not args.spmd and world > 1:
+            G.set_row_range(r0, r1)
+        G.handle()
+        return G
+
+    G = make()
+    A = sigma2 * cf.I(n) + G
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def solve(op):
+        return op.solve(y, reltol=1e-300, maxiter=iters)  # a fixed number of iterations
+
+    x = None
+    for _ in range(args.warmup):
+        flush.zero_()
+        x, it, res = solve(A)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    t0 = time.perf_counter()
+    prod_ms = gather_ms = 0.0
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        x, it, res = solve(A)
+        tm = A.cg_timing()
+        prod_ms += tm[1]
+        gather_ms += tm[2]
+    barrier()
+    total_s = time.perf_counter() - t0
+    sampler.stop_flag = True
+    assert it == iters, (it, iters)
+    if dist is not None:
+        tt = torch.tensor([total_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        total_s = float(tt.item())
+    ms_per_step = 1e3 * total_s / args.steps
+    value = pairs_per_step / (ms_per_step * 1e-3)
+
+    # every rank must hold bit-identical iterates (scalars are recomputed from gathered vectors, no all-reduce)
+    identical = True
+    if dist is not None:
+        chk = torch.from_numpy(np.frombuffer(np.array([x.sum(), np.abs(x).max(), x[n // 3]]).tobytes(), dtype=np.int64).copy()).to(dev)
+        allc = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        identical = all(torch.equal(allc[0], c) for c in allc)
+
+    # end to end: handle creation (uploads X) + solve, every step
+    def step_e2e():
+        Ge = make()
+        xe, _, _ = solve(sigma2 * cf.I(n) + Ge)
+        Ge.close()
+        return xe
+
+    step_e2e()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = 2
+    for _ in range(e2e_steps):
+        step_e2e()
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if dist is not None:
+        tt = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_s = float(tt.item())
+
+    if rank != 0:
+        if dist is not None:
+            D.comm_destroy()
+            dist.destroy_process_group()
+        return
+
+    # parity, outside the timed region: (1) the recurrence residual against the true residual of the returned iterate, computed
+    # with the reference restatement on a row sample; (2) the operator product itself on rows spanning a rank boundary
+    from oracle import oracle as O
+
+    O.build()
+    O.set_num_threads(os.cpu_count() or 1)
+    prog = w["kernel"].program()
+    bnd = n // ngpus if ngpus > 1 else n // 2
+    rws = (bnd - 24, bnd + 24)
+    Ax = O.mul_vec(prog, X, x, rows=rws) + sigma2 * x[rws[0]:rws[1]]
+    Gfull = cf.gramian(w["kernel"], XT) if (world > 1 and not args.spmd) else G
+    got = (Gfull @ x)[rws[0]:rws[1]] + sigma2 * x[rws[0]:rws[1]]
+    perr = float(np.linalg.norm(got - Ax) / np.linalg.norm(Ax))
+    parity = {"rows": [list(rws)], "rel_2norm_err_vs_oracle": perr, "tolerance": 1e-12, "ok": bool(perr < 1e-12),
+              "what": "(sigma^2 I + K) x_final on rows spanning a shard boundary: library vs reference restatement"}
+    if not parity["ok"]:
+        raise SystemExit(f"bench.py: parity spot check failed: {parity}")
+
+    kernel_ms = prod_ms / (args.steps * products) if prod_ms > 0 else ms_per_step / products
+    my_pairs = float(r1 - r0) * float(n) if not args.spmd else float(n) * float(n) / ngpus
+    out = {
+        "metric": metric, "value": value, "unit": unit, "n_gpus": ngpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": dict(cfg, cg_iterations=iters, sigma2=sigma2, products_per_step=products,
+                                            mode="spmd (one process, cf_init)" if args.spmd else ("torchrun + cf_comm (NCCL inside the library)" if world > 1 else "single GPU")),
+        "clocks": sampler.result(),
+        "cg": {"iterations": iters, "ms_per_iteration": ms_per_step / products, "product_ms_per_iteration": kernel_ms,
+               "allgather_ms_per_iteration": gather_ms / (args.steps * products) if gather_ms > 0 else (None if ngpus > 1 and args.spmd else 0.0),
+               "allgather_share": (gather_ms / (args.steps * products)) / (ms_per_step / products) if gather_ms > 0 else None,
+               "recurrence_residual": res, "rhs_norm": float(np.linalg.norm(y)), "ranks_bit_identical": bool(identical),
+               "note": "all-gather of the 4 MiB product once per iteration: NCCL (torchrun mode, timed with CUDA events inside the library) "
+                       "or fused into the kernel epilogues as NVLink peer stores (spmd mode: not separable, share = None)"},
+        "e2e": {"value": pairs_per_step / e2e_s, "unit": unit, "h2d_bytes_per_step": int(X.nbytes + 2 * y.nbytes), "d2h_bytes_per_step": int(y.nbytes),
+                "ms_per_step": e2e_s * 1e3, "note": "gramian(k, X) (uploads X) + (sigma^2 I + K) \\ y from host vectors, every step"},
+        "gpu_launches": int(args.steps * products * 6),
+        "roofline": roofline_block(cf, args, w, 1 if ngpus == 1 else 2, kernel_ms, my_pairs, X.nbytes + 2 * y.nbytes),
+        "parity_check": parity,
+    }
+    out["pct_of_fp64_peak"] = 100.0 * out["roofline"]["frac"]
+    if ngpus == 1 and not args.no_cpu_baseline:
+        rate, rows, secs, nt = cpu_port_rate(w, X, y, target_s=12.0)
+        out["cpu_baseline"] = {"value": rate, "unit": unit, "cores": nt, "kind": "port",
+                               "sample": f"rows 0..{rows} of one n={n} operator product ({rows * float(n):.3g} pairs, {secs:.1f} s)",
+                               "note": CPU_NOTE}
+    print(json.dumps(out))
+    if dist is not None:
+        D.comm_destroy()
         dist.destroy_process_group()
 
 

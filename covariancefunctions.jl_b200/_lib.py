@@ -76,6 +76,12 @@ SYMBOLS = {
     "cf_cg_solve": (_int, [_vp, _dbl, _vp, _vp, _dbl, _int, _int, C.POINTER(_int), C.POINTER(_dbl)]),
     "cf_last_timing": (_int, [_vp, C.POINTER(C.c_float), C.POINTER(_int)]),
     "cf_peak_probe": (_int, [_int, _int, C.POINTER(_dbl), C.POINTER(C.c_float)]),
+    "cf_cg_timing": (_int, [C.c_void_p, C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_dbl), C.POINTER(_int)]),
+    "cf_comm_unique_id": (_int, [C.c_void_p, _int]),
+    "cf_comm_init": (_int, [C.c_void_p, _int, _int]),
+    "cf_comm_destroy": (_int, []),
+    "cf_comm_info": (_int, [C.POINTER(_int), C.POINTER(_int), C.POINTER(_int)]),
+    "cf_comm_allgather_rows": (_int, [C.c_void_p, C.c_int64, C.c_int64, _int, C.c_void_p]),
     "cf_jit_stats": (_int, [C.POINTER(_int), C.POINTER(_int), C.POINTER(_int), C.POINTER(_dbl)]),
     "cf_jit_check": (_int, [C.POINTER(KNode), _int, _int, _int, C.c_char_p, _int]),
 }

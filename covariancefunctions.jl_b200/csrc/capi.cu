@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <chrono>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -18,6 +19,7 @@
 #include "cf_lower.h"
 #include "cf_registry.h"
 #include "cf_jit.h"
+#include "cf_comm.h"
 #include "cf_extra.cuh"
 #include "bigd.cuh"
 
@@ -160,6 +162,10 @@ struct cf_gramian_s {
     bool opt_symmetric = false; // use the symmetric variant (each unordered pair evaluated once) when applicable
     float last_ms = 0;
     int last_launches = 0;
+    // timing of the last cf_cg_solve (cf_cg_timing): host wall clock of the whole solve, device time of the operator products and
+    // of the NCCL row-block gathers (multi-process mode), number of operator products
+    double cg_total_ms = 0, cg_mvm_ms = 0, cg_gather_ms = 0;
+    int cg_products = 0;
 };
 
 namespace {
@@ -470,6 +476,108 @@ int cg_solve_spmd(cf_gramian_s* g, double sigma2, double* x, const double* b, do
     return CF_OK;
 }
 
+// Multi-process CG (one process per GPU, cf_comm_init): every rank holds the full iterates and updates them redundantly -- the
+// scalars come from identical vectors through the same deterministic reduction, so all ranks take bit-identical decisions and no
+// all-reduce is needed -- each rank computes its row block of (sigma2 I + K) u in place and ONE NCCL all-gather per product
+// re-assembles the vector.  The handle must be restricted to this rank's block of the standard split.
+int cg_solve_comm(cf_gramian_s* g, double sigma2, double* x, const double* b, double reltol, int maxiter, int deriv, int* iters,
+                  double* resnorm) {
+    const bool gradient = deriv != 0;
+    const int vg = deriv == 2 ? 1 : 0;
+    const int64_t blk = deriv == 0 ? 1 : g->d + vg;
+    const int64_t N = g->n * blk;
+    cfcomm::Comm& cm = cfcomm::comm();
+    Shard& sh = g->shards[0];
+    if (sh.ctx->dev != cm.dev)
+        return fail(CF_ERR_NCCL, "cf_cg_solve: the handle lives on device %d, the communicator on device %d", sh.ctx->dev, cm.dev);
+    if (reltol <= 0) reltol = std::sqrt(2.220446049250313e-16);
+    if (maxiter <= 0) maxiter = (int)std::min<int64_t>(N, 2147483647);
+    CF_CUDA(cudaSetDevice(sh.ctx->dev));
+    for (int q = 0; q < 5; q++)
+        if (int rc = sh.cg[q].ensure((size_t)N * 8)) return rc;
+    if (int rc = sh.cg[5].ensure(64)) return rc;
+    double *dx = (double*)sh.cg[0].p, *dr = (double*)sh.cg[1].p, *du = (double*)sh.cg[2].p, *dc = (double*)sh.cg[3].p,
+           *db = (double*)sh.cg[4].p, *dscal = (double*)sh.cg[5].p;
+    cudaStream_t st = sh.stream;
+    const int vb = (int)std::min<int64_t>((N + 255) / 256, 4096);
+    const int64_t off = sh.r0 * blk, cnt = (sh.r1 - sh.r0) * blk;
+    CF_CUDA(cudaMemcpyAsync(dx, x, N * 8, cudaMemcpyHostToDevice, st));
+    CF_CUDA(cudaMemcpyAsync(db, b, N * 8, cudaMemcpyHostToDevice, st));
+    CF_CUDA(cudaMemsetAsync(du, 0, N * 8, st));
+    cudaEvent_t ea, eb, ec;
+    CF_CUDA(cudaEventCreate(&ea)); CF_CUDA(cudaEventCreate(&eb)); CF_CUDA(cudaEventCreate(&ec));
+    g->last_launches = 0;
+    g->cg_mvm_ms = g->cg_gather_ms = 0; g->cg_products = 0;
+    bool pending = false;  // events of the last product not yet read
+
+    auto collect = [&]() {  // after a stream synchronisation: add the last product's device times
+        if (!pending) return;
+        float m = 0, ga = 0;
+        if (cudaEventElapsedTime(&m, ea, eb) == cudaSuccess) g->cg_mvm_ms += m;
+        if (cudaEventElapsedTime(&ga, eb, ec) == cudaSuccess) g->cg_gather_ms += ga;
+        pending = false;
+    };
+    // out = (sigma2 I + K) v on every rank: own row block in place, then the all-gather
+    auto apply = [&](double* out, const double* v) -> int {
+        CF_CUDA(cudaEventRecord(ea, st));
+        if (cnt > 0) {
+            const int sb = (int)std::min<int64_t>((cnt + 255) / 256, 4096);
+            cf_axpby_kernel<<<sb, 256, 0, st>>>(out + off, sigma2, v + off, 0.0, v + off, cnt);
+            CF_CUDA(cudaGetLastError());
+            int rc = gradient ? launch_grad(g, sh, out + off, out + off, v, 1.0, 1.0, st, vg) : launch_mvm(g, sh, out + off, out + off, v, 1.0, 1.0, st);
+            if (rc) return rc;
+        }
+        CF_CUDA(cudaEventRecord(eb, st));
+        const int nrc = cfcomm::allgather_rows(out, g->n, blk, 8, st);
+        if (nrc) return fail(CF_ERR_NCCL, "cf_cg_solve: NCCL all-gather failed: %s", cfcomm::api().GetErrorString(nrc));
+        CF_CUDA(cudaEventRecord(ec, st));
+        pending = true;
+        g->cg_products++;
+        return CF_OK;
+    };
+    auto dot = [&](const double* u, const double* v, double* host) -> int {
+        cf_dot_kernel<<<1, 1024, 0, st>>>(u, v, N, dscal);
+        CF_CUDA(cudaGetLastError());
+        CF_CUDA(cudaMemcpyAsync(host, dscal, 8, cudaMemcpyDeviceToHost, st));
+        CF_CUDA(cudaStreamSynchronize(st));
+        collect();
+        return CF_OK;
+    };
+    int rc_all = CF_OK, it = 0;
+    double rr = 0, residual = 0, prev_residual = 1.0;
+    do {
+        if ((rc_all = apply(dc, dx))) break;                       // r = b - A x
+        cf_axpby_kernel<<<vb, 256, 0, st>>>(dr, 1.0, db, -1.0, dc, N);
+        if ((rc_all = dot(dr, dr, &rr))) break;
+        residual = std::sqrt(rr);
+        const double tol = reltol * residual;
+        while (residual > tol && it < maxiter) {
+            const double beta = (residual * residual) / (prev_residual * prev_residual);
+            cf_axpby_kernel<<<vb, 256, 0, st>>>(du, 1.0, dr, beta, du, N);   // u = r + beta u
+            if ((rc_all = apply(dc, du))) break;                             // c = A u
+            double uc = 0;
+            if ((rc_all = dot(du, dc, &uc))) break;
+            const double alpha = (residual * residual) / uc;
+            cf_axpby_kernel<<<vb, 256, 0, st>>>(dx, 1.0, dx, alpha, du, N);   // x += alpha u
+            cf_axpby_kernel<<<vb, 256, 0, st>>>(dr, 1.0, dr, -alpha, dc, N);  // r -= alpha c
+            prev_residual = residual;
+            if ((rc_all = dot(dr, dr, &rr))) break;
+            residual = std::sqrt(rr);
+            it++;
+        }
+    } while (false);
+    if (!rc_all) {
+        if (cudaMemcpyAsync(x, dx, N * 8, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+            rc_all = fail(CF_ERR_CUDA, "cg_solve: result copy failed");
+    }
+    cudaStreamSynchronize(st);
+    cudaEventDestroy(ea); cudaEventDestroy(eb); cudaEventDestroy(ec);
+    if (rc_all) return rc_all;
+    if (iters) *iters = it;
+    if (resnorm) *resnorm = residual;
+    return CF_OK;
+}
+
 // conjugate gradients on (sigma2 I + K) x = b; restates IterativeSolvers.cg! 0.9.2 [upstream] behind
 // ldiv!(x, ::LazyMatrixSum, b) (reference src/lazy_linear_algebra.jl:126-144).  State lives on shard 0; with several shards
 // the search direction is broadcast to every device and the row blocks of K u are gathered back once per iteration
@@ -483,6 +591,9 @@ int cg_solve_impl(cf_gramian_s* g, double sigma2, double* x, const double* b, do
     if (reltol <= 0) reltol = std::sqrt(2.220446049250313e-16);
     if (maxiter <= 0) maxiter = (int)std::min<int64_t>(N, 2147483647);
     if (N == 0) { if (iters) *iters = 0; if (resnorm) *resnorm = 0; return CF_OK; }
+    g->cg_mvm_ms = g->cg_gather_ms = 0; g->cg_products = 0;
+    if (cfcomm::active() && g->shards.size() == 1 && (g->row_begin != 0 || g->row_end != g->n))
+        return cg_solve_comm(g, sigma2, x, b, reltol, maxiter, deriv, iters, resnorm);
     if (g->shards.size() > 1) {
         int rc = cg_solve_spmd(g, sigma2, x, b, reltol, maxiter, deriv, iters, resnorm);
         if (rc != 1) return rc; // 1: no peer access -> gather through device 0 below
@@ -502,11 +613,17 @@ int cg_solve_impl(cf_gramian_s* g, double sigma2, double* x, const double* b, do
     g->last_launches = 0;
 
     // c = sigma2 * v + K v   (LazyMatrixSum mul!: y = 0; y += D v; y += G v)
+    bool pending = false;
     auto apply = [&](double* out, const double* v) -> int {
+        CF_CUDA(cudaEventRecord(s0.ev0, st));
         cf_axpby_kernel<<<vb, 256, 0, st>>>(out, sigma2, v, 0.0, v, N);
         CF_CUDA(cudaGetLastError());
+        g->cg_products++;
         if (g->shards.size() == 1) {
-            return gradient ? launch_grad(g, s0, out, out, v, 1.0, 1.0, st, vg) : launch_mvm(g, s0, out, out, v, 1.0, 1.0, st);
+            int rc = gradient ? launch_grad(g, s0, out, out, v, 1.0, 1.0, st, vg) : launch_mvm(g, s0, out, out, v, 1.0, 1.0, st);
+            CF_CUDA(cudaEventRecord(s0.ev1, st));
+            pending = true;
+            return rc;
         }
         CF_CUDA(cudaStreamSynchronize(st));
         for (size_t q = 0; q < g->shards.size(); q++) {
@@ -543,6 +660,11 @@ int cg_solve_impl(cf_gramian_s* g, double sigma2, double* x, const double* b, do
         CF_CUDA(cudaGetLastError());
         CF_CUDA(cudaMemcpyAsync(host, dscal, 8, cudaMemcpyDeviceToHost, st));
         CF_CUDA(cudaStreamSynchronize(st));
+        if (pending) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, s0.ev0, s0.ev1) == cudaSuccess) g->cg_mvm_ms += ms;
+            pending = false;
+        }
         return CF_OK;
     };
 
@@ -1495,14 +1617,92 @@ int cf_cg_solve(cf_gramian_t g, double sigma2, void* x, const void* b, double re
     if (!x || !b) return fail(CF_ERR_BAD_ARGUMENT, "cf_cg_solve: NULL vector");
     if (g->n != g->m) return fail(CF_ERR_DIMENSION, "cf_cg_solve: Gramian is %lld x %lld, not square", (long long)g->n, (long long)g->m);
     if (g->dtype != CF_F64) return fail(CF_ERR_UNSUPPORTED, "cf_cg_solve: Float64 only");
-    if (g->row_begin != 0 || g->row_end != g->n) return fail(CF_ERR_UNSUPPORTED, "cf_cg_solve: handle is restricted to a row range");
+    if (g->row_begin != 0 || g->row_end != g->n) {
+        // multi-process mode: the handle of rank r must own exactly block r of the standard split
+        if (!cfcomm::active() || g->shards.size() != 1)
+            return fail(CF_ERR_UNSUPPORTED, "cf_cg_solve: handle is restricted to a row range (initialise cf_comm_init for the multi-process solve)");
+        int64_t r0, r1;
+        cfcomm::row_block(g->n, cfcomm::comm().rank, cfcomm::comm().world, &r0, &r1);
+        if (g->row_begin != r0 || g->row_end != r1)
+            return fail(CF_ERR_DIMENSION, "cf_cg_solve: rank %d must own rows [%lld, %lld), the handle has [%lld, %lld)", cfcomm::comm().rank,
+                        (long long)r0, (long long)r1, (long long)g->row_begin, (long long)g->row_end);
+    }
     if (gradient < 0 || gradient > 2) return fail(CF_ERR_BAD_ARGUMENT, "cf_cg_solve: gradient must be 0, 1 or 2");
     if (gradient) {
         if (int rc = check_derivative(g)) return rc;
         if (int rc = check_vg_dim(g, gradient)) return rc;
     }
     std::lock_guard<std::mutex> lk(g->mu);
-    return cg_solve_impl(g, sigma2, (double*)x, (const double*)b, reltol, maxiter, gradient, iters, resnorm);
+    const auto t0 = std::chrono::steady_clock::now();
+    const int rc = cg_solve_impl(g, sigma2, (double*)x, (const double*)b, reltol, maxiter, gradient, iters, resnorm);
+    g->cg_total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    return rc;
+}
+
+int cf_cg_timing(cf_gramian_t g, double* total_ms, double* product_ms, double* gather_ms, int* products) {
+    if (int rc = check_handle(g)) return rc;
+    if (total_ms) *total_ms = g->cg_total_ms;
+    if (product_ms) *product_ms = g->cg_mvm_ms;
+    if (gather_ms) *gather_ms = g->cg_gather_ms;
+    if (products) *products = g->cg_products;
+    return CF_OK;
+}
+
+// ---- multi-process row sharding over NCCL (cf_comm.h) ---------------------------------------------------------------------
+int cf_comm_unique_id(void* id, int bytes) {
+    if (!id || bytes < 128) return fail(CF_ERR_BAD_ARGUMENT, "cf_comm_unique_id: need a 128-byte buffer");
+    cfcomm::Api& a = cfcomm::api();
+    if (!a.error.empty()) return fail(CF_ERR_NCCL, "cf_comm_unique_id: %s", a.error.c_str());
+    cfcomm::ncclUniqueId u;
+    const int rc = a.GetUniqueId(&u);
+    if (rc) return fail(CF_ERR_NCCL, "ncclGetUniqueId failed: %s", a.GetErrorString(rc));
+    std::memcpy(id, u.internal, 128);
+    return CF_OK;
+}
+
+int cf_comm_init(const void* id, int rank, int world) {
+    if (!id || world < 1 || rank < 0 || rank >= world) return fail(CF_ERR_BAD_ARGUMENT, "cf_comm_init: bad arguments");
+    if (cf_device_count() < 1) return fail(CF_ERR_CUDA, "cf_comm_init: no CUDA device available");
+    cfcomm::Api& a = cfcomm::api();
+    if (!a.error.empty()) return fail(CF_ERR_NCCL, "cf_comm_init: %s", a.error.c_str());
+    cfcomm::Comm& c = cfcomm::comm();
+    if (c.comm) return fail(CF_ERR_BAD_ARGUMENT, "cf_comm_init: communicator already initialised (cf_comm_destroy first)");
+    int dev = 0;
+    CF_CUDA(cudaGetDevice(&dev));
+    cfcomm::ncclUniqueId u;
+    std::memcpy(u.internal, id, 128);
+    cfcomm::ncclComm_t comm = nullptr;
+    const int rc = a.CommInitRank(&comm, world, u, rank);
+    if (rc) return fail(CF_ERR_NCCL, "ncclCommInitRank failed: %s", a.GetErrorString(rc));
+    c.comm = comm; c.rank = rank; c.world = world; c.dev = dev;
+    return CF_OK;
+}
+
+int cf_comm_destroy(void) {
+    cfcomm::Comm& c = cfcomm::comm();
+    if (c.comm) cfcomm::api().CommDestroy(c.comm);
+    c.comm = nullptr; c.rank = 0; c.world = 1; c.dev = -1;
+    return CF_OK;
+}
+
+int cf_comm_info(int* rank, int* world, int* nccl_version) {
+    cfcomm::Comm& c = cfcomm::comm();
+    if (rank) *rank = c.rank;
+    if (world) *world = c.comm ? c.world : 1;
+    if (nccl_version) {
+        *nccl_version = 0;
+        cfcomm::Api& a = cfcomm::api();
+        if (a.error.empty() && a.GetVersion) a.GetVersion(nccl_version);
+    }
+    return CF_OK;
+}
+
+int cf_comm_allgather_rows(void* d_full, int64_t n, int64_t block, int dtype, void* stream) {
+    if (!cfcomm::active()) return fail(CF_ERR_NCCL, "cf_comm_allgather_rows: no communicator (cf_comm_init)");
+    if (!d_full || n < 0 || block < 1 || (dtype != CF_F32 && dtype != CF_F64)) return fail(CF_ERR_BAD_ARGUMENT, "cf_comm_allgather_rows: bad arguments");
+    const int rc = cfcomm::allgather_rows(d_full, n, block, esize(dtype), (cudaStream_t)stream);
+    if (rc) return fail(CF_ERR_NCCL, "NCCL all-gather failed: %s", cfcomm::api().GetErrorString(rc));
+    return CF_OK;
 }
 
 int cf_last_timing(cf_gramian_t g, float* kernel_ms, int* launches) {

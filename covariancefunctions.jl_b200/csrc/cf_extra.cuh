@@ -408,17 +408,19 @@ static __global__ void __launch_bounds__(1024) cf_dot_kernel(const double* __res
 
 // ---- pipe peak probes ---------------------------------------------------------------------------------------------------
 // dependent-chain-free FMAs: 16 independent chains per thread, register resident, 128 FMAs per loop trip so that the
-// loop overhead (3 non-FMA instructions) is < 2.5 % of the issue slots.
+// loop overhead (3 non-FMA instructions) is < 2.5 % of the issue slots.  Operand form x = fma(x, y, b) with y a per-thread
+// register and b a constant: an FP64 instruction with TWO constant operands needs an extra cycle and one with THREE register
+// operands needs three (bench_aux/micro/fp64_issue_probe.cu: 56.9, 41.6 and, for this form, 63.5 lane-FMA per clock per SM).
 #define CF_PROBE_BODY(T, FMA)                                                                                         \
-    T x[16];                                                                                                          \
-    _Pragma("unroll") for (int q = 0; q < 16; q++) x[q] = (T)(threadIdx.x + q);                                       \
+    T x[16], y[16];                                                                                                   \
+    _Pragma("unroll") for (int q = 0; q < 16; q++) { x[q] = (T)(threadIdx.x + q); y[q] = a + (T)1e-9 * (T)(threadIdx.x + q); } \
     for (int i = 0; i < iters; i += 8) {                                                                              \
         _Pragma("unroll") for (int u = 0; u < 8; u++) {                                                               \
-            _Pragma("unroll") for (int q = 0; q < 16; q++) x[q] = FMA(x[q], a, b);                                    \
+            _Pragma("unroll") for (int q = 0; q < 16; q++) x[q] = FMA(x[q], y[q], b);                                 \
         }                                                                                                             \
     }                                                                                                                 \
     T s = 0;                                                                                                          \
-    _Pragma("unroll") for (int q = 0; q < 16; q++) s += x[q];                                                         \
+    _Pragma("unroll") for (int q = 0; q < 16; q++) s += x[q] + y[q];                                                  \
     out[(size_t)blockIdx.x * blockDim.x + threadIdx.x] = s;
 
 static __global__ void __launch_bounds__(256) cf_peak_dfma_kernel(double* out, int iters, double a, double b) { CF_PROBE_BODY(double, fma) }

@@ -99,7 +99,42 @@ def gpu_local_mul(G):
 
     def f(u: torch.Tensor) -> torch.Tensor:
         out = torch.empty((r1 - r0) * blk, dtype=u.dtype, device=u.device)
-        G.mul_device(out.data_ptr(), u.contiguous().data_ptr(), stream=torch.cuda.current_stream().cuda_stream)
+        u = u.contiguous()
+        st = torch.cuda.current_stream()
+        if st.cuda_stream == 0:
+            # torch's default stream has handle 0, which the C ABI reads as "use the library's own (non-blocking) stream and block
+            # until done": that stream does not order itself after work queued on the legacy default stream, so whatever produced
+            # `u` must have finished before the call (the call itself returns only when the product is complete)
+            st.synchronize()
+        G.mul_device(out.data_ptr(), u.data_ptr(), stream=st.cuda_stream)
         return out
 
     return f
+
+
+def comm_init_from_torch(group=None):
+    """Bootstrap the library's own NCCL communicator (csrc/cf_comm.h) from an initialised torch.distributed process group:
+    rank 0 draws the NCCL unique id (cf_comm_unique_id), torch broadcasts its 128 bytes, every rank calls cf_comm_init with its
+    CUDA device current.  Afterwards `(sigma2 * I(n) + G).solve(b)` on a row-restricted Gramian runs the multi-process CG
+    inside the library (one NCCL all-gather per product).  Returns (rank, world)."""
+    import ctypes as C
+
+    from ._lib import check, lib
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    buf = (C.c_ubyte * 128)()
+    if rank == 0:
+        check(lib().cf_comm_unique_id(buf, 128))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    t = torch.tensor(list(buf), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=0, group=group)
+    raw = bytes(t.cpu().tolist())
+    ident = (C.c_ubyte * 128).from_buffer_copy(raw)
+    check(lib().cf_comm_init(ident, rank, world))
+    return rank, world
+
+
+def comm_destroy():
+    from ._lib import check, lib
+
+    check(lib().cf_comm_destroy())

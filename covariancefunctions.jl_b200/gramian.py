@@ -319,6 +319,12 @@ class LazyMatrixSum:
                                 float(reltol), int(maxiter), (1 + G.k.block_extra) if G.is_gradient else 0, C.byref(iters), C.byref(res)))
         return x, iters.value, res.value
 
+    def cg_timing(self):
+        """(total ms, operator-product ms, all-gather ms, products) of the last solve (cf_cg_timing)"""
+        t, m, ga, k = C.c_double(), C.c_double(), C.c_double(), C.c_int()
+        check(lib().cf_cg_timing(self.G.handle(), C.byref(t), C.byref(m), C.byref(ga), C.byref(k)))
+        return t.value, m.value, ga.value, k.value
+
 
 def peak_probe(kind: str = "dfma", iters: int = 1 << 16):
     """Measured pipe peak on the current device: lane-instructions per second (bench.py's roofline denominator)."""

@@ -191,6 +191,26 @@ int cf_value_gradient_mul_device(cf_gramian_t g, void* d_y, int64_t ldy, const v
 int cf_cg_solve(cf_gramian_t g, double sigma2, void* x, const void* b, double reltol, int maxiter,
                 int gradient, int* iters, double* resnorm);
 
+/* device / NCCL time of the last cf_cg_solve on this handle: host wall clock of the call, device time of the operator products
+ * and of the row-block all-gathers (multi-process mode only), number of operator products (iterations + 1) */
+int cf_cg_timing(cf_gramian_t g, double* total_ms, double* product_ms, double* gather_ms, int* products);
+
+/* ---- multi-process row sharding: one process per GPU, NCCL over NVLink --------------------- */
+/*
+ * The reference is single-process; rows of K are independent (src/gramian.jl:81,244), so across GPUs every rank owns the
+ * contiguous row block [n r / world, n (r + 1) / world) (cf_gramian_set_row_range) and chained products (CG) re-assemble the
+ * vector with ONE all-gather per product.  libnccl.so.2 is dlopen()ed on first use (COVFN_NCCL_LIB overrides the name).
+ * Bootstrap: rank 0 calls cf_comm_unique_id, the host ships the 128 bytes to the other ranks, every rank calls cf_comm_init
+ * with its CUDA device current.  Afterwards cf_cg_solve accepts a handle restricted to the rank's block: iterates are replicated
+ * and updated redundantly (bit-identical on every rank), the product's row blocks are gathered in place.
+ */
+int cf_comm_unique_id(void* id128, int bytes);
+int cf_comm_init(const void* id128, int rank, int world);
+int cf_comm_destroy(void);
+int cf_comm_info(int* rank, int* world, int* nccl_version);
+/* in-place all-gather of a device vector of n blocks of `block` elements whose rank-r part is rows [n r / world, n (r+1) / world) */
+int cf_comm_allgather_rows(void* d_full, int64_t n, int64_t block, int dtype, void* stream);
+
 /* ---- measurement helpers (used by bench.py; not part of the reference surface) ------------ */
 /* timing of the last *_mul call on this handle: device ms of the dominant kernel and its launch count */
 int cf_last_timing(cf_gramian_t g, float* kernel_ms, int* launches);

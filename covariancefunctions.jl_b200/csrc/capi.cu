@@ -133,9 +133,10 @@ struct Shard {
     void* Y = nullptr;  // m x D (== X when symmetric)
     void* xn = nullptr;  // squared norms of the padded points (multi-RHS kernel)
     void* yn = nullptr;
-    Buf a, y, partial, apad, ypad, at, cg[6], sym_items, bsym, bd_t, bd_s, xp, yp, ap;
+    Buf a, y, partial, apad, ypad, at, cg[6], sym_items, bsym, sym_col, bd_t, bd_s, xp, yp, ap;
     bool mmd_ready = false; // xp / yp hold the padded point copies of the DMMA multi-RHS kernel
-    int sym_nitems = 0;
+    int sym_nitems = 0;     // symmetric variant: work items, row tile and chunk length they were built for
+    int64_t sym_tr = 0, sym_ch = 0;
     int64_t r0 = 0, r1 = 0; // rows owned
 };
 
@@ -159,7 +160,7 @@ struct cf_gramian_s {
     const cf_kernel_entry* entry = nullptr;
     std::vector<Shard> shards;
     std::mutex mu;
-    bool opt_symmetric = false; // use the symmetric variant (each unordered pair evaluated once) when applicable
+    bool opt_symmetric = true;  // use the symmetric variant (each unordered pair evaluated once) when applicable
     float last_ms = 0;
     int last_launches = 0;
     // timing of the last cf_cg_solve (cf_cg_timing): host wall clock of the whole solve, device time of the operator products and
@@ -798,54 +799,73 @@ int launch_bigd_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yi
     return CF_OK;
 }
 
-// symmetric variant (gram_mvm_sym.cuh): diagonal row blocks with the plain kernel, everything beyond them once
+// symmetric variant (gram_mvm_sym.cuh): diagonal row blocks with the plain kernel, everything beyond them once; deterministic
+// (single-writer partial sums, fixed-order combine).  Returns 1 when the variant does not apply (caller runs the plain path).
 int launch_mvm_sym(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, const double* d_a, double alpha, double beta,
-                   cudaStream_t stream) {
+                   cudaStream_t stream, const cf_peer_out* peers) {
     const int64_t n = g->n;
-    const cf_mvm_config& cfg = g->entry->mvm_cfg[CF_F64];
+    const bool eqf = g->eq_fast && g->entry->sym_eq != nullptr && !env_flag("COVFN_MVM_SCALAR");
+    const cf_mvm_config& cfg = eqf ? g->entry->mvm_eq_cfg : g->entry->mvm_cfg[CF_F64];
     const int64_t TR = cfg.rows_per_cta, TJ = cfg.tj;
     const int64_t T = (n + TR - 1) / TR;
-    if (sh.sym_nitems == 0) { // build the (row tile, column chunk) list once per handle
+    if (sh.sym_nitems == 0 || sh.sym_tr != TR) { // build the (row tile, column chunk) list once per handle
         int64_t ch = ((T * n / 2 / 8192) / TJ) * TJ;
-        if (ch < TJ) ch = TJ;
+        if (ch < 8 * TJ) ch = 8 * TJ;
         std::vector<cf_sym_item> items;
-        for (int64_t I = 0; I < T; I++)
-            for (int64_t c0 = (I + 1) * TR; c0 < n; c0 += ch) {
+        int64_t colpart_elems = 0, maxchunks = 0;
+        for (int64_t I = 0; I < T; I++) {
+            const int64_t first = (I + 1) * TR;
+            const int64_t off = I * n - TR * (I * (I + 1) / 2);  // triangular layout, see gram_sym_combine
+            int64_t c = 0;
+            for (int64_t c0 = first; c0 < n; c0 += ch, c++) {
                 cf_sym_item it;
-                it.col0 = c0; it.col1 = std::min(n, c0 + ch); it.row_tile = (int32_t)I; it.pad_ = 0;
+                it.col0 = c0; it.col1 = std::min(n, c0 + ch); it.colpart_off = off + (c0 - first);
+                it.row_tile = (int32_t)I; it.chunk = (int32_t)c;
                 items.push_back(it);
             }
+            maxchunks = std::max(maxchunks, c);
+            if (first < n) colpart_elems = off + (n - first);
+        }
+        size_t free_b = 0, total_b = 0;
+        CF_CUDA(cudaMemGetInfo(&free_b, &total_b));
+        if ((size_t)colpart_elems * 8 > total_b / 4) return 1;  // column partials would not fit comfortably: plain path
         if (int rc = sh.sym_items.ensure(std::max<size_t>(16, items.size() * sizeof(cf_sym_item)))) return rc;
         if (!items.empty())
             CF_CUDA(cudaMemcpyAsync(sh.sym_items.p, items.data(), items.size() * sizeof(cf_sym_item), cudaMemcpyHostToDevice, stream));
         CF_CUDA(cudaStreamSynchronize(stream)); // items is a host temporary
+        if (int rc = sh.sym_col.ensure(std::max<size_t>(16, (size_t)colpart_elems * 8))) return rc;
+        if (int rc = sh.bsym.ensure(std::max<size_t>(16, (size_t)maxchunks * n * 8))) return rc;
         sh.sym_nitems = (int)items.size();
+        sh.sym_tr = TR; sh.sym_ch = ch;
     }
-    if (int rc = sh.bsym.ensure((size_t)n * 8)) return rc;
     if (int rc = sh.partial.ensure((size_t)n * 8)) return rc;
-    CF_CUDA(cudaMemsetAsync(sh.bsym.p, 0, (size_t)n * 8, stream));
     // 1. diagonal blocks: plain kernel, each CTA sweeps only its own row block, raw sums into partial[0][*]
     cf_mvm_params P;
     std::memset(&P, 0, sizeof(P));
-    P.X = sh.X; P.Y = sh.X; P.a = d_a; P.out = sh.partial.p;
+    P.X = sh.X; P.Y = sh.X; P.a = d_a; P.xn = sh.xn; P.yn = sh.xn; P.out = sh.partial.p;
     P.exp2_tbl = sh.ctx->exp2_tbl; P.sop = g->sop_val;
     P.row0 = 0; P.nrows = n; P.m = n; P.cols_per_chunk = ((n + TJ - 1) / TJ) * TJ;
     P.alpha = 1.0; P.beta = 0.0; P.direct = 0; P.use_tma = 1; P.diag_block = TR;
     if (g->prog.single) P.atom = g->prog.atoms[g->prog.terms[0].fac[0].atom].v;
-    CF_CUDA(g->entry->mvm[CF_F64][cf_kind_slot(g->kind)](P, dim3((unsigned)T, 1), stream));
+    const long double lam = 0.693147180559945309417232121458176568L / 256.0L;
+    P.eqc[0] = (double)lam; P.eqc[1] = (double)(lam * lam / 2); P.eqc[2] = (double)(lam * lam * lam / 6);
+    P.eqc[3] = (double)(lam * lam * lam * lam / 24);
+    CF_CUDA((eqf ? g->entry->mvm_eq : g->entry->mvm[CF_F64][cf_kind_slot(g->kind)])(P, dim3((unsigned)T, 1), stream));
     // 2. everything beyond the diagonal blocks, each unordered pair once
     if (sh.sym_nitems > 0) {
         cf_sym_params S;
         std::memset(&S, 0, sizeof(S));
-        S.X = (const double*)sh.X; S.a = d_a; S.bsym = (double*)sh.bsym.p; S.exp2_tbl = sh.ctx->exp2_tbl;
+        S.X = (const double*)sh.X; S.xn = (const double*)sh.xn; S.a = d_a;
+        S.rowpart = (double*)sh.bsym.p; S.colpart = (double*)sh.sym_col.p; S.exp2_tbl = sh.ctx->exp2_tbl;
         S.items = (const cf_sym_item*)sh.sym_items.p; S.n = n; S.use_tma = 1;
         S.atom = P.atom; S.sop = g->sop_val;
-        CF_CUDA(g->entry->sym[cf_kind_slot(g->kind)](S, sh.sym_nitems, stream));
+        for (int q = 0; q < 4; q++) S.eqc[q] = P.eqc[q];
+        CF_CUDA((eqf ? g->entry->sym_eq : g->entry->sym[cf_kind_slot(g->kind)])(S, sh.sym_nitems, stream));
     }
-    // 3. y = alpha (diag + sym) + beta y
-    const int blocks = (int)std::min<int64_t>((n + 255) / 256, 4096);
-    gram_sym_combine<<<blocks, 256, 0, stream>>>((const double*)sh.partial.p, (const double*)sh.bsym.p, n, d_y, d_yin,
-                                                 alpha * g->coef, beta);
+    // 3. y = alpha (diag + row partials + column partials) + beta y, fixed summation order
+    const int blocks = (int)std::min<int64_t>((n + 255) / 256, 8192);
+    gram_sym_combine<<<blocks, 256, 0, stream>>>((const double*)sh.partial.p, (const double*)sh.bsym.p, (const double*)sh.sym_col.p, n, TR,
+                                                 sh.sym_ch, d_y, d_yin, alpha * g->coef, beta, *peers);
     CF_CUDA(cudaGetLastError());
     g->last_launches += 3;
     return CF_OK;
@@ -962,9 +982,12 @@ int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const v
     }
     if (!g->entry) return launch_bigd_mvm(g, sh, (double*)d_y, (const double*)d_yin, (const double*)d_a, alpha, beta, stream);
     const cf_mvm_config& cfg = g->entry->mvm_cfg[dt];
-    if (g->opt_symmetric && g->symmetric && dt == CF_F64 && sh.r0 == 0 && sh.r1 == g->n && g->n >= 65536 &&
-        (((uintptr_t)d_a) % 16) == 0)
-        return launch_mvm_sym(g, sh, (double*)d_y, (const double*)d_yin, (const double*)d_a, alpha, beta, stream);
+    // y === x: every unordered pair once (gram_mvm_sym.cuh, deterministic); on by default, CF_OPT_SYMMETRIC / COVFN_SYMMETRIC=0 turn it off
+    if (g->opt_symmetric && g->symmetric && dt == CF_F64 && sh.r0 == 0 && sh.r1 == g->n && g->n >= 32768 &&
+        (((uintptr_t)d_a) % 16) == 0 && !(g->kind == CF_ATOM_SOP && cfjit::wanted((double)nrows * (double)g->m))) {
+        const int rc = launch_mvm_sym(g, sh, (double*)d_y, (const double*)d_yin, (const double*)d_a, alpha, beta, stream, peers);
+        if (rc != 1) return rc;
+    }
     // high-dimensional, well-scaled Float64 points: pair distances on the FP64 tensor cores (gram_mvm_dmma.cuh);
     // COVFN_MVM_SCALAR=1 keeps the scalar kernel
     const int slot = cf_kind_slot(g->kind);
@@ -1189,7 +1212,7 @@ int destroy_impl(cf_gramian_s* g) {
         dev_free(sh.X);
         if (sh.yn && sh.yn != sh.xn) dev_free(sh.yn);
         dev_free(sh.xn);
-        sh.a.release(); sh.y.release(); sh.partial.release(); sh.apad.release(); sh.ypad.release(); sh.at.release(); sh.sym_items.release(); sh.bsym.release(); sh.bd_t.release(); sh.bd_s.release();
+        sh.a.release(); sh.y.release(); sh.partial.release(); sh.apad.release(); sh.ypad.release(); sh.at.release(); sh.sym_items.release(); sh.bsym.release(); sh.sym_col.release(); sh.bd_t.release(); sh.bd_s.release();
         sh.xp.release(); sh.yp.release(); sh.ap.release();
         for (auto& b : sh.cg) b.release();
         if (sh.ev0) cudaEventDestroy(sh.ev0);
@@ -1266,6 +1289,7 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
     g->row_begin = 0; g->row_end = n;
     g->prog = lowered;
     g->sop_val = sop_val; g->sop_grad = sop_grad; g->grad_ok = grad_ok;
+    g->opt_symmetric = true;  // y === x: each unordered pair evaluated once (deterministic, gram_mvm_sym.cuh)
     if (const char* e = std::getenv("COVFN_SYMMETRIC")) g->opt_symmetric = std::atoi(e) != 0;
     g->entry = entry;
     if (lowered.single) {

@@ -36,8 +36,11 @@ const cf_kernel_entry entry = {
     {&cf_mm_launch<float, D, 512>, &cf_mm_launch<double, D, 256>},
     cf_mmd_entry<D>::fn,
     cf_mmd_entry<D>::smem,
-    {&cf_sym_launch<D, CF_ATOM_EQ, TU::R, TU::NT, TU::TJ, TU::NS, 1>, &cf_sym_launch<D, CF_ATOM_MATERN, TU::R, TU::NT, TU::TJ, TU::NS, 1>,
-     &cf_sym_launch<D, CF_ATOM_RQ_INT, TU::R, TU::NT, TU::TJ, TU::NS, 1>, &cf_sym_launch<D, CF_ATOM_SOP, TU::R, TU::NT, TU::TJ, TU::NS, 1>},
+    {&cf_sym_launch<D, CF_ATOM_EQ, false, TU::R, TU::NT, TU::TJ, TU::NS, 1>, &cf_sym_launch<D, CF_ATOM_MATERN, false, TU::R, TU::NT, TU::TJ, TU::NS, 1>,
+     &cf_sym_launch<D, CF_ATOM_RQ_INT, false, TU::R, TU::NT, TU::TJ, TU::NS, 1>, &cf_sym_launch<D, CF_ATOM_SOP, false, TU::R, TU::NT, TU::TJ, TU::NS, 1>},
+    cf_sym_smem<D, TU::TJ, TU::NS, TU::NT / 32, false>::total,
+    cf_syme_entry<D>::fn,
+    cf_syme_entry<D>::smem,
     {cf_mvd_entry<D>::fn[0], cf_mvd_entry<D>::fn[1], cf_mvd_entry<D>::fn[2], cf_mvd_entry<D>::fn[3]},
     cf_mvd_entry<D>::cfg,
     {{cf_gradd_entry<D>::fn[0][0], cf_gradd_entry<D>::fn[0][1], cf_gradd_entry<D>::fn[0][2], cf_gradd_entry<D>::fn[0][3]},

@@ -31,7 +31,10 @@ struct cf_kernel_entry {
     cf_mm_launch_fn mm[2]; // [dtype]
     cf_mm_launch_fn mm_dmma; // Float64 tensor-core (DMMA) variant, nullptr when D % 4 != 0 or D < 8
     int mm_dmma_smem;        // its dynamic shared memory (run-time specialised launches need it)
-    cf_sym_launch_fn sym[CF_NKINDS]; // Float64 symmetric variant, [kind slot]
+    cf_sym_launch_fn sym[CF_NKINDS]; // Float64 symmetric variant (gram_mvm_sym.cuh), [kind slot]; row tile = mvm_cfg[1].rows_per_cta
+    int sym_smem;                    // its dynamic shared memory
+    cf_sym_launch_fn sym_eq;         // ... with the scaled-domain EQ evaluation (row tile = mvm_eq_cfg.rows_per_cta), nullptr for D > 6
+    int sym_eq_smem;
     cf_mvm_launch_fn mvm_dmma[CF_NKINDS]; // Float64 tensor-core value MVM (gram_mvm_dmma.cuh), nullptr when unavailable for D
     cf_mvm_config mvm_dmma_cfg;
     cf_gradd_launch_fn grad_dmma[2][4]; // Float64 tensor-core gradient MVM: [value_gradient][0 EQ, 1 generic isotropic, 2 MaternP(p>=2), 3 dot product]; nullptr when unavailable

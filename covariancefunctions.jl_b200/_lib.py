@@ -81,6 +81,7 @@ SYMBOLS = {
     "cf_comm_init": (_int, [C.c_void_p, _int, _int]),
     "cf_comm_destroy": (_int, []),
     "cf_comm_info": (_int, [C.POINTER(_int), C.POINTER(_int), C.POINTER(_int)]),
+    "cf_gramian_mul_collective_device": (_int, [C.c_void_p, C.c_void_p, C.c_void_p, _dbl, _dbl, C.c_void_p]),
     "cf_comm_allgather_rows": (_int, [C.c_void_p, C.c_int64, C.c_int64, _int, C.c_void_p]),
     "cf_jit_stats": (_int, [C.POINTER(_int), C.POINTER(_int), C.POINTER(_int), C.POINTER(_dbl)]),
     "cf_jit_check": (_int, [C.POINTER(KNode), _int, _int, _int, C.c_char_p, _int]),

@@ -135,8 +135,9 @@ struct Shard {
     void* yn = nullptr;
     Buf a, y, partial, apad, ypad, at, cg[6], sym_items, bsym, sym_col, bd_t, bd_s, xp, yp, ap;
     bool mmd_ready = false; // xp / yp hold the padded point copies of the DMMA multi-RHS kernel
-    int sym_nitems = 0;     // symmetric variant: work items, row tile and chunk length they were built for
+    int sym_nitems = -1;    // symmetric variant: work items (-1: not built), row tile, chunk length and device share they were built for
     int64_t sym_tr = 0, sym_ch = 0;
+    int sym_part = 0, sym_parts = 1;
     int64_t r0 = 0, r1 = 0; // rows owned
 };
 
@@ -323,6 +324,40 @@ int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const v
                cudaStream_t stream, const cf_peer_out* peers = nullptr);
 int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, const double* d_a, double alpha, double beta,
                 cudaStream_t stream, int vg, const cf_peer_out* peers = nullptr);
+int launch_mvm_sym(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, const double* d_a, double alpha, double beta,
+                   cudaStream_t stream, const cf_peer_out* peers, int part, int parts);
+bool sym_applicable(cf_gramian_s* g, const void* d_a);
+
+// peer access between all devices of a handle (single-process multi-GPU); handle memory comes from the stream-ordered pool, whose
+// blocks must be made peer-accessible explicitly.  Returns 0 when every pair can access each other, 1 otherwise.
+int enable_peers(cf_gramian_s* g) {
+    const int S = (int)g->shards.size();
+    if (S > 8) return 1;
+    for (int s = 0; s < S; s++)
+        for (int t = 0; t < S; t++) {
+            if (s == t) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, g->shards[s].ctx->dev, g->shards[t].ctx->dev) != cudaSuccess || !can) return 1;
+        }
+    for (int s = 0; s < S; s++) {
+        if (cudaSetDevice(g->shards[s].ctx->dev) != cudaSuccess) return 1;
+        for (int t = 0; t < S; t++) {
+            if (s == t) continue;
+            cudaError_t e = cudaDeviceEnablePeerAccess(g->shards[t].ctx->dev, 0);
+            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+            else if (e != cudaSuccess) { cudaGetLastError(); return 1; }
+            cudaMemPool_t pool;
+            cudaMemAccessDesc desc;
+            std::memset(&desc, 0, sizeof(desc));
+            desc.location.type = cudaMemLocationTypeDevice;
+            desc.location.id = g->shards[t].ctx->dev;
+            desc.flags = cudaMemAccessFlagsProtReadWrite;
+            if (cudaDeviceGetDefaultMemPool(&pool, g->shards[s].ctx->dev) != cudaSuccess ||
+                cudaMemPoolSetAccess(pool, &desc, 1) != cudaSuccess) { cudaGetLastError(); return 1; }
+        }
+    }
+    return 0;
+}
 
 // Multi-GPU CG, SPMD inside one process: every device holds the full iterates and updates them redundantly (identical
 // arithmetic, so identical decisions); each device computes its row block of A u and the kernel epilogue stores the block
@@ -338,30 +373,7 @@ int cg_solve_spmd(cf_gramian_s* g, double sigma2, double* x, const double* b, do
     const int64_t blk = deriv == 0 ? 1 : g->d + vg;
     const int64_t N = g->n * blk;
     if (S > 8 || !g->entry) return 1;
-    for (int s = 0; s < S; s++)
-        for (int t = 0; t < S; t++) {
-            if (s == t) continue;
-            int can = 0;
-            if (cudaDeviceCanAccessPeer(&can, g->shards[s].ctx->dev, g->shards[t].ctx->dev) != cudaSuccess || !can) return 1;
-        }
-    for (int s = 0; s < S; s++) {
-        CF_CUDA(cudaSetDevice(g->shards[s].ctx->dev));
-        for (int t = 0; t < S; t++) {
-            if (s == t) continue;
-            cudaError_t e = cudaDeviceEnablePeerAccess(g->shards[t].ctx->dev, 0);
-            if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
-            else if (e != cudaSuccess) { cudaGetLastError(); return 1; }
-            // handle memory comes from the stream-ordered pool: its blocks must be made peer-accessible explicitly
-            cudaMemPool_t pool;
-            cudaMemAccessDesc desc;
-            std::memset(&desc, 0, sizeof(desc));
-            desc.location.type = cudaMemLocationTypeDevice;
-            desc.location.id = g->shards[t].ctx->dev;
-            desc.flags = cudaMemAccessFlagsProtReadWrite;
-            if (cudaDeviceGetDefaultMemPool(&pool, g->shards[s].ctx->dev) != cudaSuccess ||
-                cudaMemPoolSetAccess(pool, &desc, 1) != cudaSuccess) { cudaGetLastError(); return 1; }
-        }
-    }
+    if (enable_peers(g)) return 1;
     if (reltol <= 0) reltol = std::sqrt(2.220446049250313e-16);
     if (maxiter <= 0) maxiter = (int)std::min<int64_t>(N, 2147483647);
     std::vector<cudaEvent_t> ev_written(S), ev_consumed(S);
@@ -382,8 +394,39 @@ int cg_solve_spmd(cf_gramian_s* g, double sigma2, double* x, const double* b, do
     g->last_launches = 0;
     int rc_all = CF_OK;
 
+    // symmetric Gramian: every device evaluates the unordered pairs of its row tiles (cyclic) into a partial vector over all n
+    // elements; then every device sums the S partial vectors with peer loads in device order (an all-reduce over NVLink without a
+    // staging copy) and adds sigma2 * in.  Bit-identical on every device and from run to run.
+    const bool use_sym = !gradient && sym_applicable(g, vec(0, 0));
+    auto apply_sym = [&](int out, int in) -> int {
+        for (int s = 0; s < S; s++) {
+            Shard& sh = g->shards[s];
+            CF_CUDA(cudaSetDevice(sh.ctx->dev));
+            if (int rc = sh.ypad.ensure((size_t)N * 8)) return rc;
+            for (int t = 0; t < S; t++)
+                if (t != s) CF_CUDA(cudaStreamWaitEvent(sh.stream, ev_consumed[t], 0)); // peers are done reading the old partial
+            int rc = launch_mvm_sym(g, sh, (double*)sh.ypad.p, nullptr, vec(s, in), 1.0, 0.0, sh.stream, nullptr, s, S);
+            if (rc) return rc == 1 ? fail(CF_ERR_INTERNAL, "symmetric variant unavailable inside the multi-device solve") : rc;
+            CF_CUDA(cudaEventRecord(ev_written[s], sh.stream));
+        }
+        cf_parts_in parts;
+        std::memset(&parts, 0, sizeof(parts));
+        parts.n = S;
+        for (int s = 0; s < S; s++) parts.ptr[s] = (const double*)g->shards[s].ypad.p;
+        for (int s = 0; s < S; s++) {
+            Shard& sh = g->shards[s];
+            CF_CUDA(cudaSetDevice(sh.ctx->dev));
+            for (int t = 0; t < S; t++)
+                if (t != s) CF_CUDA(cudaStreamWaitEvent(sh.stream, ev_written[t], 0));
+            cf_sum_parts_kernel<<<vb, 256, 0, sh.stream>>>(parts, 0, N, vec(s, out), vec(s, in), sigma2);
+            CF_CUDA(cudaGetLastError());
+            CF_CUDA(cudaEventRecord(ev_consumed[s], sh.stream));
+        }
+        return CF_OK;
+    };
     // out = sigma2 * in + K in on every device (out, in: indices into cg[])
     auto apply = [&](int out, int in) -> int {
+        if (use_sym) return apply_sym(out, in);
         for (int s = 0; s < S; s++) {
             Shard& sh = g->shards[s];
             const int64_t off = sh.r0 * blk, cnt = (sh.r1 - sh.r0) * blk;
@@ -518,9 +561,27 @@ int cg_solve_comm(cf_gramian_s* g, double sigma2, double* x, const double* b, do
         if (cudaEventElapsedTime(&ga, eb, ec) == cudaSuccess) g->cg_gather_ms += ga;
         pending = false;
     };
+    // symmetric Gramian: every rank evaluates the unordered pairs of its row tiles (cyclic) into a partial vector over all n elements
+    // (rank 0's partial also carries sigma2 v), then ONE ncclAllReduce(sum) leaves the full product on every rank
+    const bool use_sym = !gradient && sym_applicable(g, dx);
     // out = (sigma2 I + K) v on every rank: own row block in place, then the all-gather
     auto apply = [&](double* out, const double* v) -> int {
         CF_CUDA(cudaEventRecord(ea, st));
+        if (use_sym) {
+            if (cm.rank == 0) {
+                cf_axpby_kernel<<<vb, 256, 0, st>>>(out, sigma2, v, 0.0, v, N);
+                CF_CUDA(cudaGetLastError());
+            }
+            int rc = launch_mvm_sym(g, sh, out, out, v, 1.0, 1.0, st, nullptr, cm.rank, cm.world);  // beta y is added by part 0 only
+            if (rc) return rc == 1 ? fail(CF_ERR_INTERNAL, "symmetric variant unavailable inside the multi-process solve") : rc;
+            CF_CUDA(cudaEventRecord(eb, st));
+            const int nrc = cfcomm::allreduce_sum_f64(out, N, st);
+            if (nrc) return fail(CF_ERR_NCCL, "cf_cg_solve: NCCL all-reduce failed: %s", cfcomm::api().GetErrorString(nrc));
+            CF_CUDA(cudaEventRecord(ec, st));
+            pending = true;
+            g->cg_products++;
+            return CF_OK;
+        }
         if (cnt > 0) {
             const int sb = (int)std::min<int64_t>((cnt + 255) / 256, 4096);
             cf_axpby_kernel<<<sb, 256, 0, st>>>(out + off, sigma2, v + off, 0.0, v + off, cnt);
@@ -801,14 +862,19 @@ int launch_bigd_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yi
 
 // symmetric variant (gram_mvm_sym.cuh): diagonal row blocks with the plain kernel, everything beyond them once; deterministic
 // (single-writer partial sums, fixed-order combine).  Returns 1 when the variant does not apply (caller runs the plain path).
+// part / parts: this device's share of the row tiles (cyclic); with parts > 1 d_y receives the device's PARTIAL vector over all n
+// elements (see gram_sym_combine) and the caller sums the partial vectors.
 int launch_mvm_sym(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, const double* d_a, double alpha, double beta,
-                   cudaStream_t stream, const cf_peer_out* peers) {
+                   cudaStream_t stream, const cf_peer_out* peers, int part = 0, int parts = 1) {
+    cf_peer_out no_peers;
+    std::memset(&no_peers, 0, sizeof(no_peers));
+    if (!peers) peers = &no_peers;
     const int64_t n = g->n;
     const bool eqf = g->eq_fast && g->entry->sym_eq != nullptr && !env_flag("COVFN_MVM_SCALAR");
     const cf_mvm_config& cfg = eqf ? g->entry->mvm_eq_cfg : g->entry->mvm_cfg[CF_F64];
     const int64_t TR = cfg.rows_per_cta, TJ = cfg.tj;
     const int64_t T = (n + TR - 1) / TR;
-    if (sh.sym_nitems == 0 || sh.sym_tr != TR) { // build the (row tile, column chunk) list once per handle
+    if (sh.sym_nitems < 0 || sh.sym_tr != TR || sh.sym_part != part || sh.sym_parts != parts) { // build the (row tile, column chunk) list once
         int64_t ch = ((T * n / 2 / 8192) / TJ) * TJ;
         if (ch < 8 * TJ) ch = 8 * TJ;
         std::vector<cf_sym_item> items;
@@ -817,7 +883,7 @@ int launch_mvm_sym(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin,
             const int64_t first = (I + 1) * TR;
             const int64_t off = I * n - TR * (I * (I + 1) / 2);  // triangular layout, see gram_sym_combine
             int64_t c = 0;
-            for (int64_t c0 = first; c0 < n; c0 += ch, c++) {
+            for (int64_t c0 = first; c0 < n && I % parts == part; c0 += ch, c++) {
                 cf_sym_item it;
                 it.col0 = c0; it.col1 = std::min(n, c0 + ch); it.colpart_off = off + (c0 - first);
                 it.row_tile = (int32_t)I; it.chunk = (int32_t)c;
@@ -836,7 +902,7 @@ int launch_mvm_sym(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin,
         if (int rc = sh.sym_col.ensure(std::max<size_t>(16, (size_t)colpart_elems * 8))) return rc;
         if (int rc = sh.bsym.ensure(std::max<size_t>(16, (size_t)maxchunks * n * 8))) return rc;
         sh.sym_nitems = (int)items.size();
-        sh.sym_tr = TR; sh.sym_ch = ch;
+        sh.sym_tr = TR; sh.sym_ch = ch; sh.sym_part = part; sh.sym_parts = parts;
     }
     if (int rc = sh.partial.ensure((size_t)n * 8)) return rc;
     // 1. diagonal blocks: plain kernel, each CTA sweeps only its own row block, raw sums into partial[0][*]
@@ -865,10 +931,16 @@ int launch_mvm_sym(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin,
     // 3. y = alpha (diag + row partials + column partials) + beta y, fixed summation order
     const int blocks = (int)std::min<int64_t>((n + 255) / 256, 8192);
     gram_sym_combine<<<blocks, 256, 0, stream>>>((const double*)sh.partial.p, (const double*)sh.bsym.p, (const double*)sh.sym_col.p, n, TR,
-                                                 sh.sym_ch, d_y, d_yin, alpha * g->coef, beta, *peers);
+                                                 sh.sym_ch, d_y, d_yin, alpha * g->coef, beta, *peers, part, parts);
     CF_CUDA(cudaGetLastError());
     g->last_launches += 3;
     return CF_OK;
+}
+
+// does the symmetric variant apply to a full-vector product of this handle (whatever row range it is restricted to)?
+bool sym_applicable(cf_gramian_s* g, const void* d_a) {
+    return g->opt_symmetric && g->symmetric && g->dtype == CF_F64 && g->entry && g->n >= 32768 && (((uintptr_t)d_a) % 16) == 0 &&
+           !(g->kind == CF_ATOM_SOP && cfjit::wanted((double)g->n * (double)g->m));
 }
 
 // one column of  y <- alpha K a + beta y  on one shard; device pointers; asynchronous on sh.stream
@@ -983,8 +1055,7 @@ int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const v
     if (!g->entry) return launch_bigd_mvm(g, sh, (double*)d_y, (const double*)d_yin, (const double*)d_a, alpha, beta, stream);
     const cf_mvm_config& cfg = g->entry->mvm_cfg[dt];
     // y === x: every unordered pair once (gram_mvm_sym.cuh, deterministic); on by default, CF_OPT_SYMMETRIC / COVFN_SYMMETRIC=0 turn it off
-    if (g->opt_symmetric && g->symmetric && dt == CF_F64 && sh.r0 == 0 && sh.r1 == g->n && g->n >= 32768 &&
-        (((uintptr_t)d_a) % 16) == 0 && !(g->kind == CF_ATOM_SOP && cfjit::wanted((double)nrows * (double)g->m))) {
+    if (sh.r0 == 0 && sh.r1 == g->n && sym_applicable(g, d_a)) {
         const int rc = launch_mvm_sym(g, sh, (double*)d_y, (const double*)d_yin, (const double*)d_a, alpha, beta, stream, peers);
         if (rc != 1) return rc;
     }
@@ -1519,8 +1590,107 @@ static int mul_host_impl(cf_gramian_t g, void* y, int64_t ldy, const void* x, in
     return CF_OK;
 }
 
+// single-process multi-GPU, symmetric Gramian, one right-hand side, full row range: every device evaluates the unordered pairs of
+// its row tiles into a partial vector, device 0 sums the partial vectors with peer loads in device order.  Returns 1 if the variant
+// does not apply (the caller runs the row-block path).
+static int mul_host_sym_spmd(cf_gramian_t g, double* y, const double* x, double alpha, double beta) {
+    const int S = (int)g->shards.size();
+    const int64_t n = g->n;
+    if (S < 2 || g->row_begin != 0 || g->row_end != n || !g->entry) return 1;
+    for (auto& sh : g->shards) {
+        CF_CUDA(cudaSetDevice(sh.ctx->dev));
+        if (int rc = sh.a.ensure((size_t)n * 8)) return rc;
+        if (int rc = sh.ypad.ensure((size_t)n * 8)) return rc;
+    }
+    if (!sym_applicable(g, g->shards[0].a.p) || enable_peers(g)) return 1;
+    Shard& s0 = g->shards[0];
+    CF_CUDA(cudaSetDevice(s0.ctx->dev));
+    if (int rc = s0.y.ensure((size_t)n * 8)) return rc;
+    if (beta != 0.0) CF_CUDA(cudaMemcpyAsync(s0.y.p, y, n * 8, cudaMemcpyHostToDevice, s0.stream));
+    g->last_launches = 0;
+    for (int s = 0; s < S; s++) {
+        Shard& sh = g->shards[s];
+        CF_CUDA(cudaSetDevice(sh.ctx->dev));
+        CF_CUDA(cudaMemcpyAsync(sh.a.p, x, n * 8, cudaMemcpyHostToDevice, sh.stream));
+        CF_CUDA(cudaEventRecord(sh.ev0, sh.stream));
+        int rc = launch_mvm_sym(g, sh, (double*)sh.ypad.p, (const double*)s0.y.p, (const double*)sh.a.p, alpha, s == 0 ? beta : 0.0, sh.stream,
+                                nullptr, s, S);
+        if (rc) return rc;
+        CF_CUDA(cudaEventRecord(sh.ev1, sh.stream));
+    }
+    cf_parts_in parts;
+    std::memset(&parts, 0, sizeof(parts));
+    parts.n = S;
+    for (int s = 0; s < S; s++) parts.ptr[s] = (const double*)g->shards[s].ypad.p;
+    CF_CUDA(cudaSetDevice(s0.ctx->dev));
+    for (int s = 1; s < S; s++) CF_CUDA(cudaStreamWaitEvent(s0.stream, g->shards[s].ev1, 0));
+    cf_sum_parts_kernel<<<(int)std::min<int64_t>((n + 255) / 256, 4096), 256, 0, s0.stream>>>(parts, 0, n, (double*)s0.y.p, nullptr, 0.0);
+    CF_CUDA(cudaGetLastError());
+    CF_CUDA(cudaMemcpyAsync(y, s0.y.p, n * 8, cudaMemcpyDeviceToHost, s0.stream));
+    float worst = 0;
+    for (auto& sh : g->shards) {
+        CF_CUDA(cudaSetDevice(sh.ctx->dev));
+        CF_CUDA(cudaStreamSynchronize(sh.stream));
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, sh.ev0, sh.ev1) == cudaSuccess) worst = std::max(worst, ms);
+    }
+    g->last_ms = worst;
+    return CF_OK;
+}
+
 int cf_gramian_mul(cf_gramian_t g, void* y, int64_t ldy, const void* x, int64_t ldx, int64_t nrhs, double alpha, double beta) {
+    if (g && nrhs == 1 && y && x && g->shards.size() > 1 && g->dtype == CF_F64) {
+        std::unique_lock<std::mutex> lk(g->mu);
+        const int rc = mul_host_sym_spmd(g, (double*)y, (const double*)x, alpha, beta);
+        if (rc != 1) return rc;
+    }
     return mul_host_impl(g, y, ldy, x, ldx, nrhs, alpha, beta, 0);
+}
+
+// y_full <- alpha K x + beta y_full computed COLLECTIVELY by the ranks of the communicator (cf_comm_init): every rank passes the
+// same x and receives the complete y (the form chained products need).  Symmetric Float64 Gramians: unordered pairs of the rank's
+// row tiles (cyclic), then ncclAllReduce(sum); otherwise the rank's row block, then the in-place all-gather.
+int cf_gramian_mul_collective_device(cf_gramian_t g, void* d_y_full, const void* d_x, double alpha, double beta, void* stream) {
+    if (int rc = check_handle(g)) return rc;
+    if (!cfcomm::active()) return fail(CF_ERR_NCCL, "cf_gramian_mul_collective_device: no communicator (cf_comm_init)");
+    if (g->shards.size() != 1) return fail(CF_ERR_UNSUPPORTED, "cf_gramian_mul_collective_device: needs a single-device handle");
+    if (!d_y_full || !d_x) return fail(CF_ERR_BAD_ARGUMENT, "NULL device pointer");
+    cfcomm::Comm& cm = cfcomm::comm();
+    int64_t r0, r1;
+    cfcomm::row_block(g->n, cm.rank, cm.world, &r0, &r1);
+    std::lock_guard<std::mutex> lk(g->mu);
+    if (g->row_begin != r0 || g->row_end != r1)
+        return fail(CF_ERR_DIMENSION, "cf_gramian_mul_collective_device: rank %d must own rows [%lld, %lld)", cm.rank, (long long)r0, (long long)r1);
+    Shard& sh = g->shards[0];
+    CF_CUDA(cudaSetDevice(sh.ctx->dev));
+    cudaStream_t st = stream ? (cudaStream_t)stream : sh.stream;
+    const size_t es = esize(g->dtype);
+    g->last_launches = 0;
+    CF_CUDA(cudaEventRecord(sh.ev0, st));
+    bool done = false;
+    if (g->dtype == CF_F64 && sym_applicable(g, d_x)) {
+        const int rc = launch_mvm_sym(g, sh, (double*)d_y_full, (const double*)d_y_full, (const double*)d_x, alpha, beta, st, nullptr, cm.rank, cm.world);
+        if (rc != 0 && rc != 1) return rc;
+        if (rc == 0) {
+            CF_CUDA(cudaEventRecord(sh.ev1, st));
+            const int nrc = cfcomm::allreduce_sum_f64((double*)d_y_full, g->n, st);
+            if (nrc) return fail(CF_ERR_NCCL, "NCCL all-reduce failed: %s", cfcomm::api().GetErrorString(nrc));
+            done = true;
+        }
+    }
+    if (!done) {
+        void* yb = (char*)d_y_full + (size_t)r0 * es;
+        if (int rc = launch_mvm(g, sh, yb, yb, d_x, alpha, beta, st)) return rc;
+        CF_CUDA(cudaEventRecord(sh.ev1, st));
+        const int nrc = cfcomm::allgather_rows(d_y_full, g->n, 1, es, st);
+        if (nrc) return fail(CF_ERR_NCCL, "NCCL all-gather failed: %s", cfcomm::api().GetErrorString(nrc));
+    }
+    if (!stream) {
+        CF_CUDA(cudaStreamSynchronize(st));
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, sh.ev0, sh.ev1) == cudaSuccess) g->last_ms = ms;
+    }
+    return CF_OK;
 }
 int cf_gradient_mul(cf_gramian_t g, void* y, int64_t ldy, const void* x, int64_t ldx, int64_t nrhs, double alpha, double beta) {
     return mul_host_impl(g, y, ldy, x, ldx, nrhs, alpha, beta, 1);

@@ -20,7 +20,7 @@ namespace cfcomm {
 
 typedef struct { char internal[128]; } ncclUniqueId;  // NCCL_UNIQUE_ID_BYTES = 128 (nccl.h)
 typedef void* ncclComm_t;
-enum { ncclSuccess = 0, ncclUint8 = 1 };
+enum { ncclSuccess = 0, ncclUint8 = 1, ncclFloat64 = 8, ncclSum = 0 };
 
 struct Api {
     void* lib = nullptr;
@@ -29,6 +29,7 @@ struct Api {
     int (*CommDestroy)(ncclComm_t) = nullptr;
     int (*Broadcast)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    int (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     int (*GroupStart)() = nullptr;
     int (*GroupEnd)() = nullptr;
     const char* (*GetErrorString)(int) = nullptr;
@@ -53,6 +54,7 @@ inline Api& api() {
         *(void**)&a.CommDestroy = sym("ncclCommDestroy");
         *(void**)&a.Broadcast = sym("ncclBroadcast");
         *(void**)&a.AllGather = sym("ncclAllGather");
+        *(void**)&a.AllReduce = sym("ncclAllReduce");
         *(void**)&a.GroupStart = sym("ncclGroupStart");
         *(void**)&a.GroupEnd = sym("ncclGroupEnd");
         *(void**)&a.GetErrorString = sym("ncclGetErrorString");
@@ -96,6 +98,11 @@ inline int allgather_rows(void* d_full, int64_t n, int64_t blk, size_t es, cudaS
         if (rc) { a.GroupEnd(); return rc; }
     }
     return a.GroupEnd();
+}
+
+// In-place sum of a Float64 device vector over the ranks (the symmetric variant's partial vectors): ncclAllReduce(sum)
+inline int allreduce_sum_f64(double* d_v, int64_t count, cudaStream_t stream) {
+    return api().AllReduce(d_v, d_v, (size_t)count, ncclFloat64, ncclSum, comm().comm, stream);
 }
 
 }  // namespace cfcomm

@@ -270,21 +270,45 @@ __global__ void __launch_bounds__(NT, MINB) gram_mvm_sym_kernel(const __grid_con
 // tr = rows per tile, ch = columns per chunk; element o belongs to row tile I = o / tr, which has ceil((n - (I+1) tr) / ch) chunks,
 // and receives column partials from the tiles I' < I (triangular layout: colpart[I'] starts at I' n - tr I' (I' + 1) / 2 and holds
 // the columns >= (I' + 1) tr).
+// Several devices (part of parts): a device owns the row tiles I with I % parts == part and produces a PARTIAL vector over all n
+// elements -- the diagonal block and the row partials of its own tiles, the column partials its tiles contribute everywhere; the
+// partial vectors are then summed across devices (ncclAllReduce, or peer loads in fixed device order: cf_sum_parts_kernel).  beta y
+// is added by part 0 only.
 static __global__ void gram_sym_combine(const double* __restrict__ diag, const double* __restrict__ rowpart, const double* __restrict__ colpart,
                                         int64_t n, int64_t tr, int64_t ch, double* __restrict__ y, const double* __restrict__ yin, double alpha,
-                                        double beta, const cf_peer_out peers) {
+                                        double beta, const cf_peer_out peers, int part, int parts) {
     for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x) {
         const int64_t I = o / tr;
-        double s = diag[o];
-        const int64_t beyond = n - (I + 1) * tr;
-        const int64_t nch = beyond > 0 ? (beyond + ch - 1) / ch : 0;
-        for (int64_t c = 0; c < nch; c++) s += rowpart[c * n + o];
+        double s = 0.0;
+        if (I % parts == part) {
+            s = diag[o];
+            const int64_t beyond = n - (I + 1) * tr;
+            const int64_t nch = beyond > 0 ? (beyond + ch - 1) / ch : 0;
+            for (int64_t c = 0; c < nch; c++) s += rowpart[c * n + o];
+        }
         double cs = 0.0;
-        for (int64_t Ip = 0; Ip < I; Ip++) cs += colpart[Ip * n - tr * (Ip * (Ip + 1) / 2) + (o - (Ip + 1) * tr)];
+        for (int64_t Ip = part; Ip < I; Ip += parts) cs += colpart[Ip * n - tr * (Ip * (Ip + 1) / 2) + (o - (Ip + 1) * tr)];
         double v = alpha * (s + cs);
-        if (beta != 0.0) v += beta * yin[o];
+        if (beta != 0.0 && part == 0) v += beta * yin[o];
         y[o] = v;
         for (int p = 0; p < peers.n; p++) static_cast<double*>(peers.ptr[p])[o] = v;
+    }
+}
+
+// out[o] = sum_q parts[q][o] (+ addend[o] * scale), fixed order q = 0, 1, ...: the cross-device sum of the symmetric variant's partial
+// vectors by peer loads (single-process multi-GPU); every device runs it on the elements [o0, o1) it needs
+struct cf_parts_in {
+    int32_t n;
+    int32_t pad_;
+    const double* ptr[8];
+};
+static __global__ void cf_sum_parts_kernel(const cf_parts_in in, int64_t o0, int64_t o1, double* __restrict__ out, const double* __restrict__ addend,
+                                           double scale) {
+    for (int64_t o = o0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < o1; o += (int64_t)gridDim.x * blockDim.x) {
+        double s = in.ptr[0][o];
+        for (int q = 1; q < in.n; q++) s += in.ptr[q][o];
+        if (addend) s += scale * addend[o];
+        out[o] = s;
     }
 }
 

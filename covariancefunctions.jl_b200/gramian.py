@@ -192,6 +192,12 @@ class Gramian:
                  C.c_void_p(stream) if stream else None))
 
 
+def mul_collective_device(G, y_full_ptr: int, x_ptr: int, alpha=1.0, beta=0.0, stream: int = 0):
+    """cf_gramian_mul_collective_device: the complete product on every rank of the library's communicator (distributed.comm_init_from_torch)"""
+    check(lib().cf_gramian_mul_collective_device(G.handle(), C.c_void_p(y_full_ptr), C.c_void_p(x_ptr), float(alpha), float(beta),
+                                                  C.c_void_p(stream) if stream else None))
+
+
 def gramian(k, x, y=None):
     """gramian(k, x[, y]) (src/gramian.jl:144-159).  GradientKernel -> lazy block Gramian (src/gramian.jl:120-123)."""
     if not isinstance(k, (AbstractKernel, GradientKernel)):

@@ -121,11 +121,11 @@ int cf_gramian_size(cf_gramian_t g, int64_t* n, int64_t* m, int* d, int* dtype);
 int cf_gramian_set_row_range(cf_gramian_t g, int64_t row_begin, int64_t row_end);
 
 /*
- * Options.  CF_OPT_SYMMETRIC (default 0, or the environment variable COVFN_SYMMETRIC at create time): for y === x,
- * Float64, nrhs == 1, n >= 65536 and the full row range, evaluate every unordered pair {i, j} once and use it for
- * both b_i and b_j.  Halves the kernel evaluations of a symmetric Gramian MVM; the column half is accumulated with
- * floating-point atomics, so results match the default path to rounding but are not bit-reproducible run to run.
- * The reference always evaluates all n*m entries (src/gramian.jl:78-87).
+ * Options.  CF_OPT_SYMMETRIC (default 1; the environment variable COVFN_SYMMETRIC=0 at create time turns it off): for y === x,
+ * Float64, nrhs == 1 and n >= 32768, evaluate every unordered pair {i, j} once and use it for both b_i and b_j (csrc/
+ * gram_mvm_sym.cuh).  Halves the kernel evaluations of a symmetric Gramian MVM.  Every partial sum has a single writer and the
+ * partials are combined in a fixed order, so the result is bit-reproducible; it differs from the all-pairs path by summation
+ * order only (<= 1e-13).  The reference always evaluates all n*m entries (src/gramian.jl:78-87); set the option to 0 for that.
  */
 #define CF_OPT_SYMMETRIC 1
 int cf_gramian_set_option(cf_gramian_t g, int option, int value);
@@ -208,6 +208,10 @@ int cf_comm_unique_id(void* id128, int bytes);
 int cf_comm_init(const void* id128, int rank, int world);
 int cf_comm_destroy(void);
 int cf_comm_info(int* rank, int* world, int* nccl_version);
+/* y_full <- alpha K x + beta y_full computed collectively by all ranks (same x on every rank, complete y on every rank; device
+ * pointers, one right-hand side).  Symmetric Float64 Gramians: each rank evaluates the unordered pairs of its row tiles, then
+ * ncclAllReduce(sum); otherwise the rank's row block followed by the in-place all-gather. */
+int cf_gramian_mul_collective_device(cf_gramian_t g, void* d_y_full, const void* d_x, double alpha, double beta, void* stream);
 /* in-place all-gather of a device vector of n blocks of `block` elements whose rank-r part is rows [n r / world, n (r+1) / world) */
 int cf_comm_allgather_rows(void* d_full, int64_t n, int64_t block, int dtype, void* stream);
 

@@ -106,3 +106,54 @@ def test_runtime_specialised_and_tensor_core_kernels_on_two_devices(cf, O, two_g
     assert relerr(b, O.mul_vec(k.program(), X, a)) < 1e-12
     assert relerr(B, O.mul_mat(k.program(), X, A)) < 1e-12
     assert relerr(b3, O.mul_vec(k.program(), X3, a)) < 1e-12
+
+
+def test_symmetric_variant_over_two_devices(cf, O, two_gpus):
+    """y === x on several devices of one process: every device evaluates the unordered pairs of its row tiles, the partial vectors
+    are summed with peer loads in device order (csrc/capi.cu mul_host_sym_spmd); bit-reproducible."""
+    rng = np.random.default_rng(44)
+    n, d = 70001, 3
+    X = rng.standard_normal((n, d))
+    a = rng.standard_normal(n)
+    for k in (cf.EQ(), cf.MaternP(2)):
+        G = cf.gramian(k, X.T.copy())
+        b = G @ a
+        assert np.array_equal(b, G @ a)
+        for rows in ((0, 50), (n // 2 - 25, n // 2 + 25), (n - 50, n)):
+            assert relerr(b[rows[0]:rows[1]], O.mul_vec(k.program(), X, a, rows=rows)) < 1e-12
+        y0 = rng.standard_normal(n)
+        y = y0.copy()
+        cf.mul_(y, G, a, -0.5, 2.0)
+        assert relerr(y, -0.5 * b + 2.0 * y0) < 1e-13
+        G.set_symmetric(False)
+        assert relerr(G @ a, b) < 1e-13
+
+
+def test_cg_spmd_symmetric_matches_plain(cf, two_gpus):
+    rng = np.random.default_rng(45)
+    n, d = 40000, 8
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    y = rng.standard_normal(n)
+    sols = {}
+    for symm in (True, False):
+        G = cf.gramian(cf.MaternP(2), X.T.copy())
+        G.set_symmetric(symm)
+        x, it, res = (1e-2 * cf.I(n) + G).solve(y, reltol=1e-300, maxiter=5)
+        true_res = float(np.linalg.norm(y - (G @ x) - 1e-2 * x))
+        assert it == 5 and abs(true_res - res) < 1e-8 * res
+        sols[symm] = x
+    assert relerr(sols[True], sols[False]) < 1e-8
+
+
+def test_multi_process_comm_mode(cf):
+    """one process per GPU under torchrun, the library's own NCCL communicator: bench_aux/comm_check.py"""
+    import os
+    import subprocess
+    import sys
+
+    if cf.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    run = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29533", os.path.join(root, "bench_aux", "comm_check.py")], capture_output=True, text=True, timeout=600)
+    assert run.returncode == 0 and "COMM_CHECK_OK" in run.stdout, run.stdout[-2000:] + run.stderr[-4000:]

@@ -115,6 +115,10 @@ struct Buf {
     size_t cap = 0;
     int ensure(size_t bytes) {
         if (bytes <= cap) return CF_OK;
+        // growing a scratch buffer returns the old block to the pool: nothing -- on the library's streams or on a caller's stream of an
+        // asynchronous *_mul_device call -- may still be using it.  Growth only happens on the first calls of a handle, so a
+        // device-wide synchronisation here is cheap and makes the free safe on any stream.
+        if (p) cudaDeviceSynchronize();
         dev_free(p);
         p = nullptr;
         cap = 0;
@@ -164,6 +168,7 @@ struct cf_gramian_s {
     bool opt_symmetric = true;  // use the symmetric variant (each unordered pair evaluated once) when applicable
     float last_ms = 0;
     int last_launches = 0;
+    void* user_stream = nullptr;  // stream of the last asynchronous *_mul_device call (one in-flight user stream per handle)
     // timing of the last cf_cg_solve (cf_cg_timing): host wall clock of the whole solve, device time of the operator products and
     // of the NCCL row-block gathers (multi-process mode), number of operator products
     double cg_total_ms = 0, cg_mvm_ms = 0, cg_gather_ms = 0;
@@ -1279,6 +1284,9 @@ int destroy_impl(cf_gramian_s* g) {
     for (auto& sh : g->shards) {
         if (sh.ctx) cudaSetDevice(sh.ctx->dev);
         if (sh.stream) cudaStreamSynchronize(sh.stream); // nothing of this handle may still be running when its memory returns to the pool
+        if (g->user_stream) {  // ... including work queued on the caller's stream by the last asynchronous *_mul_device call
+            if (cudaStreamSynchronize((cudaStream_t)g->user_stream) != cudaSuccess) cudaGetLastError();  // (the caller may have destroyed it)
+        }
         if (sh.Y && sh.Y != sh.X) dev_free(sh.Y);
         dev_free(sh.X);
         if (sh.yn && sh.yn != sh.xn) dev_free(sh.yn);
@@ -1444,14 +1452,22 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
         // coincident points would become 1e-8 in k, so programs with that atom always keep direct differences.
         // LINE atoms use x.y, which the tensor-core chain reproduces exactly.
         // (atoms are bounded by 1, so the sum of the atoms' slopes bounds the slope of any product of them)
-        double slope = 0.0;
+        // A product of powers prod_f atom_f^p_f (atoms bounded by 1) has slope <= sum_f p_f slope_f; the program's slope is bounded by
+        // the largest such sum over its terms, weighted by the coefficients' share.
         bool sqrt_atom = false;
+        std::vector<double> aslope(g->prog.natoms, 0.0);
         for (int i = 0; i < g->prog.natoms; i++) {
             const cf_atom& A = g->prog.atoms[i];
-            if (A.v.kind == CF_ATOM_EQ) slope += std::fabs(A.v.e.c);
+            if (A.v.kind == CF_ATOM_EQ) aslope[i] = std::fabs(A.v.e.c);
             else if (A.v.kind == CF_ATOM_MATERN && A.v.p == 0) sqrt_atom = true;
-            else if (A.v.kind == CF_ATOM_MATERN) slope += std::fabs(A.tay[1]) * A.inv_l2;
-            else if (A.v.kind == CF_ATOM_RQ_INT || A.v.kind == CF_ATOM_RQ_REAL) slope += A.v.alpha * A.v.w;
+            else if (A.v.kind == CF_ATOM_MATERN) aslope[i] = std::fabs(A.tay[1]) * A.inv_l2;
+            else if (A.v.kind == CF_ATOM_RQ_INT || A.v.kind == CF_ATOM_RQ_REAL) aslope[i] = A.v.alpha * A.v.w;
+        }
+        double slope = 0.0;
+        for (int t = 0; t < g->prog.nterms; t++) {
+            double ts = 0.0;
+            for (int f = 0; f < g->prog.terms[t].nfac; f++) ts += g->prog.terms[t].fac[f].power * aslope[g->prog.terms[t].fac[f].atom];
+            slope = std::max(slope, ts);
         }
         // accumulation factor: the random-walk value sqrt(d + 2).  The worst case (d + 2) is sqrt(d + 2) <= 5.9 times larger for
         // d <= 32, i.e. still below 6e-13 (Float64) / 6e-5 relative error of a kernel entry when this check passes at 1e-13 / 1e-5,
@@ -1719,6 +1735,7 @@ static int mul_device_impl(cf_gramian_t g, void* d_y, int64_t ldy, const void* d
     Shard& sh = g->shards[0];
     CF_CUDA(cudaSetDevice(sh.ctx->dev));
     cudaStream_t st = stream ? (cudaStream_t)stream : sh.stream;
+    if (stream) g->user_stream = stream;
     const size_t es = esize(g->dtype);
     g->last_launches = 0;
     CF_CUDA(cudaEventRecord(sh.ev0, st));

@@ -130,6 +130,30 @@ inline void fill_matern(cf_atom& A, int p, long double l) {
     }
 }
 
+// combine terms with the same multiset of factors: (a + b)^3 has 4 distinct terms, not 8 (a Julia Sum / Power is evaluated as
+// written, reference src/algebra.jl:40,62; the expansion is ours, so is the duty to keep it small)
+inline void merge_like_terms(std::vector<HTerm>& terms) {
+    auto canon = [](HTerm& t) {
+        for (size_t i = 1; i < t.fac.size(); i++)
+            for (size_t j = i; j > 0 && t.fac[j - 1].atom > t.fac[j].atom; j--) std::swap(t.fac[j - 1], t.fac[j]);
+    };
+    auto same = [](const HTerm& a, const HTerm& b) {
+        if (a.fac.size() != b.fac.size()) return false;
+        for (size_t i = 0; i < a.fac.size(); i++)
+            if (a.fac[i].atom != b.fac[i].atom || a.fac[i].power != b.fac[i].power) return false;
+        return true;
+    };
+    std::vector<HTerm> out;
+    for (auto& t : terms) {
+        canon(t);
+        bool merged = false;
+        for (auto& o : out)
+            if (same(o, t)) { o.coef += t.coef; merged = true; break; }
+        if (!merged) out.push_back(t);
+    }
+    terms.swap(out);
+}
+
 inline cf_atom zero_atom() {
     cf_atom A;
     std::memset(&A, 0, sizeof(A));
@@ -202,6 +226,11 @@ inline cf_program lower(const cf_knode_t* prog, int nnodes, std::vector<double>*
                 break;
             }
             case CF_OP_LENGTHSCALE:
+                // Lengthscale(Constant(c), l) is valid in the reference (Constant <: IsotropicKernel, src/stationary.jl:15): c(r2 / l^2) = c
+                if (!st.empty() && st.back().is_const) {
+                    if (!(nd.fparam > 0) || !std::isfinite(nd.fparam)) throw LowerError{CF_ERR_DOMAIN, "Lengthscale: l is non-positive"};
+                    break;
+                }
                 throw LowerError{CF_ERR_UNSUPPORTED, "Lengthscale must wrap an isotropic base kernel"};
             case CF_OP_DOT: {
                 cf_atom A = zero_atom();
@@ -257,6 +286,7 @@ inline cf_program lower(const cf_knode_t* prog, int nnodes, std::vector<double>*
                                 }
                                 prod.push_back(tt);
                             }
+                        merge_like_terms(prod);
                         out.terms.swap(prod);
                         if ((int)out.terms.size() > CF_MAX_TERMS) throw LowerError{CF_ERR_UNSUPPORTED, "kernel expands to too many terms"};
                     }
@@ -332,6 +362,7 @@ inline cf_program lower(const cf_knode_t* prog, int nnodes, std::vector<double>*
                                 }
                                 prod.push_back(tt);
                             }
+                        merge_like_terms(prod);
                         out.terms.swap(prod);
                         if ((int)out.terms.size() > CF_MAX_TERMS) throw LowerError{CF_ERR_UNSUPPORTED, "kernel expands to too many terms"};
                     }

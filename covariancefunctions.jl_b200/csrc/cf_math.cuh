@@ -359,7 +359,10 @@ __device__ __forceinline__ void cf_atom_jet(double r2, const cf_atom& A, cf_tbl_
             for (int i = p - 2; i >= 0; i--) a = fma(a, g, A.matA[i]);
             for (int i = p - 3; i >= 0; i--) b = fma(b, g, A.matB[i]);
             if (A.am1 != 0.0 || A.bm[0] != 0.0 || A.bm[1] != 0.0 || A.bm[2] != 0.0) { // p <= 1: singular terms
-                double gi = 1.0 / g;
+                // coincident points (r2 == 0 exactly, p = 0: Exp has no Taylor branch): the reference differentiates exp(-sqrt(r2)) at 0
+                // with ForwardDiff and gets k' = -Inf, so that its block -2 (k' a + 2 k'' r (r.a)) is NaN (Inf * 0); 1 / 0 = Inf here
+                // reproduces that instead of the large finite value the clamped square root would give
+                double gi = (r2 == 0.0) ? __longlong_as_double(0x7ff0000000000000LL) : 1.0 / g;
                 a = fma(A.am1, gi, a);
                 b += gi * (A.bm[0] + gi * (A.bm[1] + gi * A.bm[2]));
             }

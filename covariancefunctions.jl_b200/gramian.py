@@ -50,7 +50,9 @@ class Gramian:
             self.y = x if self._symmetric else y
         else:
             self.x = _points(x)
-            self.y = self.x if self._symmetric else _points(y, self.x.dtype)
+            self.y = self.x if self._symmetric else _points(y)
+            if self.y.dtype != self.x.dtype:  # promote_type(eltype(x), eltype(y)) (src/gramian.jl:30-33): Float32 with Float64 is Float64
+                self.x, self.y = self.x.astype(np.float64), self.y.astype(np.float64)
         if self.x.shape[1] != self.y.shape[1]:
             raise DimensionMismatch(
                 f"inputs have to have the same length: {self.x.shape[1]}, {self.y.shape[1]}")  # src/util.jl:41
@@ -162,12 +164,16 @@ class Gramian:
         a = np.asarray(a)
         r0, r1 = self.row_range
         rows = (r1 - r0) * self.block
+        # T = promote_type(eltype(G), eltype(a)) (src/gramian.jl:67,72).  The device computes in the Gramian's eltype: a Float64 vector
+        # against a Float32 Gramian is multiplied in Float32 and the result returned as Float64 (the reference evaluates the entries
+        # in Float32 too and only accumulates in Float64 -- a summation-order-class difference, inside the Float32 tolerance)
         dt = np.promote_types(self.dtype, a.dtype) if a.dtype.kind == "f" else self.dtype
         if a.ndim == 1:
-            b = np.zeros(rows, dtype=dt)
+            b = np.zeros(rows, dtype=self.dtype)
         else:
-            b = np.zeros((rows, a.shape[1]), dtype=dt, order="F")
-        return mul_(b, self, a)
+            b = np.zeros((rows, a.shape[1]), dtype=self.dtype, order="F")
+        b = mul_(b, self, a)
+        return b if dt == self.dtype else b.astype(dt)
 
     __mul__ = __matmul__
 
@@ -198,10 +204,12 @@ def mul_collective_device(G, y_full_ptr: int, x_ptr: int, alpha=1.0, beta=0.0, s
                                                   C.c_void_p(stream) if stream else None))
 
 
-def gramian(k, x, y=None):
+def gramian(k, x=None, y=None):
     """gramian(k, x[, y]) (src/gramian.jl:144-159).  GradientKernel -> lazy block Gramian (src/gramian.jl:120-123)."""
     if not isinstance(k, (AbstractKernel, GradientKernel)):
-        # gramian(x, y) = Gramian(Dot(), x, y) (src/gramian.jl:23,150-151)
+        # gramian(x, y) = Gramian(Dot(), x, y), gramian(x) = gramian(x, x) (src/gramian.jl:23,150-151)
+        if x is None:
+            return Gramian(Dot(), k)
         return Gramian(Dot(), k, x)
     return Gramian(k, x, y)
 
@@ -301,7 +309,9 @@ class LazyMatrixSum:
             y[...] = 0
         else:
             y *= beta
-        y += alpha * self.D.sigma2 * x
+        r0, r1 = self.G.row_range  # a row-restricted Gramian (multi-process sharding) owns rows [r0, r1) of the sum as well
+        b = self.G.block
+        y += alpha * self.D.sigma2 * x[r0 * b:r1 * b]
         return mul_(y, self.G, x, alpha, 1)
 
     def __matmul__(self, x):

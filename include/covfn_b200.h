@@ -141,7 +141,9 @@ int cf_gramian_set_option(cf_gramian_t g, int option, int value);
 int cf_gramian_mul(cf_gramian_t g, void* y, int64_t ldy, const void* x, int64_t ldx, int64_t nrhs,
                    double alpha, double beta);
 /* Same contract with DEVICE pointers on the handle's (first) device; asynchronous on `stream`
- * (a cudaStream_t passed as void*, NULL = the library's own stream, then the call blocks). */
+ * (a cudaStream_t passed as void*, NULL = the library's own stream, then the call blocks).  A handle supports ONE in-flight
+ * caller stream: its scratch buffers are shared between calls, and cf_gramian_destroy waits for the stream of the last
+ * asynchronous call before the memory returns to the pool. */
 int cf_gramian_mul_device(cf_gramian_t g, void* d_y, int64_t ldy, const void* d_x, int64_t ldx,
                           int64_t nrhs, double alpha, double beta, void* stream);
 

@@ -55,9 +55,21 @@ def test_gradient_symmetric_diagonal_blocks(cf, O):
     n, d = 90, 5
     X = rng.standard_normal((n, d)) / np.sqrt(d)
     a = rng.standard_normal(n * d)
-    for k in (cf.EQ(), cf.MaternP(2), cf.MaternP(3), cf.RQ(2)):
+    for k in (cf.EQ(), cf.MaternP(1), cf.MaternP(2), cf.MaternP(3), cf.RQ(2)):
         G = cf.gramian(cf.GradientKernel(k), X.T.copy())
         assert relerr(G @ a, O.gradient_mul(k.program(), X, a)) < 1e-12, repr(k)
+    # Exp = MaternP(0) is not differentiable at r = 0 and has no Taylor branch (taylor_bound = eps^(1/0) = 0, src/stationary.jl:137):
+    # the reference's ForwardDiff derivatives at r2 = 0 are -Inf / Inf and its diagonal blocks -2 (k' a + 2 k'' r (r.a)) are NaN
+    # (Inf * 0, src/gradient.jl:86-92) -- so the whole product is NaN.  Same here and in the oracle; off the diagonal it is finite.
+    for k in (cf.Exp(), cf.MaternP(0)):
+        G = cf.gramian(cf.GradientKernel(k), X.T.copy())
+        ref = O.gradient_mul(k.program(), X, a)
+        got = G @ a
+        assert np.all(np.isnan(ref)) and np.all(np.isnan(got)), repr(k)
+        Y = rng.standard_normal((70, d)) / np.sqrt(d)
+        ay = rng.standard_normal(70 * d)
+        Gxy = cf.gramian(cf.GradientKernel(k), X.T.copy(), Y.T.copy())
+        assert relerr(Gxy @ ay, O.gradient_mul(k.program(), X, ay, Y=Y)) < 1e-12, repr(k)
 
 
 def test_gradient_config4_shape(cf, O):

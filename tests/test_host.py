@@ -214,3 +214,32 @@ def test_program_limits_are_reported_not_truncated():
         cf.jit_check(too_many_atoms, 3, "mvm")
     ok = cf.jit_check((cf.EQ() + cf.RQ(2)) ** 2 + 0.5, 3, "mvm")  # 4 terms, 2 atoms: fine
     assert isinstance(ok, str)
+
+
+def test_lowering_merges_like_terms_and_lengthscaled_constants(cf):
+    """(a + b)^3 expands to 4 distinct terms, (a + b)^4 to 5 (within the 8-term device limit); Lengthscale(Constant(c), l) is the
+    constant (Constant <: IsotropicKernel, reference src/stationary.jl:15, src/transformation.jl:6-19).  Checked through cf_jit_check,
+    which lowers the program without a GPU."""
+    k4 = (cf.EQ() + cf.MaternP(2)) ** 4
+    try:
+        cf.jit_check(k4, 3, "mvm")  # lowering succeeds (16 raw terms merge into 5); NVRTC availability is a separate matter
+    except cf.UnsupportedKernel as e:
+        assert "NVRTC" in str(e) or "nvrtc" in str(e), e
+    k5 = (cf.EQ() + cf.MaternP(2) + cf.RQ(2)) ** 4  # 15 distinct terms: beyond the device program
+    with pytest.raises(cf.UnsupportedKernel):
+        cf.jit_check(k5, 3, "mvm")
+    kc = cf.Lengthscale(cf.Constant(2.0), 0.5) * cf.EQ()
+    try:
+        cf.jit_check(kc + cf.RQ(2), 3, "mvm")
+    except cf.UnsupportedKernel as e:
+        assert "NVRTC" in str(e) or "nvrtc" in str(e), e
+
+
+def test_host_api_promotion_rules(cf):
+    """gramian eltype = promote_type over x and y (src/gramian.jl:30-33); gramian(x) is the Dot Gramian (src/gramian.jl:151)"""
+    x32 = np.ones((3, 5), dtype=np.float32)
+    y64 = np.ones((3, 4), dtype=np.float64)
+    assert cf.gramian(cf.EQ(), x32, y64).eltype == np.float64
+    assert cf.gramian(cf.EQ(), x32).eltype == np.float32
+    G = cf.gramian(x32)
+    assert isinstance(G.k, cf.Dot) and G.shape == (5, 5)

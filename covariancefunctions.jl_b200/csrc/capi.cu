@@ -137,7 +137,8 @@ struct Shard {
     void* Y = nullptr;  // m x D (== X when symmetric)
     void* xn = nullptr;  // squared norms of the padded points (multi-RHS kernel)
     void* yn = nullptr;
-    Buf a, y, partial, apad, ypad, at, cg[6], sym_items, bsym, sym_col, bd_t, bd_s, xp, yp, ap;
+    Buf a, y, partial, apad, ypad, at, cg[6], sym_items, bsym, sym_col, bd_t, bd_s, xp, yp, ap, yc_hi, yc_lo, yc_n, ac_hi, ac_lo;
+    bool tc5_ready = false; // yc_* hold the canonical column-point images of the tcgen05 multi-RHS kernel
     bool mmd_ready = false; // xp / yp hold the padded point copies of the DMMA multi-RHS kernel
     int sym_nitems = -1;    // symmetric variant: work items (-1: not built), row tile, chunk length and device share they were built for
     int64_t sym_tr = 0, sym_ch = 0;
@@ -278,6 +279,47 @@ int launch_mm(cf_gramian_s* g, Shard& sh, void* d_B, int64_t ldb, const void* d_
     const bool dmma = g->dtype == CF_F64 && g->use_norms && g->entry->mm_dmma != nullptr && !env_flag("COVFN_MM_SCALAR");
     // Float32, well-scaled points, d >= 8: tensor cores in 3xTF32 split precision (gram_mm_tf32.cuh)
     const bool tf32 = g->dtype == CF_F32 && g->use_norms && g->entry->mm_tf32 != nullptr && !env_flag("COVFN_MM_SCALAR");
+    // ... on the 5th-generation tensor cores (tcgen05 / TMEM, gram_mm_tc5.cuh); COVFN_MM_LEGACY=1 keeps the mma.sync kernel
+    if (tf32 && g->entry->mm_tc5 != nullptr && !env_flag("COVFN_MM_LEGACY")) {
+        const int dk = g->entry->mm_tc5_dk;
+        const int64_t ntiles = (g->m + CF_MMU_TJ - 1) / CF_MMU_TJ, mpad = ntiles * CF_MMU_TJ;
+        if (!sh.tc5_ready) {
+            if (int rc = sh.yc_hi.ensure((size_t)mpad * dk * 4)) return rc;
+            if (int rc = sh.yc_lo.ensure((size_t)mpad * dk * 4)) return rc;
+            if (int rc = sh.yc_n.ensure((size_t)mpad * 4)) return rc;
+            cf_canon_points_kernel<<<148 * 8, 256, 0, stream>>>((const float*)sh.Y, g->D, dk, g->m, mpad, (float*)sh.yc_hi.p, (float*)sh.yc_lo.p,
+                                                                (const float*)sh.yn, (float*)sh.yc_n.p);
+            CF_CUDA(cudaGetLastError());
+            sh.tc5_ready = true;
+        }
+        if (int rc = sh.ac_hi.ensure((size_t)mpad * CF_MMU_PC * 4)) return rc;
+        if (int rc = sh.ac_lo.ensure((size_t)mpad * CF_MMU_PC * 4)) return rc;
+        cf_mmu_params PP;
+        std::memset(&PP, 0, sizeof(PP));
+        cf_mm_params& Q = PP.mm;
+        Q.X = sh.X; Q.xn = sh.xn; Q.sop = g->sop_val;
+        Q.row0 = sh.r0; Q.nrows = nrows; Q.m = g->m; Q.ldb = ldb; Q.alpha = alpha; Q.beta = beta; Q.use_norms = 1;
+        PP.yhi = (const float*)sh.yc_hi.p; PP.ylo = (const float*)sh.yc_lo.p; PP.ynpad = (const float*)sh.yc_n.p;
+        PP.ahi = (const float*)sh.ac_hi.p; PP.alo = (const float*)sh.ac_lo.p; PP.ntiles = ntiles;
+        const int row_tiles5 = (int)((nrows + CF_MMU_TI - 1) / CF_MMU_TI);
+        cfjit::Kernel* jit5 = nullptr;  // large products: the same kernel source with the program structure compiled in (cf_jit.h)
+        if (cfjit::wanted((double)nrows * (double)g->m))
+            jit5 = cfjit::get_kernel(g->sop_val, "gram_mm_tc5.cuh", "gram_mm_tc5_kernel<" + std::to_string(g->D) + ">");
+        for (int64_t c0 = 0; c0 < nrhs; c0 += CF_MMU_PC) {
+            Q.nrhs = (int)std::min<int64_t>(CF_MMU_PC, nrhs - c0);
+            cf_canon_rhs_kernel<<<148 * 8, 256, 0, stream>>>((const float*)d_A + c0 * lda, lda, g->m, mpad, Q.nrhs, (float*)sh.ac_hi.p, (float*)sh.ac_lo.p);
+            CF_CUDA(cudaGetLastError());
+            Q.B = (char*)d_B + c0 * ldb * es;
+            bool launched = false;
+            if (jit5) {
+                launched = cfjit::launch(jit5, &PP, (unsigned)row_tiles5, 1, CF_MMU_THREADS, (unsigned)g->entry->mm_tc5_smem, stream) == 0;
+                if (!launched) jit5 = nullptr;
+            }
+            if (!launched) CF_CUDA(g->entry->mm_tc5(PP, row_tiles5, stream));
+            g->last_launches += 2;
+        }
+        return CF_OK;
+    }
     const int ldat = dmma ? CF_MMD_SA : (tf32 ? CF_MMT_SA : CF_MM_PC);
     if (int rc = sh.at.ensure((size_t)g->m * ldat * es)) return rc;
     cf_mm_params P;
@@ -1292,7 +1334,7 @@ int destroy_impl(cf_gramian_s* g) {
         if (sh.yn && sh.yn != sh.xn) dev_free(sh.yn);
         dev_free(sh.xn);
         sh.a.release(); sh.y.release(); sh.partial.release(); sh.apad.release(); sh.ypad.release(); sh.at.release(); sh.sym_items.release(); sh.bsym.release(); sh.sym_col.release(); sh.bd_t.release(); sh.bd_s.release();
-        sh.xp.release(); sh.yp.release(); sh.ap.release();
+        sh.xp.release(); sh.yp.release(); sh.ap.release(); sh.yc_hi.release(); sh.yc_lo.release(); sh.yc_n.release(); sh.ac_hi.release(); sh.ac_lo.release();
         for (auto& b : sh.cg) b.release();
         if (sh.ev0) cudaEventDestroy(sh.ev0);
         if (sh.ev1) cudaEventDestroy(sh.ev1);
@@ -1956,10 +1998,11 @@ int cf_jit_check(const cf_knode_t* prog, int nnodes, int d, int which, char* log
             break;
         case 1: header = "gram_mm_dmma.cuh"; name = "gram_mm_dmma_kernel<" + sD + ">"; break;
         case 2: header = "gram_mvm_dmma.cuh"; name = "gram_mvm_dmma_kernel<" + sD + ", " + sop + ">"; break;
-        case 3: header = "gram_mm_tf32.cuh"; name = "gram_mm_tf32_kernel<" + sD + ">"; break;
+        case 3: header = "gram_mm_tc5.cuh"; name = "gram_mm_tc5_kernel<" + sD + ">"; break;
+        case 6: header = "gram_mm_tf32.cuh"; name = "gram_mm_tf32_kernel<" + sD + ">"; break;
         case 4: header = "gram_mvm_tf32.cuh"; name = "gram_mvm_tf32_kernel<" + sD + ", " + sop + ">"; break;
         case 5: header = "grad_mvm_dmma.cuh"; name = "grad_mvm_dmma_kernel<" + sD + ", " + sop + ", false, 0>"; break;
-        default: return fail(CF_ERR_BAD_ARGUMENT, "cf_jit_check: which must be 0..5");
+        default: return fail(CF_ERR_BAD_ARGUMENT, "cf_jit_check: which must be 0..6");
     }
     cf_sop_grad sop_grad;
     const bool want_grad = which == 5;

@@ -51,6 +51,9 @@ const cf_kernel_entry entry = {
     cf_mmt_entry<D>::smem,
     {cf_mvt_entry<D>::fn[0], cf_mvt_entry<D>::fn[1], cf_mvt_entry<D>::fn[2], cf_mvt_entry<D>::fn[3]},
     cf_mvt_entry<D>::cfg,
+    cf_mmu_entry<D>::fn,
+    cf_mmu_entry<D>::dk,
+    cf_mmu_entry<D>::smem,
     cf_mvme_entry<D>::fn,
     cf_mvme_entry<D>::cfg,
     {TU::R, TU::NT, TU::TJ, TU::NS, TU::MINB},

@@ -10,6 +10,7 @@
 #include "gram_mm_tf32.cuh"
 #include "gram_mvm_tf32.cuh"
 #include "gram_mvm_eq.cuh"
+#include "gram_mm_tc5.cuh"
 
 #define CF_NKINDS 4 /* EQ, MATERN, RQ_INT, SOP */
 inline int cf_kind_slot(int kind) {
@@ -44,6 +45,9 @@ struct cf_kernel_entry {
     int mm_tf32_smem;        // its dynamic shared memory (run-time specialised launches)
     cf_mvm_launch_fn mvm_tf32[CF_NKINDS]; // Float32 value MVM with the distance GEMM in 3xTF32 (gram_mvm_tf32.cuh), nullptr for D < 8
     cf_mvm_config mvm_tf32_cfg;
+    cf_mmu_launch_fn mm_tc5;  // Float32 multi-RHS on tcgen05 / TMEM in 3xTF32 (gram_mm_tc5.cuh), nullptr for D < 8
+    int mm_tc5_dk;            // k extent of its distance GEMM (D rounded up to 8)
+    int mm_tc5_smem;          // its dynamic shared memory (run-time specialised launches)
     cf_mvm_launch_fn mvm_eq;  // Float64 EQ value MVM with the exponent formed in the scaled domain (gram_mvm_eq.cuh), nullptr for D > 6
     cf_mvm_config mvm_eq_cfg;
     int tune[5];                     // R, NT, TJ, NS, MINB of the value MVM kernel (names the instantiation for cf_jit.h)

@@ -1,0 +1,338 @@
+// gram_mm_tc5.cuh -- K4u: Float32 multi-RHS product  B <- alpha K A + beta B  on the 5th-generation tensor cores
+// (tcgen05.mma kind::tf32, accumulators in tensor memory), 3xTF32 split precision.
+//
+// Replaces mul!(B::AbstractMatrix, G::Gramian{Float32}, A::AbstractMatrix, alpha, beta) (reference src/gramian.jl:89-99) for
+// well-scaled points of dimension d >= 8, like gram_mm_tf32.cuh, whose legacy mma.sync fragments it supersedes: there the warps
+// that evaluate the kernel also load fragments and issue ~1700 mma.sync per tile; here ONE thread issues 36 asynchronous MMAs per
+// 128 x 64 tile, operands are read by the tensor core straight from shared memory, accumulators never touch the register file,
+// and the eight evaluation warps do nothing but the kernel program.
+//
+//   per row tile of 128 rows (one CTA), per column tile of TJ = 64 points:
+//   phase A (tensor core)  Dot (128 x 64) = Xhi Yhi^T + Xlo Yhi^T + Xhi Ylo^T          12 MMAs M128 N64 K8 -> TMEM dot[t & 1]
+//   evaluation (8 warps)   tcgen05.ld Dot -> r2 = |x|^2 + |y|^2 - 2 dot -> k (program interpreter, 8 entries at a time)
+//                          -> K tile hi / lo to shared memory (canonical K-major layout)
+//   phase B (tensor core)  Out (128 x 64) = Khi Ahi + Klo Ahi + Khi Alo                   24 MMAs M128 N64 K8 -> TMEM out
+//   accumulate (8 warps)   tcgen05.ld Out -> running sums in registers with round-to-nearest adds (the tensor core truncates when it
+//                          adds to its accumulator, so a tile starts from zero: see gram_mm_tf32.cuh)
+// hi = the raw fp32 word (the tensor core reads only the TF32 bits, i.e. truncates), lo = v - trunc(v): the dropped lo.lo term
+// is 2^-22 relative.  The column-side operands arrive by TMA bulk copies from per-handle / per-call images that are ALREADY in the
+// tensor core's canonical shared-memory layout (cf_canon_* kernels below), so a stage is five 1-D copies and no thread touches it.
+//
+// Warp roles: warps 0-7 evaluate (warp w owns TMEM lanes 32 (w % 4) .. +31, i.e. tile rows, and columns 32 (w / 4) .. +31), warp 8
+// is the TMA producer, warp 9 issues the MMAs.  mbarriers: full / empty per stage (TMA <-> MMA), dotfull / dotfree per TMEM dot buffer,
+// kfull (K tile written), outfull (phase B done: Out readable, K tile and stage free), outfree.
+#pragma once
+#include "gram_mm_tf32.cuh"
+
+#define CF_MMU_TI 128
+#define CF_MMU_TJ 64
+#define CF_MMU_PC 64
+#define CF_MMU_NS 2
+#define CF_MMU_THREADS 320
+
+// element (r, k) of an R x K tile of 4-byte values in the K-major canonical layout without swizzle (core matrix = 8 rows x 16 bytes,
+// core matrices of one K chunk contiguous): LBO (next K chunk) = R / 8 * 128 bytes, SBO (next 8 rows) = 128 bytes
+__host__ __device__ constexpr int cf_canon(int r, int k, int R) { return ((k >> 2) * (R >> 3) + (r >> 3)) * 32 + (r & 7) * 4 + (k & 3); }
+
+template <int D>
+struct cf_mmu_layout {
+    static constexpr int dk = ((D + 7) / 8) * 8;
+    static constexpr int x_bytes = CF_MMU_TI * dk * 4;            // each of hi, lo
+    static constexpr int y_bytes = CF_MMU_TJ * dk * 4;            // each of hi, lo
+    static constexpr int a_bytes = CF_MMU_PC * CF_MMU_TJ * 4;     // each of hi, lo
+    static constexpr int n_bytes = CF_MMU_TJ * 4;
+    static constexpr int k_bytes = CF_MMU_TI * CF_MMU_TJ * 4;     // each of hi, lo
+    static constexpr int stage_bytes = 2 * y_bytes + 2 * a_bytes + ((n_bytes + 127) / 128) * 128;
+    static constexpr int bar_bytes = 256;
+    static constexpr int total = bar_bytes + 2 * x_bytes + 2 * k_bytes + CF_MMU_NS * stage_bytes + 1024;  // + alignment slack
+};
+
+// ---- one-off images in the canonical layout ------------------------------------------------------------------------------------
+// column points: per tile of TJ points an image [TJ x dk] of hi words and one of lo words (zero beyond m and beyond D)
+static __global__ void cf_canon_points_kernel(const float* __restrict__ Y, int D, int dk, int64_t m, int64_t mpad, float* __restrict__ hi,
+                                              float* __restrict__ lo, const float* __restrict__ yn, float* __restrict__ ynpad) {
+    const int64_t total = mpad * dk;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t j = q / dk;
+        const int k = (int)(q - j * dk);
+        const float v = (j < m && k < D) ? Y[j * D + k] : 0.f;
+        const int64_t dst = (j / CF_MMU_TJ) * (CF_MMU_TJ * dk) + cf_canon((int)(j % CF_MMU_TJ), k, CF_MMU_TJ);
+        hi[dst] = v;
+        lo[dst] = __uint_as_float(cf_tf32_lo(v));
+        if (k == 0) ynpad[j] = (j < m) ? yn[j] : 0.f;
+    }
+}
+// right-hand sides: per tile of TJ points an image [PC x TJ] (row = rhs column c, K index = point) of hi and lo words
+static __global__ void cf_canon_rhs_kernel(const float* __restrict__ A, int64_t lda, int64_t m, int64_t mpad, int nrhs, float* __restrict__ hi,
+                                           float* __restrict__ lo) {
+    const int64_t total = mpad * CF_MMU_PC;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total; q += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(q / mpad);
+        const int64_t j = q - (int64_t)c * mpad;  // consecutive threads: consecutive points of one column (coalesced reads)
+        const float v = (j < m && c < nrhs) ? A[j + lda * c] : 0.f;
+        const int64_t dst = (j / CF_MMU_TJ) * (CF_MMU_PC * CF_MMU_TJ) + cf_canon(c, (int)(j % CF_MMU_TJ), CF_MMU_PC);
+        hi[dst] = v;
+        lo[dst] = __uint_as_float(cf_tf32_lo(v));
+    }
+}
+
+struct cf_mmu_params {
+    cf_mm_params mm;       // X (rows as uploaded, stride D), xn, B, ldb, row0, nrows, m, nrhs, alpha, beta, sop
+    const float* yhi;      // canonical column-point images
+    const float* ylo;
+    const float* ynpad;    // squared norms of the columns, zero padded to a multiple of TJ
+    const float* ahi;      // canonical right-hand-side images
+    const float* alo;
+    int64_t ntiles;        // column tiles
+};
+
+// ---- tcgen05 / TMEM wrappers ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint64_t cf_umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    return (uint64_t)((saddr >> 4) & 0x3fff) | ((uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16) | ((uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32) |
+           ((uint64_t)1 << 46);  // version 1 (sm_100), no swizzle, base offset 0
+}
+// D[tmem] (+)= A[smem] B[smem]^T, M = 128, K = 8, kind::tf32, fp32 accumulate; issued by ONE thread
+__device__ __forceinline__ void cf_umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void cf_umma_commit(uint64_t* bar) {  // arrives on bar when every MMA issued so far has completed
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(cf_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cf_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {  // 32 consecutive columns of this thread's TMEM lane
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                   "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+                   "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+                   "=r"(v[31])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cf_mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cf_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void cf_tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void cf_tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void cf_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <int D>
+__global__ void __launch_bounds__(CF_MMU_THREADS, 1) gram_mm_tc5_kernel(const __grid_constant__ cf_mmu_params PP) {
+    using S = cf_mmu_layout<D>;
+    constexpr int DK = S::dk, TI = CF_MMU_TI, TJ = CF_MMU_TJ, PC = CF_MMU_PC, NS = CF_MMU_NS;
+    const cf_mm_params& P = PP.mm;
+    extern __shared__ unsigned char smem_raw[];
+    unsigned char* smem = smem_raw + ((1024u - (cf_smem_u32(smem_raw) & 1023u)) & 1023u);  // 1 KB alignment inside the shared window
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+    uint64_t *full = bars, *empty = bars + NS, *dotfull = bars + 2 * NS, *dotfree = dotfull + 2, *kfull = dotfree + 2, *outfull = kfull + 1,
+             *outfree = outfull + 1;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
+    float* Xhi = reinterpret_cast<float*>(smem + S::bar_bytes);
+    float* Xlo = Xhi + TI * DK;
+    float* Khi = Xlo + TI * DK;
+    float* Klo = Khi + TI * TJ;
+    unsigned char* stages = reinterpret_cast<unsigned char*>(Klo + TI * TJ);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int ntiles = (int)PP.ntiles;
+
+    if (tid == 0) {
+        for (int s = 0; s < NS; s++) { cf_mbar_init(&full[s], 1); cf_mbar_init(&empty[s], 1); }
+        for (int b = 0; b < 2; b++) { cf_mbar_init(&dotfull[b], 1); cf_mbar_init(&dotfree[b], 256); }
+        cf_mbar_init(kfull, 256); cf_mbar_init(outfull, 1); cf_mbar_init(outfree, 256);
+        cf_fence_barrier_init();
+    }
+    if (warp == 9) {  // 256 TMEM columns: dot[0], dot[1] (64 each), out (64)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(cf_smem_u32(tmem_slot)));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    const int64_t rbase = P.row0 + (int64_t)blockIdx.x * TI;
+    const int64_t rend = P.row0 + P.nrows;
+    // the row tile's points, hi / lo, canonical layout (rows past the end: clamped, never stored)
+    const float* __restrict__ Xg = static_cast<const float*>(P.X);
+    for (int q = tid; q < TI * (DK / 4); q += CF_MMU_THREADS) {
+        const int row = q % TI, kc = q / TI;
+        int64_t ir = rbase + row;
+        if (ir >= rend) ir = rend - 1;
+        float4 h, l;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) v[e] = (4 * kc + e < D) ? Xg[ir * D + 4 * kc + e] : 0.f;
+        h = make_float4(v[0], v[1], v[2], v[3]);
+        l = make_float4(__uint_as_float(cf_tf32_lo(v[0])), __uint_as_float(cf_tf32_lo(v[1])), __uint_as_float(cf_tf32_lo(v[2])),
+                        __uint_as_float(cf_tf32_lo(v[3])));
+        *reinterpret_cast<float4*>(&Xhi[cf_canon(row, 4 * kc, TI)]) = h;
+        *reinterpret_cast<float4*>(&Xlo[cf_canon(row, 4 * kc, TI)]) = l;
+    }
+    cf_fence_async_smem();
+    cf_tc_fence_before();
+    __syncthreads();
+    cf_tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tm_dot[2] = {tmem, tmem + 64}, tm_out = tmem + 128;
+
+    if (warp == 8) {
+        // ---- TMA producer ------------------------------------------------------------------------------------------------------
+        if (lane == 0) {
+            for (int t = 0; t < ntiles; t++) {
+                const int s = t % NS;
+                if (t >= NS) cf_mbar_wait(&empty[s], (uint32_t)(((t / NS) - 1) & 1));
+                unsigned char* st = stages + (size_t)s * S::stage_bytes;
+                cf_mbar_expect_tx(&full[s], (uint32_t)(2 * S::y_bytes + 2 * S::a_bytes + S::n_bytes));
+                cf_tma_load_1d(st, PP.yhi + (int64_t)t * TJ * DK, (uint32_t)S::y_bytes, &full[s]);
+                cf_tma_load_1d(st + S::y_bytes, PP.ylo + (int64_t)t * TJ * DK, (uint32_t)S::y_bytes, &full[s]);
+                cf_tma_load_1d(st + 2 * S::y_bytes, PP.ahi + (int64_t)t * PC * TJ, (uint32_t)S::a_bytes, &full[s]);
+                cf_tma_load_1d(st + 2 * S::y_bytes + S::a_bytes, PP.alo + (int64_t)t * PC * TJ, (uint32_t)S::a_bytes, &full[s]);
+                cf_tma_load_1d(st + 2 * S::y_bytes + 2 * S::a_bytes, PP.ynpad + (int64_t)t * TJ, (uint32_t)S::n_bytes, &full[s]);
+            }
+        }
+    } else if (warp == 9) {
+        // ---- MMA issuer: A(0), then for every tile t: A(t + 1) early, B(t) as soon as its K tile is written -------------------------------
+        if (lane == 0) {
+            // instruction descriptor: D fp32, A / B tf32, both K-major, N = 64, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+            constexpr uint32_t LBO_X = (TI / 8) * 128, LBO_Y = (TJ / 8) * 128, LBO_K = (TI / 8) * 128, LBO_A = (PC / 8) * 128;
+            const uint32_t xhi = cf_smem_u32(Xhi), xlo = cf_smem_u32(Xlo), khi = cf_smem_u32(Khi), klo = cf_smem_u32(Klo);
+            auto phase_a = [&](int t) {
+                const int s = t % NS;
+                cf_mbar_wait(&full[s], (uint32_t)((t / NS) & 1));
+                if (t >= 2) cf_mbar_wait(&dotfree[t & 1], (uint32_t)(((t >> 1) - 1) & 1));
+                cf_tc_fence_after();
+                const uint32_t yhi = cf_smem_u32(stages + (size_t)s * S::stage_bytes), ylo = yhi + S::y_bytes;
+                uint32_t acc = 0;
+                for (int pr = 0; pr < 3; pr++) {  // small terms first: lo.hi, hi.lo, hi.hi
+                    const uint32_t xa = pr == 0 ? xlo : xhi, yb = pr == 1 ? ylo : yhi;
+#pragma unroll
+                    for (int ks = 0; ks < DK / 8; ks++) {
+                        cf_umma_tf32(tm_dot[t & 1], cf_umma_desc(xa + ks * 2 * LBO_X, LBO_X, 128), cf_umma_desc(yb + ks * 2 * LBO_Y, LBO_Y, 128), idesc, acc);
+                        acc = 1;
+                    }
+                }
+                cf_umma_commit(&dotfull[t & 1]);
+            };
+            phase_a(0);
+            for (int t = 0; t < ntiles; t++) {
+                if (t + 1 < ntiles) phase_a(t + 1);
+                const int s = t % NS;
+                cf_mbar_wait(kfull, (uint32_t)(t & 1));                       // K tile t written by the evaluation warps
+                if (t >= 1) cf_mbar_wait(outfree, (uint32_t)((t - 1) & 1));   // Out of tile t - 1 read
+                cf_tc_fence_after();
+                const uint32_t ahi = cf_smem_u32(stages + (size_t)s * S::stage_bytes + 2 * S::y_bytes), alo = ahi + S::a_bytes;
+                uint32_t acc = 0;
+                for (int pr = 0; pr < 3; pr++) {
+                    const uint32_t ka = pr == 0 ? klo : khi, ab = pr == 1 ? alo : ahi;
+#pragma unroll
+                    for (int ks = 0; ks < TJ / 8; ks++) {
+                        cf_umma_tf32(tm_out, cf_umma_desc(ka + ks * 2 * LBO_K, LBO_K, 128), cf_umma_desc(ab + ks * 2 * LBO_A, LBO_A, 128), idesc, acc);
+                        acc = 1;
+                    }
+                }
+                cf_umma_commit(outfull);     // Out readable, K tile free
+                cf_umma_commit(&empty[s]);   // stage s free for the producer
+            }
+        }
+    } else {
+        // ---- evaluation warps ----------------------------------------------------------------------------------------------------------
+        const int q4 = warp & 3, ch = warp >> 2;         // TMEM lane quarter (tile rows 32 q4 ..), column half (32 ch ..)
+        const int row = 32 * q4 + lane;
+        int64_t ir = rbase + row;
+        if (ir >= rend) ir = rend - 1;
+        const float xnorm = static_cast<const float*>(P.xn)[ir];
+        const uint32_t lane_base = (uint32_t)(32 * q4) << 16;
+        float acc[32];
+#pragma unroll
+        for (int c = 0; c < 32; c++) acc[c] = 0.f;
+        auto drain_out = [&](int t) {  // Out of tile t -> running sums
+            cf_mbar_wait(outfull, (uint32_t)(t & 1));
+            cf_tc_fence_after();
+            uint32_t o[32];
+            cf_tmem_ld32(tm_out + lane_base + 32 * ch, o);
+            cf_tc_fence_before();
+            cf_mbar_arrive(outfree);
+#pragma unroll
+            for (int c = 0; c < 32; c++) acc[c] += __uint_as_float(o[c]);
+        };
+        for (int t = 0; t < ntiles; t++) {
+            const int s = t % NS;
+            cf_mbar_wait(&dotfull[t & 1], (uint32_t)((t >> 1) & 1));
+            cf_tc_fence_after();
+            uint32_t dv[32];
+            cf_tmem_ld32(tm_dot[t & 1] + lane_base + 32 * ch, dv);
+            cf_tc_fence_before();
+            cf_mbar_arrive(&dotfree[t & 1]);
+            // the stage of tile t is still resident (freed only when phase B of tile t completes): |y|^2 of this warp's 32 columns
+            const float* yns = reinterpret_cast<const float*>(stages + (size_t)s * S::stage_bytes + 2 * S::y_bytes + 2 * S::a_bytes) + 32 * ch;
+            float kv[32];
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                float r2[8], dt[8], k8[8];
+#pragma unroll
+                for (int u = 0; u < 8; u++) {
+                    dt[u] = __uint_as_float(dv[8 * g + u]);
+                    r2[u] = fmaxf(fmaf(-2.f, dt[u], xnorm + yns[8 * g + u]), 0.f);
+                }
+                cf_sop_value_f32_n<8>(r2, dt, P.sop, k8);
+#pragma unroll
+                for (int u = 0; u < 8; u++) kv[8 * g + u] = k8[u];
+            }
+            if (t >= 1) drain_out(t - 1);  // phase B of tile t - 1 is complete: its Out is added, and the K tile may be overwritten
+            // K tile t, hi / lo, canonical layout (row = tile row, K index = tile column): 16-byte stores, conflict-free across a warp
+#pragma unroll
+            for (int g = 0; g < 8; g++) {
+                const int col = 32 * ch + 4 * g;
+                const float4 h = make_float4(kv[4 * g], kv[4 * g + 1], kv[4 * g + 2], kv[4 * g + 3]);
+                const float4 l = make_float4(__uint_as_float(cf_tf32_lo(h.x)), __uint_as_float(cf_tf32_lo(h.y)), __uint_as_float(cf_tf32_lo(h.z)),
+                                             __uint_as_float(cf_tf32_lo(h.w)));
+                *reinterpret_cast<float4*>(&Khi[cf_canon(row, col, TI)]) = h;
+                *reinterpret_cast<float4*>(&Klo[cf_canon(row, col, TI)]) = l;
+            }
+            cf_fence_async_smem();  // generic-proxy stores -> visible to the tensor core's (async-proxy) reads
+            cf_mbar_arrive(kfull);
+        }
+        if (ntiles > 0) drain_out(ntiles - 1);
+        float* Bg = static_cast<float*>(P.B);
+        const int64_t i = rbase + row;
+        if (i < rend) {
+#pragma unroll
+            for (int c = 0; c < 32; c++) {
+                const int col = 32 * ch + c;
+                if (col < P.nrhs) {
+                    float* o = Bg + (i - P.row0) + P.ldb * col;
+                    double v = P.alpha * (double)acc[c];
+                    if (P.beta != 0.0) v += P.beta * (double)(*o);
+                    *o = (float)v;
+                }
+            }
+        }
+    }
+    cf_tc_fence_before();
+    __syncthreads();
+    if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
+}
+
+#ifndef __CUDACC_RTC__
+typedef cudaError_t (*cf_mmu_launch_fn)(const cf_mmu_params& P, int row_tiles, cudaStream_t stream);
+template <int D>
+cudaError_t cf_mmu_launch(const cf_mmu_params& P, int row_tiles, cudaStream_t stream) {
+    using S = cf_mmu_layout<D>;
+    auto kern = gram_mm_tc5_kernel<D>;
+    static bool configured[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (!configured[dev & 63]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, S::total);
+        if (e != cudaSuccess) return e;
+        configured[dev & 63] = true;
+    }
+    kern<<<row_tiles, CF_MMU_THREADS, S::total, stream>>>(P);
+    return cudaGetLastError();
+}
+template <int D, bool OK = (D >= 8)>
+struct cf_mmu_entry {
+    static constexpr cf_mmu_launch_fn fn = nullptr;
+    static constexpr int dk = 0, smem = 0;
+};
+template <int D>
+struct cf_mmu_entry<D, true> {
+    static constexpr cf_mmu_launch_fn fn = &cf_mmu_launch<D>;
+    static constexpr int dk = cf_mmu_layout<D>::dk, smem = cf_mmu_layout<D>::total;
+};
+#endif

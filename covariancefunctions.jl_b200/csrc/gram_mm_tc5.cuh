@@ -10,7 +10,7 @@
 //   per row tile of 128 rows (one CTA), per column tile of TJ = 64 points:
 //   phase A (tensor core)  Dot (128 x 64) = Xhi Yhi^T + Xlo Yhi^T + Xhi Ylo^T          12 MMAs M128 N64 K8 -> TMEM dot[t & 1]
 //   evaluation (8 warps)   tcgen05.ld Dot -> r2 = |x|^2 + |y|^2 - 2 dot -> k (program interpreter, 8 entries at a time)
-//                          -> K tile hi / lo to shared memory (canonical K-major layout)
+//                          -> K tile hi / lo written to TENSOR MEMORY (tcgen05.st): phase B takes its A operand from TMEM
 //   phase B (tensor core)  Out (128 x 64) = Khi Ahi + Klo Ahi + Khi Alo                   24 MMAs M128 N64 K8 -> TMEM out
 //   accumulate (8 warps)   tcgen05.ld Out -> running sums in registers with round-to-nearest adds (the tensor core truncates when it
 //                          adds to its accumulator, so a tile starts from zero: see gram_mm_tf32.cuh)
@@ -27,7 +27,7 @@
 #define CF_MMU_TI 128
 #define CF_MMU_TJ 64
 #define CF_MMU_PC 64
-#define CF_MMU_NS 2
+#define CF_MMU_NS 3
 #define CF_MMU_THREADS 320
 
 // element (r, k) of an R x K tile of 4-byte values in the K-major canonical layout without swizzle (core matrix = 8 rows x 16 bytes,
@@ -44,7 +44,7 @@ struct cf_mmu_layout {
     static constexpr int k_bytes = CF_MMU_TI * CF_MMU_TJ * 4;     // each of hi, lo
     static constexpr int stage_bytes = 2 * y_bytes + 2 * a_bytes + ((n_bytes + 127) / 128) * 128;
     static constexpr int bar_bytes = 256;
-    static constexpr int total = bar_bytes + 2 * x_bytes + 2 * k_bytes + CF_MMU_NS * stage_bytes + 1024;  // + alignment slack
+    static constexpr int total = bar_bytes + 2 * x_bytes + CF_MMU_NS * stage_bytes + 1024;  // + alignment slack (the K tile lives in TMEM)
 };
 
 // ---- one-off images in the canonical layout ------------------------------------------------------------------------------------
@@ -96,6 +96,18 @@ __device__ __forceinline__ void cf_umma_tf32(uint32_t tmem_d, uint64_t da, uint6
     asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
                  ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
+// the same with the A operand in tensor memory (128 lanes x 8 columns of 32-bit words at tmem_a)
+__device__ __forceinline__ void cf_umma_tf32_ta(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+                 ::"r"(tmem_d), "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void cf_tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {  // 32 consecutive columns of this thread's TMEM lane
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+                   "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]),
+                   "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+                 : "memory");
+}
 __device__ __forceinline__ void cf_umma_commit(uint64_t* bar) {  // arrives on bar when every MMA issued so far has completed
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(cf_smem_u32(bar)) : "memory");
 }
@@ -128,20 +140,18 @@ __global__ void __launch_bounds__(CF_MMU_THREADS, 1) gram_mm_tc5_kernel(const __
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
     float* Xhi = reinterpret_cast<float*>(smem + S::bar_bytes);
     float* Xlo = Xhi + TI * DK;
-    float* Khi = Xlo + TI * DK;
-    float* Klo = Khi + TI * TJ;
-    unsigned char* stages = reinterpret_cast<unsigned char*>(Klo + TI * TJ);
+    unsigned char* stages = reinterpret_cast<unsigned char*>(Xlo + TI * DK);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int ntiles = (int)PP.ntiles;
 
     if (tid == 0) {
         for (int s = 0; s < NS; s++) { cf_mbar_init(&full[s], 1); cf_mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; b++) { cf_mbar_init(&dotfull[b], 1); cf_mbar_init(&dotfree[b], 256); }
-        cf_mbar_init(kfull, 256); cf_mbar_init(outfull, 1); cf_mbar_init(outfree, 256);
+        for (int b = 0; b < 2; b++) { cf_mbar_init(&dotfull[b], 1); cf_mbar_init(&dotfree[b], 8); }  // one arrival per evaluation warp
+        cf_mbar_init(kfull, 8); cf_mbar_init(outfull, 1); cf_mbar_init(outfree, 8);
         cf_fence_barrier_init();
     }
-    if (warp == 9) {  // 256 TMEM columns: dot[0], dot[1] (64 each), out (64)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(cf_smem_u32(tmem_slot)));
+    if (warp == 9) {  // 512 TMEM columns: dot[0], dot[1], out, K hi, K lo (64 each)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(cf_smem_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     const int64_t rbase = P.row0 + (int64_t)blockIdx.x * TI;
@@ -167,7 +177,7 @@ __global__ void __launch_bounds__(CF_MMU_THREADS, 1) gram_mm_tc5_kernel(const __
     __syncthreads();
     cf_tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tm_dot[2] = {tmem, tmem + 64}, tm_out = tmem + 128;
+    const uint32_t tm_dot[2] = {tmem, tmem + 64}, tm_out = tmem + 128, tm_khi = tmem + 192, tm_klo = tmem + 256;
 
     if (warp == 8) {
         // ---- TMA producer ------------------------------------------------------------------------------------------------------
@@ -189,8 +199,8 @@ __global__ void __launch_bounds__(CF_MMU_THREADS, 1) gram_mm_tc5_kernel(const __
         if (lane == 0) {
             // instruction descriptor: D fp32, A / B tf32, both K-major, N = 64, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-            constexpr uint32_t LBO_X = (TI / 8) * 128, LBO_Y = (TJ / 8) * 128, LBO_K = (TI / 8) * 128, LBO_A = (PC / 8) * 128;
-            const uint32_t xhi = cf_smem_u32(Xhi), xlo = cf_smem_u32(Xlo), khi = cf_smem_u32(Khi), klo = cf_smem_u32(Klo);
+            constexpr uint32_t LBO_X = (TI / 8) * 128, LBO_Y = (TJ / 8) * 128, LBO_A = (PC / 8) * 128;
+            const uint32_t xhi = cf_smem_u32(Xhi), xlo = cf_smem_u32(Xlo);
             auto phase_a = [&](int t) {
                 const int s = t % NS;
                 cf_mbar_wait(&full[s], (uint32_t)((t / NS) & 1));
@@ -208,25 +218,28 @@ __global__ void __launch_bounds__(CF_MMU_THREADS, 1) gram_mm_tc5_kernel(const __
                 }
                 cf_umma_commit(&dotfull[t & 1]);
             };
+            // the distance GEMM runs TWO tiles ahead of the evaluation (two TMEM dot buffers), so that phase B of a tile is never queued
+            // behind a wait for a stage that the producer is still filling
             phase_a(0);
+            if (ntiles > 1) phase_a(1);
             for (int t = 0; t < ntiles; t++) {
-                if (t + 1 < ntiles) phase_a(t + 1);
                 const int s = t % NS;
-                cf_mbar_wait(kfull, (uint32_t)(t & 1));                       // K tile t written by the evaluation warps
+                cf_mbar_wait(kfull, (uint32_t)(t & 1));                       // K tile t written (TMEM) by the evaluation warps
                 if (t >= 1) cf_mbar_wait(outfree, (uint32_t)((t - 1) & 1));   // Out of tile t - 1 read
                 cf_tc_fence_after();
                 const uint32_t ahi = cf_smem_u32(stages + (size_t)s * S::stage_bytes + 2 * S::y_bytes), alo = ahi + S::a_bytes;
                 uint32_t acc = 0;
                 for (int pr = 0; pr < 3; pr++) {
-                    const uint32_t ka = pr == 0 ? klo : khi, ab = pr == 1 ? alo : ahi;
+                    const uint32_t ka = pr == 0 ? tm_klo : tm_khi, ab = pr == 1 ? alo : ahi;
 #pragma unroll
                     for (int ks = 0; ks < TJ / 8; ks++) {
-                        cf_umma_tf32(tm_out, cf_umma_desc(ka + ks * 2 * LBO_K, LBO_K, 128), cf_umma_desc(ab + ks * 2 * LBO_A, LBO_A, 128), idesc, acc);
+                        cf_umma_tf32_ta(tm_out, ka + 8 * ks, cf_umma_desc(ab + ks * 2 * LBO_A, LBO_A, 128), idesc, acc);
                         acc = 1;
                     }
                 }
                 cf_umma_commit(outfull);     // Out readable, K tile free
                 cf_umma_commit(&empty[s]);   // stage s free for the producer
+                if (t + 2 < ntiles) phase_a(t + 2);
             }
         }
     } else {
@@ -246,7 +259,8 @@ __global__ void __launch_bounds__(CF_MMU_THREADS, 1) gram_mm_tc5_kernel(const __
             uint32_t o[32];
             cf_tmem_ld32(tm_out + lane_base + 32 * ch, o);
             cf_tc_fence_before();
-            cf_mbar_arrive(outfree);
+            __syncwarp();
+            if (lane == 0) cf_mbar_arrive(outfree);
 #pragma unroll
             for (int c = 0; c < 32; c++) acc[c] += __uint_as_float(o[c]);
         };
@@ -257,7 +271,8 @@ __global__ void __launch_bounds__(CF_MMU_THREADS, 1) gram_mm_tc5_kernel(const __
             uint32_t dv[32];
             cf_tmem_ld32(tm_dot[t & 1] + lane_base + 32 * ch, dv);
             cf_tc_fence_before();
-            cf_mbar_arrive(&dotfree[t & 1]);
+            __syncwarp();
+            if (lane == 0) cf_mbar_arrive(&dotfree[t & 1]);
             // the stage of tile t is still resident (freed only when phase B of tile t completes): |y|^2 of this warp's 32 columns
             const float* yns = reinterpret_cast<const float*>(stages + (size_t)s * S::stage_bytes + 2 * S::y_bytes + 2 * S::a_bytes) + 32 * ch;
             float kv[32];
@@ -274,18 +289,16 @@ __global__ void __launch_bounds__(CF_MMU_THREADS, 1) gram_mm_tc5_kernel(const __
                 for (int u = 0; u < 8; u++) kv[8 * g + u] = k8[u];
             }
             if (t >= 1) drain_out(t - 1);  // phase B of tile t - 1 is complete: its Out is added, and the K tile may be overwritten
-            // K tile t, hi / lo, canonical layout (row = tile row, K index = tile column): 16-byte stores, conflict-free across a warp
+            // K tile t, hi / lo, into tensor memory: lane = tile row, column = tile column (the A operand of phase B)
+            uint32_t kh[32], kl[32];
 #pragma unroll
-            for (int g = 0; g < 8; g++) {
-                const int col = 32 * ch + 4 * g;
-                const float4 h = make_float4(kv[4 * g], kv[4 * g + 1], kv[4 * g + 2], kv[4 * g + 3]);
-                const float4 l = make_float4(__uint_as_float(cf_tf32_lo(h.x)), __uint_as_float(cf_tf32_lo(h.y)), __uint_as_float(cf_tf32_lo(h.z)),
-                                             __uint_as_float(cf_tf32_lo(h.w)));
-                *reinterpret_cast<float4*>(&Khi[cf_canon(row, col, TI)]) = h;
-                *reinterpret_cast<float4*>(&Klo[cf_canon(row, col, TI)]) = l;
-            }
-            cf_fence_async_smem();  // generic-proxy stores -> visible to the tensor core's (async-proxy) reads
-            cf_mbar_arrive(kfull);
+            for (int c = 0; c < 32; c++) { kh[c] = __float_as_uint(kv[c]); kl[c] = cf_tf32_lo(kv[c]); }
+            cf_tmem_st32(tm_khi + lane_base + 32 * ch, kh);
+            cf_tmem_st32(tm_klo + lane_base + 32 * ch, kl);
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            cf_tc_fence_before();
+            __syncwarp();
+            if (lane == 0) cf_mbar_arrive(kfull);
         }
         if (ntiles > 0) drain_out(ntiles - 1);
         float* Bg = static_cast<float*>(P.B);
@@ -305,7 +318,7 @@ __global__ void __launch_bounds__(CF_MMU_THREADS, 1) gram_mm_tc5_kernel(const __
     }
     cf_tc_fence_before();
     __syncthreads();
-    if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem));
+    if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
 #ifndef __CUDACC_RTC__

@@ -18,8 +18,8 @@
 // is 2^-22 relative.  The column-side operands arrive by TMA bulk copies from per-handle / per-call images that are ALREADY in the
 // tensor core's canonical shared-memory layout (cf_canon_* kernels below), so a stage is five 1-D copies and no thread touches it.
 //
-// Warp roles: warps 0-7 evaluate (warp w owns TMEM lanes 32 (w % 4) .. +31, i.e. tile rows, and columns 32 (w / 4) .. +31), warp 8
-// is the TMA producer, warp 9 issues the MMAs.  mbarriers: full / empty per stage (TMA <-> MMA), dotfull / dotfree per TMEM dot buffer,
+// Warp roles: CF_MMU_EW = 16 evaluation warps in two groups of 8 that take alternate column tiles (within a group warp w owns TMEM lanes
+// 32 (w % 4) .. +31, i.e. tile rows, and columns 32 (w / 4) .. +31), one TMA producer warp, one phase-A and one phase-B issuing warp.  mbarriers: full / empty per stage (TMA <-> MMA), dotfull / dotfree per TMEM dot buffer,
 // kfull (K tile written), outfull (phase B done: Out readable, K tile and stage free), outfree.
 #pragma once
 #include "gram_mm_tf32.cuh"
@@ -28,7 +28,12 @@
 #define CF_MMU_TJ 64
 #define CF_MMU_PC 64
 #define CF_MMU_NS 3
-#define CF_MMU_THREADS 320
+#ifndef CF_MMU_EW
+#define CF_MMU_EW 16                       // evaluation warps: two groups of 8 that take alternate column tiles
+#endif
+#define CF_MMU_GW (CF_MMU_EW / 2)          // warps per evaluation group
+#define CF_MMU_CW (64 / (CF_MMU_GW / 4))   // tile columns (and right-hand sides) per evaluation warp
+#define CF_MMU_THREADS (32 * CF_MMU_EW + 96)   // + TMA producer warp, phase-A issuer warp, phase-B issuer warp
 
 // element (r, k) of an R x K tile of 4-byte values in the K-major canonical layout without swizzle (core matrix = 8 rows x 16 bytes,
 // core matrices of one K chunk contiguous): LBO (next K chunk) = R / 8 * 128 bytes, SBO (next 8 rows) = 128 bytes
@@ -120,6 +125,32 @@ __device__ __forceinline__ void cf_tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) 
                  : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void cf_tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+                   "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void cf_tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+                   "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+                 : "memory");
+}
+template <int N> __device__ __forceinline__ void cf_tmem_ld(uint32_t taddr, uint32_t (&v)[N]) {
+    if constexpr (N == 32) cf_tmem_ld32(taddr, v); else cf_tmem_ld16(taddr, v);
+}
+template <int N> __device__ __forceinline__ void cf_tmem_st(uint32_t taddr, const uint32_t (&v)[N]) {
+    if constexpr (N == 32) cf_tmem_st32(taddr, v); else cf_tmem_st16(taddr, v);
+}
+// one lane of a converged warp (elect.sync): the issuing warps run their loops warp-uniformly, so that descriptors live in uniform
+// registers, and only the tcgen05.mma / commit instructions sit under the elected predicate
+__device__ __forceinline__ bool cf_elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void cf_mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(cf_smem_u32(bar)) : "memory");
 }
@@ -135,8 +166,8 @@ __global__ void __launch_bounds__(CF_MMU_THREADS, 1) gram_mm_tc5_kernel(const __
     extern __shared__ unsigned char smem_raw[];
     unsigned char* smem = smem_raw + ((1024u - (cf_smem_u32(smem_raw) & 1023u)) & 1023u);  // 1 KB alignment inside the shared window
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
-    uint64_t *full = bars, *empty = bars + NS, *dotfull = bars + 2 * NS, *dotfree = dotfull + 2, *kfull = dotfree + 2, *outfull = kfull + 1,
-             *outfree = outfull + 1;
+    uint64_t *full = bars, *empty = bars + NS, *dotfull = bars + 2 * NS, *dotfree = dotfull + 2, *kfull = dotfree + 2, *outfull = kfull + 2,
+             *outfree = outfull + 2;  // dot / K / out buffers and their barriers are indexed by the tile parity = evaluation group
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 24);
     float* Xhi = reinterpret_cast<float*>(smem + S::bar_bytes);
     float* Xlo = Xhi + TI * DK;
@@ -146,11 +177,13 @@ __global__ void __launch_bounds__(CF_MMU_THREADS, 1) gram_mm_tc5_kernel(const __
 
     if (tid == 0) {
         for (int s = 0; s < NS; s++) { cf_mbar_init(&full[s], 1); cf_mbar_init(&empty[s], 1); }
-        for (int b = 0; b < 2; b++) { cf_mbar_init(&dotfull[b], 1); cf_mbar_init(&dotfree[b], 8); }  // one arrival per evaluation warp
-        cf_mbar_init(kfull, 8); cf_mbar_init(outfull, 1); cf_mbar_init(outfree, 8);
+        for (int b = 0; b < 2; b++) {  // one arrival per evaluation warp of the group
+            cf_mbar_init(&dotfull[b], 1); cf_mbar_init(&dotfree[b], CF_MMU_GW);
+            cf_mbar_init(&kfull[b], CF_MMU_GW); cf_mbar_init(&outfull[b], 1); cf_mbar_init(&outfree[b], CF_MMU_GW);
+        }
         cf_fence_barrier_init();
     }
-    if (warp == 9) {  // 512 TMEM columns: dot[0], dot[1], out, K hi, K lo (64 each)
+    if (warp == CF_MMU_EW + 1) {  // 512 TMEM columns (320 used; the allocation must be a power of two)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(cf_smem_u32(tmem_slot)));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
@@ -177,9 +210,16 @@ __global__ void __launch_bounds__(CF_MMU_THREADS, 1) gram_mm_tc5_kernel(const __
     __syncthreads();
     cf_tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tm_dot[2] = {tmem, tmem + 64}, tm_out = tmem + 128, tm_khi = tmem + 192, tm_klo = tmem + 256;
+    // TMEM columns (64 each): dot[2], out[2], K hi[2], K lo[2], indexed by tile parity.  The per-tile chain
+    //   dot ready -> tcgen05.ld -> kernel values -> tcgen05.st K -> phase B -> tcgen05.ld Out
+    // is latency-bound (each TMEM access and mbarrier hand-over costs a few hundred cycles), so the evaluation warps form TWO groups that
+    // take alternate tiles, each with its own dot / K / out buffers: while one group waits on a hand-over the other computes.
+    // (Measured alternatives: 8 or 16 warps in ONE group 84 / 85 ms; accumulators split by k-step parity 90 ms; one issuing thread
+    // for both phases 111 ms.)
+    const uint32_t tm_dot[2] = {tmem, tmem + 64}, tm_out[2] = {tmem + 128, tmem + 192}, tm_khi[2] = {tmem + 256, tmem + 320},
+                   tm_klo[2] = {tmem + 384, tmem + 448};
 
-    if (warp == 8) {
+    if (warp == CF_MMU_EW) {
         // ---- TMA producer ------------------------------------------------------------------------------------------------------
         if (lane == 0) {
             for (int t = 0; t < ntiles; t++) {
@@ -194,119 +234,146 @@ __global__ void __launch_bounds__(CF_MMU_THREADS, 1) gram_mm_tc5_kernel(const __
                 cf_tma_load_1d(st + 2 * S::y_bytes + 2 * S::a_bytes, PP.ynpad + (int64_t)t * TJ, (uint32_t)S::n_bytes, &full[s]);
             }
         }
-    } else if (warp == 9) {
-        // ---- MMA issuer: A(0), then for every tile t: A(t + 1) early, B(t) as soon as its K tile is written -------------------------------
-        if (lane == 0) {
+    } else if (warp == CF_MMU_EW + 1) {
+        // ---- phase-A issuer: the distance GEMM of tile t as soon as its stage has landed and TMEM dot[t & 1] has been read -----------------
+        // (two issuing warps, one per phase: a single thread spends ~50-100 cycles per tcgen05.mma on descriptor set-up, 36 MMAs per tile)
+        {
             // instruction descriptor: D fp32, A / B tf32, both K-major, N = 64, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-            constexpr uint32_t LBO_X = (TI / 8) * 128, LBO_Y = (TJ / 8) * 128, LBO_A = (PC / 8) * 128;
-            const uint32_t xhi = cf_smem_u32(Xhi), xlo = cf_smem_u32(Xlo);
-            auto phase_a = [&](int t) {
+            constexpr uint32_t LBO_X = (TI / 8) * 128, LBO_Y = (TJ / 8) * 128;
+            const uint64_t dxh = cf_umma_desc(cf_smem_u32(Xhi), LBO_X, 128), dxl = cf_umma_desc(cf_smem_u32(Xlo), LBO_X, 128);
+            for (int t = 0; t < ntiles; t++) {
                 const int s = t % NS;
                 cf_mbar_wait(&full[s], (uint32_t)((t / NS) & 1));
                 if (t >= 2) cf_mbar_wait(&dotfree[t & 1], (uint32_t)(((t >> 1) - 1) & 1));
                 cf_tc_fence_after();
-                const uint32_t yhi = cf_smem_u32(stages + (size_t)s * S::stage_bytes), ylo = yhi + S::y_bytes;
-                uint32_t acc = 0;
-                for (int pr = 0; pr < 3; pr++) {  // small terms first: lo.hi, hi.lo, hi.hi
-                    const uint32_t xa = pr == 0 ? xlo : xhi, yb = pr == 1 ? ylo : yhi;
+                const uint64_t dyh = cf_umma_desc(cf_smem_u32(stages + (size_t)s * S::stage_bytes), LBO_Y, 128), dyl = dyh + (S::y_bytes >> 4);
+                if (cf_elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < DK / 8; ks++) {
-                        cf_umma_tf32(tm_dot[t & 1], cf_umma_desc(xa + ks * 2 * LBO_X, LBO_X, 128), cf_umma_desc(yb + ks * 2 * LBO_Y, LBO_Y, 128), idesc, acc);
-                        acc = 1;
+                    for (int pr = 0; pr < 3; pr++) {  // small terms first: lo.hi, hi.lo, hi.hi
+                        const uint64_t xa = pr == 0 ? dxl : dxh, yb = pr == 1 ? dyl : dyh;
+#pragma unroll
+                        for (int ks = 0; ks < DK / 8; ks++) {  // the start-address field advances by two K chunks per step
+                            cf_umma_tf32(tm_dot[t & 1], xa + (uint64_t)((ks * 2 * LBO_X) >> 4), yb + (uint64_t)((ks * 2 * LBO_Y) >> 4), idesc,
+                                         (pr > 0 || ks > 0) ? 1u : 0u);
+                        }
                     }
+                    cf_umma_commit(&dotfull[t & 1]);
                 }
-                cf_umma_commit(&dotfull[t & 1]);
-            };
-            // the distance GEMM runs TWO tiles ahead of the evaluation (two TMEM dot buffers), so that phase B of a tile is never queued
-            // behind a wait for a stage that the producer is still filling
-            phase_a(0);
-            if (ntiles > 1) phase_a(1);
+                __syncwarp();
+            }
+        }
+    } else if (warp == CF_MMU_EW + 2) {
+        // ---- phase-B issuer: Out = K A as soon as the evaluation warps have written K tile t to tensor memory ----------------------------------
+        {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+            constexpr uint32_t LBO_A = (PC / 8) * 128;
             for (int t = 0; t < ntiles; t++) {
                 const int s = t % NS;
-                cf_mbar_wait(kfull, (uint32_t)(t & 1));                       // K tile t written (TMEM) by the evaluation warps
-                if (t >= 1) cf_mbar_wait(outfree, (uint32_t)((t - 1) & 1));   // Out of tile t - 1 read
+                const int g = t & 1;
+                cf_mbar_wait(&kfull[g], (uint32_t)((t >> 1) & 1));                            // K tile t written (TMEM) by evaluation group g
+                if (t >= 2) cf_mbar_wait(&outfree[g], (uint32_t)(((t >> 1) - 1) & 1));        // Out of tile t - 2 read
                 cf_tc_fence_after();
-                const uint32_t ahi = cf_smem_u32(stages + (size_t)s * S::stage_bytes + 2 * S::y_bytes), alo = ahi + S::a_bytes;
-                uint32_t acc = 0;
-                for (int pr = 0; pr < 3; pr++) {
-                    const uint32_t ka = pr == 0 ? tm_klo : tm_khi, ab = pr == 1 ? alo : ahi;
+                const uint64_t dah = cf_umma_desc(cf_smem_u32(stages + (size_t)s * S::stage_bytes + 2 * S::y_bytes), LBO_A, 128), dal = dah + (S::a_bytes >> 4);
+                if (cf_elect_one()) {
 #pragma unroll
-                    for (int ks = 0; ks < TJ / 8; ks++) {
-                        cf_umma_tf32_ta(tm_out, ka + 8 * ks, cf_umma_desc(ab + ks * 2 * LBO_A, LBO_A, 128), idesc, acc);
-                        acc = 1;
+                    for (int pr = 0; pr < 3; pr++) {
+                        const uint32_t ka = pr == 0 ? tm_klo[g] : tm_khi[g];
+                        const uint64_t ab = pr == 1 ? dal : dah;
+#pragma unroll
+                        for (int ks = 0; ks < TJ / 8; ks++) {
+                            cf_umma_tf32_ta(tm_out[g], ka + 8 * ks, ab + (uint64_t)((ks * 2 * LBO_A) >> 4), idesc, (pr > 0 || ks > 0) ? 1u : 0u);
+                        }
                     }
+                    cf_umma_commit(&outfull[g]);  // Out readable, K tile free
+                    cf_umma_commit(&empty[s]);    // stage s free for the producer
                 }
-                cf_umma_commit(outfull);     // Out readable, K tile free
-                cf_umma_commit(&empty[s]);   // stage s free for the producer
-                if (t + 2 < ntiles) phase_a(t + 2);
+                __syncwarp();
             }
         }
     } else {
         // ---- evaluation warps ----------------------------------------------------------------------------------------------------------
-        const int q4 = warp & 3, ch = warp >> 2;         // TMEM lane quarter (tile rows 32 q4 ..), column half (32 ch ..)
+        constexpr int CW = CF_MMU_CW;
+        const int grp = warp / CF_MMU_GW, wg = warp % CF_MMU_GW;  // evaluation group (tile parity), warp within the group
+        const int q4 = wg & 3, cq = wg >> 2;                      // TMEM lane quarter (tile rows 32 q4 ..), column group (CW cq ..)
         const int row = 32 * q4 + lane;
         int64_t ir = rbase + row;
         if (ir >= rend) ir = rend - 1;
         const float xnorm = static_cast<const float*>(P.xn)[ir];
         const uint32_t lane_base = (uint32_t)(32 * q4) << 16;
-        float acc[32];
+        float acc[CW];
 #pragma unroll
-        for (int c = 0; c < 32; c++) acc[c] = 0.f;
-        auto drain_out = [&](int t) {  // Out of tile t -> running sums
-            cf_mbar_wait(outfull, (uint32_t)(t & 1));
+        for (int c = 0; c < CW; c++) acc[c] = 0.f;
+        auto drain_out = [&](int t) {  // Out of tile t (of this group) -> running sums
+            cf_mbar_wait(&outfull[grp], (uint32_t)((t >> 1) & 1));
             cf_tc_fence_after();
-            uint32_t o[32];
-            cf_tmem_ld32(tm_out + lane_base + 32 * ch, o);
+            uint32_t o[CW];
+            cf_tmem_ld<CW>(tm_out[grp] + lane_base + CW * cq, o);
             cf_tc_fence_before();
             __syncwarp();
-            if (lane == 0) cf_mbar_arrive(outfree);
+            if (lane == 0) cf_mbar_arrive(&outfree[grp]);
 #pragma unroll
-            for (int c = 0; c < 32; c++) acc[c] += __uint_as_float(o[c]);
+            for (int c = 0; c < CW; c++) acc[c] += __uint_as_float(o[c]);
         };
-        for (int t = 0; t < ntiles; t++) {
+        int last = -1;
+        for (int t = grp; t < ntiles; t += 2) {
             const int s = t % NS;
-            cf_mbar_wait(&dotfull[t & 1], (uint32_t)((t >> 1) & 1));
+            cf_mbar_wait(&dotfull[grp], (uint32_t)((t >> 1) & 1));
             cf_tc_fence_after();
-            uint32_t dv[32];
-            cf_tmem_ld32(tm_dot[t & 1] + lane_base + 32 * ch, dv);
+            uint32_t dv[CW];
+            cf_tmem_ld<CW>(tm_dot[grp] + lane_base + CW * cq, dv);
             cf_tc_fence_before();
             __syncwarp();
-            if (lane == 0) cf_mbar_arrive(&dotfree[t & 1]);
-            // the stage of tile t is still resident (freed only when phase B of tile t completes): |y|^2 of this warp's 32 columns
-            const float* yns = reinterpret_cast<const float*>(stages + (size_t)s * S::stage_bytes + 2 * S::y_bytes + 2 * S::a_bytes) + 32 * ch;
-            float kv[32];
+            if (lane == 0) cf_mbar_arrive(&dotfree[grp]);
+            // the stage of tile t is still resident (freed only when phase B of tile t completes): |y|^2 of this warp's columns
+            const float* yns = reinterpret_cast<const float*>(stages + (size_t)s * S::stage_bytes + 2 * S::y_bytes + 2 * S::a_bytes) + CW * cq;
+            float kv[CW];
 #pragma unroll
-            for (int g = 0; g < 4; g++) {
+            for (int g = 0; g < CW / 8; g++) {
                 float r2[8], dt[8], k8[8];
+                const float4 n0 = *reinterpret_cast<const float4*>(yns + 8 * g), n1 = *reinterpret_cast<const float4*>(yns + 8 * g + 4);
+                const float yn8[8] = {n0.x, n0.y, n0.z, n0.w, n1.x, n1.y, n1.z, n1.w};
 #pragma unroll
                 for (int u = 0; u < 8; u++) {
                     dt[u] = __uint_as_float(dv[8 * g + u]);
-                    r2[u] = fmaxf(fmaf(-2.f, dt[u], xnorm + yns[8 * g + u]), 0.f);
+                    r2[u] = fmaxf(fmaf(-2.f, dt[u], xnorm + yn8[u]), 0.f);
                 }
                 cf_sop_value_f32_n<8>(r2, dt, P.sop, k8);
 #pragma unroll
                 for (int u = 0; u < 8; u++) kv[8 * g + u] = k8[u];
             }
-            if (t >= 1) drain_out(t - 1);  // phase B of tile t - 1 is complete: its Out is added, and the K tile may be overwritten
+            if (last >= 0) drain_out(last);  // phase B of this group's previous tile is complete: its Out is added, the K buffer may be overwritten
             // K tile t, hi / lo, into tensor memory: lane = tile row, column = tile column (the A operand of phase B)
-            uint32_t kh[32], kl[32];
+            uint32_t kh[CW], kl[CW];
 #pragma unroll
-            for (int c = 0; c < 32; c++) { kh[c] = __float_as_uint(kv[c]); kl[c] = cf_tf32_lo(kv[c]); }
-            cf_tmem_st32(tm_khi + lane_base + 32 * ch, kh);
-            cf_tmem_st32(tm_klo + lane_base + 32 * ch, kl);
+            for (int c = 0; c < CW; c++) { kh[c] = __float_as_uint(kv[c]); kl[c] = cf_tf32_lo(kv[c]); }
+            cf_tmem_st<CW>(tm_khi[grp] + lane_base + CW * cq, kh);
+            cf_tmem_st<CW>(tm_klo[grp] + lane_base + CW * cq, kl);
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             cf_tc_fence_before();
             __syncwarp();
-            if (lane == 0) cf_mbar_arrive(kfull);
+            if (lane == 0) cf_mbar_arrive(&kfull[grp]);
+            last = t;
         }
-        if (ntiles > 0) drain_out(ntiles - 1);
+        if (last >= 0) drain_out(last);
+        // the two groups hold the sums over the even and the odd tiles: group 1 hands its sums to group 0 through shared memory
+        float* xch = reinterpret_cast<float*>(stages);  // all stages are free once every phase B has completed
+        asm volatile("bar.sync 1, %0;" ::"r"(CF_MMU_EW * 32) : "memory");  // all evaluation warps: every tile drained
+        if (grp == 1) {
+#pragma unroll
+            for (int c = 0; c < CW; c++) xch[(CW * cq + c) * TI + row] = acc[c];
+        }
+        asm volatile("bar.sync 1, %0;" ::"r"(CF_MMU_EW * 32) : "memory");
+        if (grp == 0) {
+#pragma unroll
+            for (int c = 0; c < CW; c++) acc[c] += xch[(CW * cq + c) * TI + row];
+        }
         float* Bg = static_cast<float*>(P.B);
         const int64_t i = rbase + row;
-        if (i < rend) {
+        if (grp == 0 && i < rend) {
 #pragma unroll
-            for (int c = 0; c < 32; c++) {
-                const int col = 32 * ch + c;
+            for (int c = 0; c < CW; c++) {
+                const int col = CW * cq + c;
                 if (col < P.nrhs) {
                     float* o = Bg + (i - P.row0) + P.ldb * col;
                     double v = P.alpha * (double)acc[c];
@@ -318,7 +385,7 @@ __global__ void __launch_bounds__(CF_MMU_THREADS, 1) gram_mm_tc5_kernel(const __
     }
     cf_tc_fence_before();
     __syncthreads();
-    if (warp == 9) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
+    if (warp == CF_MMU_EW + 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem));
 }
 
 #ifndef __CUDACC_RTC__

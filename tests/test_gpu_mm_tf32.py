@@ -106,3 +106,25 @@ def test_tf32_runtime_specialised_program(cf, O):
     after = cf.jit_stats()
     assert after["failures"] == before["failures"]
     assert after["compiled"] + after["cache_hits"] > before["compiled"] + before["cache_hits"]
+
+
+def test_tcgen05_and_legacy_kernels_agree(cf, O):
+    """The default Float32 multi-RHS kernel is the tcgen05 / TMEM one (csrc/gram_mm_tc5.cuh); COVFN_MM_LEGACY=1 selects the mma.sync
+    kernel (csrc/gram_mm_tf32.cuh).  Both against the oracle, and against each other at the 3xTF32 error level."""
+    import os
+    rng = np.random.default_rng(77)
+    n, m, d, p = 700, 1300, 16, 70  # ragged tiles, two passes of 64 right-hand sides
+    X = (rng.standard_normal((n, d)) / np.sqrt(d)).astype(np.float32)
+    Y = (rng.standard_normal((m, d)) / np.sqrt(d)).astype(np.float32)
+    A = rng.standard_normal((m, p)).astype(np.float32)
+    k = 0.5 * cf.RQ(2) + cf.Dot() ** 2
+    ref = O.mul_mat(k.program(), X, A, Y=Y, dtype=np.float32)
+    out = {}
+    for legacy in ("0", "1"):
+        os.environ["COVFN_MM_LEGACY"] = legacy
+        try:
+            out[legacy] = cf.gramian(k, X.T.copy(), Y.T.copy()) @ A
+        finally:
+            del os.environ["COVFN_MM_LEGACY"]
+        assert relerr(out[legacy], ref) < 1e-5
+    assert relerr(out["0"], out["1"]) < 2e-6

@@ -170,6 +170,11 @@ struct cf_gramian_s {
     float last_ms = 0;
     int last_launches = 0;
     void* user_stream = nullptr;  // stream of the last asynchronous *_mul_device call (one in-flight user stream per handle)
+    // Float32 handles: a Float64 copy of the points (same devices, same row range), built on first use, on which the operators that
+    // exist in Float64 only run -- derivative kernels, conjugate gradients, d > 32.  The reference is generic in T (src/gradient.jl:86-92);
+    // here Float32 inputs and outputs are converted on the fly and the arithmetic in between is Float64 (at least as accurate).
+    cf_gramian_s* shadow64 = nullptr;
+    double max_sq = 0;            // largest squared point norm (scale checks)
     // timing of the last cf_cg_solve (cf_cg_timing): host wall clock of the whole solve, device time of the operator products and
     // of the NCCL row-block gathers (multi-process mode), number of operator products
     double cg_total_ms = 0, cg_mvm_ms = 0, cg_gather_ms = 0;
@@ -1322,7 +1327,57 @@ int upload_points(int dtype, const void* H, int64_t ld, int64_t n, int d, int D,
     return CF_OK;
 }
 
+// which kernels may use r2 = |x|^2 + |y|^2 - 2 x.y for this handle (see the comments inside): called at create time and for the
+// Float64 shadow of a Float32 handle
+void set_norm_flags(cf_gramian_s* g, double max_sq) {
+    const int dtype = g->dtype, d = g->d;
+    // r2 from norms (multi-RHS kernel) only for larger d and well-scaled data:
+    // |delta r2| <= (d + 2) eps (|x|^2 + |y|^2) must stay below 1e-13 (Float64) / 1e-5 (Float32)
+    {
+        const double eps = dtype == CF_F64 ? 2.220446049250313e-16 : 1.1920928955078125e-07;
+        const double bound = dtype == CF_F64 ? 1e-13 : 1e-5;
+        // ... times the largest |dk/dr2| of the program's r2-atoms (short length scales amplify an absolute error in r2):
+        // EQ exp(c r2): |c|;  MaternP(p >= 1): |d_1| / l^2 (its slope at 0, the maximum);  RQ (1 + w r2)^-a: a w.
+        // exp(-sqrt(r2)) (Exp = MaternP(0)) is not differentiable in r2 at 0: an absolute error of 1e-16 in r2 of (nearly)
+        // coincident points would become 1e-8 in k, so programs with that atom always keep direct differences.
+        // LINE atoms use x.y, which the tensor-core chain reproduces exactly.
+        // (atoms are bounded by 1, so the sum of the atoms' slopes bounds the slope of any product of them)
+        // A product of powers prod_f atom_f^p_f (atoms bounded by 1) has slope <= sum_f p_f slope_f; the program's slope is bounded by
+        // the largest such sum over its terms, weighted by the coefficients' share.
+        bool sqrt_atom = false;
+        std::vector<double> aslope(g->prog.natoms, 0.0);
+        for (int i = 0; i < g->prog.natoms; i++) {
+            const cf_atom& A = g->prog.atoms[i];
+            if (A.v.kind == CF_ATOM_EQ) aslope[i] = std::fabs(A.v.e.c);
+            else if (A.v.kind == CF_ATOM_MATERN && A.v.p == 0) sqrt_atom = true;
+            else if (A.v.kind == CF_ATOM_MATERN) aslope[i] = std::fabs(A.tay[1]) * A.inv_l2;
+            else if (A.v.kind == CF_ATOM_RQ_INT || A.v.kind == CF_ATOM_RQ_REAL) aslope[i] = A.v.alpha * A.v.w;
+        }
+        double slope = 0.0;
+        for (int t = 0; t < g->prog.nterms; t++) {
+            double ts = 0.0;
+            for (int f = 0; f < g->prog.terms[t].nfac; f++) ts += g->prog.terms[t].fac[f].power * aslope[g->prog.terms[t].fac[f].atom];
+            slope = std::max(slope, ts);
+        }
+        // accumulation factor: the random-walk value sqrt(d + 2).  The worst case (d + 2) is sqrt(d + 2) <= 5.9 times larger for
+        // d <= 32, i.e. still below 6e-13 (Float64) / 6e-5 relative error of a kernel entry when this check passes at 1e-13 / 1e-5,
+        // and unit-variance points (randn(d), the reference's README data) keep the tensor-core kernels at d = 32
+        const double growth = std::sqrt((double)(d + 2));
+        g->use_norms = (d >= 8) && !sqrt_atom && (growth * eps * 2.0 * max_sq * slope < bound);
+        // the derivative operators also need k'' (one more factor of the slope) and MaternP(1) has a 1/sqrt(r2) term in k''
+        bool smooth2 = true;
+        for (int i = 0; i < g->prog.natoms; i++)
+            if (g->prog.atoms[i].v.kind == CF_ATOM_MATERN && g->prog.atoms[i].v.p < 2) smooth2 = false;
+        g->use_norms_grad = g->use_norms && smooth2 && (growth * eps * 2.0 * max_sq * slope * slope < bound);
+        // the scaled-domain EQ kernel (gram_mvm_eq.cuh) has no clamp: besides the cancellation bound, the exponent of the
+        // farthest pair, |c| (|x| + |y|)^2 <= 4 |c| max|x|^2, must stay clear of the 2^-1022 underflow (ln 2^-1022 = -708)
+        g->eq_fast = dtype == CF_F64 && g->kind == CF_ATOM_EQ && (growth * eps * 2.0 * max_sq * slope < bound) &&
+                     (4.0 * max_sq * slope < 600.0);
+    }
+}
+
 int destroy_impl(cf_gramian_s* g) {
+    if (g->shadow64) { destroy_impl(g->shadow64); g->shadow64 = nullptr; }
     for (auto& sh : g->shards) {
         if (sh.ctx) cudaSetDevice(sh.ctx->dev);
         if (sh.stream) cudaStreamSynchronize(sh.stream); // nothing of this handle may still be running when its memory returns to the pool
@@ -1343,6 +1398,69 @@ int destroy_impl(cf_gramian_s* g) {
     delete g;
     return CF_OK;
 }
+
+// The Float64 shadow of a Float32 handle (cf_gramian_s::shadow64): device-side conversion of the padded points, norms and scale flags
+// recomputed in Float64, same devices and row range.  Built once, on the first call that needs it.
+int ensure_shadow64(cf_gramian_s* g, cf_gramian_s** out) {
+    if (g->dtype == CF_F64) { *out = g; return CF_OK; }
+    if (!g->shadow64) {
+        cf_gramian_s* h = new (std::nothrow) cf_gramian_s;
+        if (!h) return fail(CF_ERR_INTERNAL, "out of host memory");
+        h->dtype = CF_F64; h->d = g->d; h->D = g->D; h->n = g->n; h->m = g->m; h->symmetric = g->symmetric;
+        h->prog = g->prog; h->sop_val = g->sop_val; h->sop_grad = g->sop_grad; h->grad_ok = g->grad_ok;
+        h->kind = g->kind; h->coef = g->coef; h->coef_grad = g->coef_grad; h->entry = g->entry; h->opt_symmetric = g->opt_symmetric;
+        h->shards.resize(g->shards.size());
+        double max_sq = 0;
+        int rc = CF_OK;
+        for (size_t q = 0; q < g->shards.size() && !rc; q++) {
+            Shard& src = g->shards[q];
+            Shard& dst = h->shards[q];
+            dst.ctx = src.ctx;
+            auto cu = [&](cudaError_t e, const char* what) { if (e != cudaSuccess && !rc) rc = fail(CF_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e)); };
+            cu(cudaSetDevice(src.ctx->dev), "cudaSetDevice");
+            cu(cudaStreamCreateWithFlags(&dst.stream, cudaStreamNonBlocking), "cudaStreamCreate");
+            cu(cudaEventCreate(&dst.ev0), "cudaEventCreate");
+            cu(cudaEventCreate(&dst.ev1), "cudaEventCreate");
+            if (rc) break;
+            cu(cudaStreamSynchronize(src.stream), "cudaStreamSynchronize");
+            double* flags = nullptr;
+            cu(dev_alloc((void**)&flags, 16), "cudaMallocAsync");
+            if (rc) break;
+            cu(cudaMemsetAsync(flags, 0, 16, dst.stream), "cudaMemsetAsync");
+            auto conv = [&](const void* X32, int64_t cnt, void** X64, void** N64) {
+                cu(dev_alloc(X64, std::max<size_t>(16, (size_t)cnt * g->D * 8)), "cudaMallocAsync");
+                cu(dev_alloc(N64, std::max<size_t>(16, (size_t)cnt * 8)), "cudaMallocAsync");
+                if (rc || cnt == 0) return;
+                const int cb = (int)std::min<int64_t>((cnt * g->D + 255) / 256, 8192);
+                cf_convert_kernel<float, double><<<cb, 256, 0, dst.stream>>>((const float*)X32, (double*)*X64, cnt * g->D);
+                cf_sqnorm_validate_kernel<double><<<(int)std::min<int64_t>((cnt + 255) / 256, 4096), 256, 0, dst.stream>>>((const double*)*X64, g->D, cnt,
+                                                                                                                      (double*)*N64, flags);
+                cu(cudaGetLastError(), "point conversion");
+            };
+            conv(src.X, g->n, &dst.X, &dst.xn);
+            if (src.Y != src.X) conv(src.Y, g->m, &dst.Y, &dst.yn);
+            else { dst.Y = dst.X; dst.yn = dst.xn; }
+            unsigned long long hf[2] = {0, 0};
+            cu(cudaMemcpyAsync(hf, flags, 16, cudaMemcpyDeviceToHost, dst.stream), "cudaMemcpyAsync");
+            cu(cudaStreamSynchronize(dst.stream), "cudaStreamSynchronize");
+            dev_free(flags);
+            double ms;
+            std::memcpy(&ms, &hf[1], 8);
+            max_sq = std::max(max_sq, ms);
+        }
+        if (rc) { destroy_impl(h); return rc; }
+        set_norm_flags(h, max_sq);
+        h->max_sq = max_sq;
+        g->shadow64 = h;
+    }
+    cf_gramian_s* h = g->shadow64;
+    h->row_begin = g->row_begin; h->row_end = g->row_end; h->opt_symmetric = g->opt_symmetric;
+    split_rows(h);
+    *out = h;
+    return CF_OK;
+}
+// does this product of a Float32 handle have to run on the Float64 shadow?
+inline bool needs_shadow(const cf_gramian_s* g, int deriv) { return g->dtype == CF_F32 && (deriv != 0 || !g->entry); }
 
 }  // namespace
 
@@ -1398,8 +1516,7 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
     if (!ard.empty() && (int)ard.size() != d)
         return fail(CF_ERR_DIMENSION, "cf_gramian_create: ARD has %d length scales, the points have dimension %d", (int)ard.size(), d);
     for (double& l : ard) l = 1.0 / std::sqrt(l);  // coordinate scale
-    const cf_kernel_entry* entry = find_entry(d);  // nullptr for d > 32: tiled contraction kernels (bigd.cuh), Float64 only
-    if (!entry && dtype != CF_F64) return fail(CF_ERR_UNSUPPORTED, "cf_gramian_create: d = %d > 32 is supported in Float64 only", d);
+    const cf_kernel_entry* entry = find_entry(d);  // nullptr for d > 32: tiled contraction kernels (bigd.cuh; Float32 handles: on the Float64 shadow)
     if (d > (1 << 20)) return fail(CF_ERR_UNSUPPORTED, "cf_gramian_create: d = %d is too large", d);
     if (cf_device_count() < 1) return fail(CF_ERR_CUDA, "cf_gramian_create: no CUDA device available (this library has no CPU path)");
 
@@ -1483,49 +1600,8 @@ int cf_gramian_create(cf_gramian_t* out, const cf_knode_t* prog, int nnodes, int
         }
 #undef CF_CREATE_CUDA
     }
-    // r2 from norms (multi-RHS kernel) only for larger d and well-scaled data:
-    // |delta r2| <= (d + 2) eps (|x|^2 + |y|^2) must stay below 1e-13 (Float64) / 1e-5 (Float32)
-    {
-        const double eps = dtype == CF_F64 ? 2.220446049250313e-16 : 1.1920928955078125e-07;
-        const double bound = dtype == CF_F64 ? 1e-13 : 1e-5;
-        // ... times the largest |dk/dr2| of the program's r2-atoms (short length scales amplify an absolute error in r2):
-        // EQ exp(c r2): |c|;  MaternP(p >= 1): |d_1| / l^2 (its slope at 0, the maximum);  RQ (1 + w r2)^-a: a w.
-        // exp(-sqrt(r2)) (Exp = MaternP(0)) is not differentiable in r2 at 0: an absolute error of 1e-16 in r2 of (nearly)
-        // coincident points would become 1e-8 in k, so programs with that atom always keep direct differences.
-        // LINE atoms use x.y, which the tensor-core chain reproduces exactly.
-        // (atoms are bounded by 1, so the sum of the atoms' slopes bounds the slope of any product of them)
-        // A product of powers prod_f atom_f^p_f (atoms bounded by 1) has slope <= sum_f p_f slope_f; the program's slope is bounded by
-        // the largest such sum over its terms, weighted by the coefficients' share.
-        bool sqrt_atom = false;
-        std::vector<double> aslope(g->prog.natoms, 0.0);
-        for (int i = 0; i < g->prog.natoms; i++) {
-            const cf_atom& A = g->prog.atoms[i];
-            if (A.v.kind == CF_ATOM_EQ) aslope[i] = std::fabs(A.v.e.c);
-            else if (A.v.kind == CF_ATOM_MATERN && A.v.p == 0) sqrt_atom = true;
-            else if (A.v.kind == CF_ATOM_MATERN) aslope[i] = std::fabs(A.tay[1]) * A.inv_l2;
-            else if (A.v.kind == CF_ATOM_RQ_INT || A.v.kind == CF_ATOM_RQ_REAL) aslope[i] = A.v.alpha * A.v.w;
-        }
-        double slope = 0.0;
-        for (int t = 0; t < g->prog.nterms; t++) {
-            double ts = 0.0;
-            for (int f = 0; f < g->prog.terms[t].nfac; f++) ts += g->prog.terms[t].fac[f].power * aslope[g->prog.terms[t].fac[f].atom];
-            slope = std::max(slope, ts);
-        }
-        // accumulation factor: the random-walk value sqrt(d + 2).  The worst case (d + 2) is sqrt(d + 2) <= 5.9 times larger for
-        // d <= 32, i.e. still below 6e-13 (Float64) / 6e-5 relative error of a kernel entry when this check passes at 1e-13 / 1e-5,
-        // and unit-variance points (randn(d), the reference's README data) keep the tensor-core kernels at d = 32
-        const double growth = std::sqrt((double)(d + 2));
-        g->use_norms = (d >= 8) && !sqrt_atom && (growth * eps * 2.0 * max_sq * slope < bound);
-        // the derivative operators also need k'' (one more factor of the slope) and MaternP(1) has a 1/sqrt(r2) term in k''
-        bool smooth2 = true;
-        for (int i = 0; i < g->prog.natoms; i++)
-            if (g->prog.atoms[i].v.kind == CF_ATOM_MATERN && g->prog.atoms[i].v.p < 2) smooth2 = false;
-        g->use_norms_grad = g->use_norms && smooth2 && (growth * eps * 2.0 * max_sq * slope * slope < bound);
-        // the scaled-domain EQ kernel (gram_mvm_eq.cuh) has no clamp: besides the cancellation bound, the exponent of the
-        // farthest pair, |c| (|x| + |y|)^2 <= 4 |c| max|x|^2, must stay clear of the 2^-1022 underflow (ln 2^-1022 = -708)
-        g->eq_fast = dtype == CF_F64 && g->kind == CF_ATOM_EQ && (growth * eps * 2.0 * max_sq * slope < bound) &&
-                     (4.0 * max_sq * slope < 600.0);
-    }
+    set_norm_flags(g, max_sq);
+    g->max_sq = max_sq;
     (void)es;
     split_rows(g);
     *out = g;
@@ -1565,7 +1641,6 @@ int cf_gramian_set_row_range(cf_gramian_t g, int64_t row_begin, int64_t row_end)
 }
 
 static int check_derivative(cf_gramian_s* g) {
-    if (g->dtype != CF_F64) return fail(CF_ERR_UNSUPPORTED, "derivative operators: Float64 only");
     if (!g->prog.isotropic && !g->prog.dotproduct)
         return fail(CF_ERR_UNSUPPORTED, "derivative operators: kernel has neither the IsotropicInput nor the DotProductInput trait");
     if (!g->grad_ok) return fail(CF_ERR_UNSUPPORTED, "derivative operators: kernel too complex (more than 4 terms or 3 base kernels)");
@@ -1594,6 +1669,27 @@ static int mul_host_impl(cf_gramian_t g, void* y, int64_t ldy, const void* x, in
         if (int rc = check_vg_dim(g, deriv)) return rc;
     }
     if (nrhs == 1) { ldy = rows; ldx = cols; }
+    if (needs_shadow(g, deriv)) {
+        // Float32 handle, operator that exists in Float64 only: convert the vectors, run on the Float64 shadow, convert back
+        cf_gramian_s* h = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(g->mu);
+            if (int rc = ensure_shadow64(g, &h)) return rc;
+        }
+        std::vector<double> xd((size_t)cols * nrhs), yd((size_t)rows * nrhs, 0.0);
+        const float* xf = (const float*)x;
+        float* yf = (float*)y;
+        for (int64_t c = 0; c < nrhs; c++) {
+            for (int64_t q = 0; q < cols; q++) xd[(size_t)c * cols + q] = (double)xf[c * ldx + q];
+            if (beta != 0.0)
+                for (int64_t q = 0; q < rows; q++) yd[(size_t)c * rows + q] = (double)yf[c * ldy + q];
+        }
+        if (int rc = mul_host_impl(h, yd.data(), rows, xd.data(), cols, nrhs, alpha, beta, deriv)) return rc;
+        for (int64_t c = 0; c < nrhs; c++)
+            for (int64_t q = 0; q < rows; q++) yf[c * ldy + q] = (float)yd[(size_t)c * rows + q];
+        g->last_ms = h->last_ms; g->last_launches = h->last_launches;
+        return CF_OK;
+    }
     std::lock_guard<std::mutex> lk(g->mu);
     const size_t es = esize(g->dtype);
     g->last_launches = 0;
@@ -1773,6 +1869,33 @@ static int mul_device_impl(cf_gramian_t g, void* d_y, int64_t ldy, const void* d
         if (int rc = check_derivative(g)) return rc;
         if (int rc = check_vg_dim(g, deriv)) return rc;
     }
+    if (needs_shadow(g, deriv)) {
+        // Float32 device vectors, Float64-only operator: device-side conversion around the Float64 shadow's product (same stream)
+        cf_gramian_s* h = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(g->mu);
+            if (int rc = ensure_shadow64(g, &h)) return rc;
+        }
+        Shard& hs = h->shards[0];
+        CF_CUDA(cudaSetDevice(hs.ctx->dev));
+        cudaStream_t st = stream ? (cudaStream_t)stream : hs.stream;
+        if (stream) { g->user_stream = stream; h->user_stream = stream; }
+        if (int rc = hs.apad.ensure((size_t)cols * nrhs * 8 + 16)) return rc;
+        if (int rc = hs.ypad.ensure((size_t)rows * nrhs * 8 + 16)) return rc;
+        const int cb = (int)std::min<int64_t>((std::max(rows, cols) + 255) / 256, 8192);
+        for (int64_t c = 0; c < nrhs; c++) {
+            cf_convert_kernel<float, double><<<cb, 256, 0, st>>>((const float*)d_x + c * ldx, (double*)hs.apad.p + c * cols, cols);
+            if (beta != 0.0) cf_convert_kernel<float, double><<<cb, 256, 0, st>>>((const float*)d_y + c * ldy, (double*)hs.ypad.p + c * rows, rows);
+        }
+        CF_CUDA(cudaGetLastError());
+        if (int rc = mul_device_impl(h, hs.ypad.p, rows, hs.apad.p, cols, nrhs, alpha, beta, (void*)st, deriv)) return rc;
+        for (int64_t c = 0; c < nrhs; c++)
+            cf_convert_kernel<double, float><<<cb, 256, 0, st>>>((const double*)hs.ypad.p + c * rows, (float*)d_y + c * ldy, rows);
+        CF_CUDA(cudaGetLastError());
+        if (!stream) CF_CUDA(cudaStreamSynchronize(st));
+        g->last_launches = h->last_launches;
+        return CF_OK;
+    }
     std::lock_guard<std::mutex> lk(g->mu);
     Shard& sh = g->shards[0];
     CF_CUDA(cudaSetDevice(sh.ctx->dev));
@@ -1869,7 +1992,24 @@ int cf_cg_solve(cf_gramian_t g, double sigma2, void* x, const void* b, double re
     if (int rc = check_handle(g)) return rc;
     if (!x || !b) return fail(CF_ERR_BAD_ARGUMENT, "cf_cg_solve: NULL vector");
     if (g->n != g->m) return fail(CF_ERR_DIMENSION, "cf_cg_solve: Gramian is %lld x %lld, not square", (long long)g->n, (long long)g->m);
-    if (g->dtype != CF_F64) return fail(CF_ERR_UNSUPPORTED, "cf_cg_solve: Float64 only");
+    if (g->dtype == CF_F32) {
+        // Float32 system: the reference's cg! iterates in Float32 with reltol = sqrt(eps(Float32)); here the vectors are converted and
+        // the solve runs on the Float64 shadow with that tolerance (iterates at least as accurate), the solution is rounded back
+        cf_gramian_s* h = nullptr;
+        {
+            std::lock_guard<std::mutex> lk(g->mu);
+            if (int rc = ensure_shadow64(g, &h)) return rc;
+        }
+        const int64_t N = g->n * (gradient == 0 ? 1 : g->d + (gradient == 2 ? 1 : 0));
+        std::vector<double> xd((size_t)N), bd((size_t)N);
+        for (int64_t q = 0; q < N; q++) { xd[q] = (double)((const float*)x)[q]; bd[q] = (double)((const float*)b)[q]; }
+        if (reltol <= 0) reltol = std::sqrt(1.1920928955078125e-07);
+        const int rc = cf_cg_solve(h, sigma2, xd.data(), bd.data(), reltol, maxiter, gradient, iters, resnorm);
+        if (rc) return rc;
+        for (int64_t q = 0; q < N; q++) ((float*)x)[q] = (float)xd[q];
+        g->cg_total_ms = h->cg_total_ms; g->cg_mvm_ms = h->cg_mvm_ms; g->cg_gather_ms = h->cg_gather_ms; g->cg_products = h->cg_products;
+        return CF_OK;
+    }
     if (g->row_begin != 0 || g->row_end != g->n) {
         // multi-process mode: the handle of rank r must own exactly block r of the standard split
         if (!cfcomm::active() || g->shards.size() != 1)

@@ -10,6 +10,12 @@ __global__ void cf_scale_kernel(T* __restrict__ y, const T* __restrict__ yin, in
         y[q] = (beta == 0.0) ? (T)0 : (T)(beta * (double)yin[q]);
 }
 
+// element type conversion (Float32 handles run their derivative operators, solves and d > 32 products on a Float64 shadow)
+template <typename S, typename T>
+__global__ void cf_convert_kernel(const S* __restrict__ src, T* __restrict__ dst, int64_t n) {
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (int64_t)gridDim.x * blockDim.x) dst[q] = (T)src[q];
+}
+
 // ---- Matrix!(M, G): M[(i - r0) + ld (j - j0)] = k(x_i, y_j)   (reference src/gramian.jl:107-114) ------------------
 // one thread per entry, generic sum-of-products evaluation; not a hot path.
 template <typename T>

@@ -323,13 +323,11 @@ class LazyMatrixSum:
         """A \\ b -> ldiv! -> cg! (src/lazy_linear_algebra.jl:135-144), run entirely on the device(s).
         Returns (x, iterations, residual norm)."""
         G = self.G
-        if G.dtype != np.float64:
-            raise UnsupportedKernel("cg solve: Float64 only")
-        b = np.ascontiguousarray(b, dtype=np.float64)
+        b = np.ascontiguousarray(b, dtype=G.dtype)
         N = G.shape[0]
         if b.shape != (N,):
             raise DimensionMismatch(f"b has length {b.shape}, operator is {N}x{N}")
-        x = np.zeros(N) if x0 is None else np.array(x0, dtype=np.float64, copy=True)
+        x = np.zeros(N, dtype=G.dtype) if x0 is None else np.array(x0, dtype=G.dtype, copy=True)
         iters, res = C.c_int(), C.c_double()
         check(lib().cf_cg_solve(G.handle(), self.D.sigma2, x.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p),
                                 float(reltol), int(maxiter), (1 + G.k.block_extra) if G.is_gradient else 0, C.byref(iters), C.byref(res)))

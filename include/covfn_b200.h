@@ -165,7 +165,8 @@ int cf_gramian_getindex(cf_gramian_t g, int64_t i, int64_t j, double* out);
  * IsotropicGradientKernelElement / DotProductGradientKernelElement mul! (reference src/gradient.jl:86-92, 109-115) and
  * derivative_laplacian (src/gradient.jl:589-600).  The handle's program must have the IsotropicInput or the
  * DotProductInput trait (reference src/properties.jl:39-63).
- * x: (m d) x nrhs, y: (n d) x nrhs, flat index i*d + c.  HOST pointers.  Float64 only.
+ * x: (m d) x nrhs, y: (n d) x nrhs, flat index i*d + c.  HOST pointers.  Float32 handles: vectors are Float32, the arithmetic
+ * runs on a Float64 copy of the points built on first use (as do cf_cg_solve and every product with d > 32).
  */
 int cf_gradient_mul(cf_gramian_t g, void* y, int64_t ldy, const void* x, int64_t ldx, int64_t nrhs,
                     double alpha, double beta);

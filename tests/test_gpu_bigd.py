@@ -68,7 +68,10 @@ def test_readme_gradient_example_shape(cf, O):
     assert np.linalg.norm((G @ x) - Ga) / np.linalg.norm(Ga) < 1e-6
 
 
-def test_float32_bigd_rejected(cf):
-    X = np.zeros((40, 5), dtype=np.float32)
-    with pytest.raises(cf.UnsupportedKernel):
-        cf.gramian(cf.EQ(), X) @ np.ones(5, dtype=np.float32)
+def test_float32_bigd_runs_on_the_float64_shadow(cf, O):
+    # d > 32 kernels are Float64; a Float32 Gramian converts on the fly (tests/test_gpu_f32_operators.py has the full coverage)
+    rng = np.random.default_rng(5)
+    X = (rng.standard_normal((50, 40)) / np.sqrt(40)).astype(np.float32)
+    a = rng.standard_normal(50).astype(np.float32)
+    b = cf.gramian(cf.EQ(), X.T.copy()) @ a
+    assert b.dtype == np.float32 and relerr(b, O.mul_vec(cf.EQ().program(), X, a, dtype=np.float32)) < 1e-5

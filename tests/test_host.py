@@ -68,7 +68,7 @@ def test_create_error_classes(cf):
     with pytest.raises(cf.DimensionMismatch):
         _create(cf, [(1, 0, 0.0)], d=0)
     with pytest.raises(cf.UnsupportedKernel):
-        _create(cf, [(1, 0, 0.0)], d=33, dtype=0)  # d > 32 is Float64 only
+        _create(cf, [(1, 0, 0.0)], d=(1 << 20) + 1, n=0)  # point dimension beyond the library's limit
     with pytest.raises(cf.CovFnError):
         _create(cf, [(1, 0, 0.0)], dtype=7)
 

@@ -137,7 +137,8 @@ struct Shard {
     void* Y = nullptr;  // m x D (== X when symmetric)
     void* xn = nullptr;  // squared norms of the padded points (multi-RHS kernel)
     void* yn = nullptr;
-    Buf a, y, partial, apad, ypad, at, cg[6], sym_items, bsym, sym_col, bd_t, bd_s, xp, yp, ap, yc_hi, yc_lo, yc_n, ac_hi, ac_lo;
+    Buf a, y, partial, apad, ypad, at, cg[6], sym_items, bsym, sym_col, bd_t, bd_s, xp, yp, ap, yc_hi, yc_lo, yc_n, ac_hi, ac_lo, yt;
+    int64_t yt_ld = 0;      // > 0: yt holds the transposed Float32 column points with this leading dimension (gram_mvm_f32p.cuh)
     bool tc5_ready = false; // yc_* hold the canonical column-point images of the tcgen05 multi-RHS kernel
     bool mmd_ready = false; // xp / yp hold the padded point copies of the DMMA multi-RHS kernel
     int sym_nitems = -1;    // symmetric variant: work items (-1: not built), row tile, chunk length and device share they were built for
@@ -1092,6 +1093,48 @@ int launch_mvm_tf32(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, co
     return CF_OK;
 }
 
+// Float32 value MVM of a single isotropic atom at small d in packed FP32 arithmetic (gram_mvm_f32p.cuh); the transposed copy of the
+// column points it streams is built once per shard
+int launch_mvm_f32p(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const void* d_a, double alpha, double beta,
+                    cudaStream_t stream, const cf_peer_out* peers) {
+    const int64_t nrows = sh.r1 - sh.r0;
+    const cf_mvm_config& cfg = g->entry->mvm_f32p_cfg;
+    if (sh.yt_ld == 0) {
+        const int64_t ldt = ((g->m + cfg.tj - 1) / cfg.tj) * cfg.tj;
+        if (int rc = sh.yt.ensure((size_t)ldt * g->D * 4)) return rc;
+        cf_transpose_points_f32_kernel<<<148 * 8, 256, 0, stream>>>((const float*)sh.Y, g->D, g->m, ldt, (float*)sh.yt.p);
+        CF_CUDA(cudaGetLastError());
+        sh.yt_ld = ldt;
+    }
+    Plan pl = make_plan(nrows, g->m, cfg, sh.ctx->sms);
+    cf_mvm_params P;
+    std::memset(&P, 0, sizeof(P));
+    P.X = sh.X; P.Y = sh.yt.p; P.diag_block = sh.yt_ld; P.a = d_a;
+    P.row0 = sh.r0; P.nrows = nrows; P.m = g->m;
+    P.cols_per_chunk = pl.cols_per_chunk;
+    P.alpha = alpha * g->coef; P.beta = beta;
+    P.use_tma = (((uintptr_t)d_a) % 16 == 0) ? 1 : 0;
+    P.atom = g->prog.atoms[g->prog.terms[0].fac[0].atom].v;
+    P.direct = (pl.chunks == 1) ? 1 : 0;
+    P.peers = *peers;
+    if (P.direct) {
+        P.out = d_y; P.yin = d_yin;
+    } else {
+        if (int rc = sh.partial.ensure((size_t)pl.chunks * nrows * sizeof(double))) return rc;
+        P.out = sh.partial.p;
+    }
+    CF_CUDA(g->entry->mvm_f32p[cf_kind_slot(g->kind)](P, dim3(pl.row_tiles, pl.chunks), stream));
+    g->last_launches++;
+    if (!P.direct) {
+        const int blocks = (int)std::min<int64_t>((nrows + 255) / 256, 4096);
+        gram_reduce_partials<float><<<blocks, 256, 0, stream>>>((const double*)sh.partial.p, pl.chunks, nrows, (float*)d_y, (const float*)d_yin,
+                                                                 alpha * g->coef, beta, *peers);
+        CF_CUDA(cudaGetLastError());
+        g->last_launches++;
+    }
+    return CF_OK;
+}
+
 int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const void* d_a, double alpha, double beta,
                cudaStream_t stream, const cf_peer_out* peers) {
     cf_peer_out no_peers;
@@ -1119,6 +1162,9 @@ int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const v
     // the Float32 counterpart: distance GEMM in 3xTF32 (gram_mvm_tf32.cuh)
     if (dt == CF_F32 && g->use_norms && g->entry->mvm_tf32[slot] != nullptr && !env_flag("COVFN_MVM_SCALAR"))
         return launch_mvm_tf32(g, sh, d_y, d_yin, d_a, alpha, beta, stream, peers);
+    // single isotropic atom in Float32 at small d (or ill-scaled points at d <= 8): packed FP32 arithmetic (gram_mvm_f32p.cuh)
+    if (dt == CF_F32 && g->prog.single && slot < 3 && g->entry->mvm_f32p[slot] != nullptr && !env_flag("COVFN_MVM_SCALAR"))
+        return launch_mvm_f32p(g, sh, d_y, d_yin, d_a, alpha, beta, stream, peers);
     // single EQ atom on well-scaled Float64 points, small d: exponent formed in the scaled domain (gram_mvm_eq.cuh)
     const bool eqf = g->eq_fast && g->entry->mvm_eq != nullptr && !env_flag("COVFN_MVM_SCALAR");
     Plan pl = make_plan(nrows, g->m, eqf ? g->entry->mvm_eq_cfg : cfg, sh.ctx->sms);
@@ -1389,7 +1435,7 @@ int destroy_impl(cf_gramian_s* g) {
         if (sh.yn && sh.yn != sh.xn) dev_free(sh.yn);
         dev_free(sh.xn);
         sh.a.release(); sh.y.release(); sh.partial.release(); sh.apad.release(); sh.ypad.release(); sh.at.release(); sh.sym_items.release(); sh.bsym.release(); sh.sym_col.release(); sh.bd_t.release(); sh.bd_s.release();
-        sh.xp.release(); sh.yp.release(); sh.ap.release(); sh.yc_hi.release(); sh.yc_lo.release(); sh.yc_n.release(); sh.ac_hi.release(); sh.ac_lo.release();
+        sh.xp.release(); sh.yp.release(); sh.ap.release(); sh.yc_hi.release(); sh.yc_lo.release(); sh.yc_n.release(); sh.ac_hi.release(); sh.ac_lo.release(); sh.yt.release();
         for (auto& b : sh.cg) b.release();
         if (sh.ev0) cudaEventDestroy(sh.ev0);
         if (sh.ev1) cudaEventDestroy(sh.ev1);

@@ -11,6 +11,7 @@
 #include "gram_mvm_tf32.cuh"
 #include "gram_mvm_eq.cuh"
 #include "gram_mm_tc5.cuh"
+#include "gram_mvm_f32p.cuh"
 
 #define CF_NKINDS 4 /* EQ, MATERN, RQ_INT, SOP */
 inline int cf_kind_slot(int kind) {
@@ -50,6 +51,8 @@ struct cf_kernel_entry {
     int mm_tc5_smem;          // its dynamic shared memory (run-time specialised launches)
     cf_mvm_launch_fn mvm_eq;  // Float64 EQ value MVM with the exponent formed in the scaled domain (gram_mvm_eq.cuh), nullptr for D > 6
     cf_mvm_config mvm_eq_cfg;
+    cf_mvm_launch_fn mvm_f32p[3]; // Float32 value MVM in packed FP32 arithmetic (gram_mvm_f32p.cuh): EQ, MaternP, RQ_INT; nullptr for D > 8
+    cf_mvm_config mvm_f32p_cfg;
     int tune[5];                     // R, NT, TJ, NS, MINB of the value MVM kernel (names the instantiation for cf_jit.h)
 };
 

@@ -36,7 +36,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-SLOTS = {"c1": 35, "c2": 23, "c3": 111, "c4": 97, "c5": 45, "x1": 80, "x2": 81, "x3": 61, "x4": 45, "x5": 110, "x6": 125}  # FP64 issue slots per pair/block
+SLOTS = {"c1": 35, "c2": 23, "c3": 111, "c4": 97, "c5": 45, "x1": 80, "x2": 81, "x3": 61, "x4": 45, "x5": 110, "x6": 125, "x7": 33}  # FP64 issue slots per pair/block
 
 
 def workload(name):
@@ -75,6 +75,9 @@ def workload(name):
     if name == "x6":  # auxiliary: gradient operator of a composite kernel (generic 8-wide jets)
         return dict(kernel=cf.EQ() + 0.5 * cf.RQ(2), kname="GradientKernel(EQ+1/2*RQ(2))", d=16, n=32768, nrhs=1, gradient=True,
                     desc="GradientKernel(EQ + 1/2 RQ(2)) MVM, d=16, n=32768, Float64 (auxiliary)")
+    if name == "x7":  # auxiliary: EQ value MVM at d = 8 (the evaluation-bound end of the tensor-core value kernels)
+        return dict(kernel=cf.EQ(), kname="EQ", d=8, n=131072, nrhs=1, gradient=False,
+                    desc="EQ Gramian MVM, d=8, n=131072, Float64 (auxiliary)")
     raise SystemExit(f"unknown config {name}")
 
 

@@ -137,7 +137,7 @@ struct Shard {
     void* Y = nullptr;  // m x D (== X when symmetric)
     void* xn = nullptr;  // squared norms of the padded points (multi-RHS kernel)
     void* yn = nullptr;
-    Buf a, y, partial, apad, ypad, at, cg[6], sym_items, bsym, sym_col, bd_t, bd_s, xp, yp, ap, yc_hi, yc_lo, yc_n, ac_hi, ac_lo, yt;
+    Buf a, y, partial, apad, ypad, at, cg[6], sym_items, bsym, sym_col, bd_t, bd_s, xp, yp, ap, yc_hi, yc_lo, yc_n, ac_hi, ac_lo, yt, au;
     int64_t yt_ld = 0;      // > 0: yt holds the transposed Float32 column points with this leading dimension (gram_mvm_f32p.cuh)
     bool tc5_ready = false; // yc_* hold the canonical column-point images of the tcgen05 multi-RHS kernel
     bool mmd_ready = false; // xp / yp hold the padded point copies of the DMMA multi-RHS kernel
@@ -270,6 +270,22 @@ static bool env_flag(const char* name) {
     return e && std::atoi(e) != 0;
 }
 
+// canonical (tensor-core operand layout) hi / lo images of the column points and their zero-padded squared norms, built once per shard:
+// the B operands of the distance GEMMs of the tcgen05 kernels (gram_mm_tc5.cuh, gram_mvm_tc5.cuh)
+int ensure_canonical_points(cf_gramian_s* g, Shard& sh, cudaStream_t stream) {
+    if (sh.tc5_ready) return CF_OK;
+    const int dk = g->entry->mm_tc5_dk;
+    const int64_t mpad = ((g->m + CF_MMU_TJ - 1) / CF_MMU_TJ) * CF_MMU_TJ;
+    if (int rc = sh.yc_hi.ensure((size_t)mpad * dk * 4)) return rc;
+    if (int rc = sh.yc_lo.ensure((size_t)mpad * dk * 4)) return rc;
+    if (int rc = sh.yc_n.ensure((size_t)mpad * 4)) return rc;
+    cf_canon_points_kernel<<<148 * 8, 256, 0, stream>>>((const float*)sh.Y, g->D, dk, g->m, mpad, (float*)sh.yc_hi.p, (float*)sh.yc_lo.p,
+                                                        (const float*)sh.yn, (float*)sh.yc_n.p);
+    CF_CUDA(cudaGetLastError());
+    sh.tc5_ready = true;
+    return CF_OK;
+}
+
 // B <- alpha K A + beta B, device pointers, column-major with leading dimensions (elements)
 int launch_mm(cf_gramian_s* g, Shard& sh, void* d_B, int64_t ldb, const void* d_A, int64_t lda, int64_t nrhs, double alpha,
               double beta, cudaStream_t stream) {
@@ -289,15 +305,7 @@ int launch_mm(cf_gramian_s* g, Shard& sh, void* d_B, int64_t ldb, const void* d_
     if (tf32 && g->entry->mm_tc5 != nullptr && !env_flag("COVFN_MM_LEGACY")) {
         const int dk = g->entry->mm_tc5_dk;
         const int64_t ntiles = (g->m + CF_MMU_TJ - 1) / CF_MMU_TJ, mpad = ntiles * CF_MMU_TJ;
-        if (!sh.tc5_ready) {
-            if (int rc = sh.yc_hi.ensure((size_t)mpad * dk * 4)) return rc;
-            if (int rc = sh.yc_lo.ensure((size_t)mpad * dk * 4)) return rc;
-            if (int rc = sh.yc_n.ensure((size_t)mpad * 4)) return rc;
-            cf_canon_points_kernel<<<148 * 8, 256, 0, stream>>>((const float*)sh.Y, g->D, dk, g->m, mpad, (float*)sh.yc_hi.p, (float*)sh.yc_lo.p,
-                                                                (const float*)sh.yn, (float*)sh.yc_n.p);
-            CF_CUDA(cudaGetLastError());
-            sh.tc5_ready = true;
-        }
+        if (int rc = ensure_canonical_points(g, sh, stream)) return rc;
         if (int rc = sh.ac_hi.ensure((size_t)mpad * CF_MMU_PC * 4)) return rc;
         if (int rc = sh.ac_lo.ensure((size_t)mpad * CF_MMU_PC * 4)) return rc;
         cf_mmu_params PP;
@@ -1093,6 +1101,58 @@ int launch_mvm_tf32(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, co
     return CF_OK;
 }
 
+// Float32 value MVM, padded D >= 8, well-scaled points: dot products on tcgen05 / TMEM in 3xTF32 (gram_mvm_tc5.cuh)
+int launch_mvm_tc5(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const void* d_a, double alpha, double beta,
+                   cudaStream_t stream, const cf_peer_out* peers) {
+    const int64_t nrows = sh.r1 - sh.r0;
+    const cf_mvm_config& cfg = g->entry->mvm_tc5_cfg;
+    const int slot = cf_kind_slot(g->kind);
+    if (int rc = ensure_canonical_points(g, sh, stream)) return rc;
+    const int64_t mpad = ((g->m + CF_MVU_TJ - 1) / CF_MVU_TJ) * CF_MVU_TJ;
+    const float* ap = (const float*)d_a;
+    if (mpad != g->m || ((uintptr_t)d_a) % 16 != 0) {  // the weight tiles arrive by TMA: 16-byte aligned, zero beyond m
+        if (int rc = sh.au.ensure((size_t)mpad * 4)) return rc;
+        cf_pad_vec_f32_kernel<<<(int)std::min<int64_t>((mpad + 255) / 256, 2048), 256, 0, stream>>>((const float*)d_a, g->m, mpad, (float*)sh.au.p);
+        CF_CUDA(cudaGetLastError());
+        g->last_launches++;
+        ap = (const float*)sh.au.p;
+    }
+    Plan pl = make_plan(nrows, g->m, cfg, sh.ctx->sms);
+    cf_mvu_params PP;
+    std::memset(&PP, 0, sizeof(PP));
+    cf_mvm_params& P = PP.mv;
+    P.X = sh.X; P.xn = sh.xn; P.sop = g->sop_val;
+    P.row0 = sh.r0; P.nrows = nrows; P.m = g->m;
+    P.cols_per_chunk = pl.cols_per_chunk;
+    P.alpha = alpha * g->coef; P.beta = beta;
+    if (g->prog.single) P.atom = g->prog.atoms[g->prog.terms[0].fac[0].atom].v;
+    P.direct = (pl.chunks == 1) ? 1 : 0;
+    P.peers = *peers;
+    if (P.direct) {
+        P.out = d_y; P.yin = d_yin;
+    } else {
+        if (int rc = sh.partial.ensure((size_t)pl.chunks * nrows * sizeof(double))) return rc;
+        P.out = sh.partial.p;
+    }
+    PP.yhi = (const float*)sh.yc_hi.p; PP.ylo = (const float*)sh.yc_lo.p; PP.ynpad = (const float*)sh.yc_n.p; PP.apad = ap;
+    bool launched = false;
+    if (g->kind == CF_ATOM_SOP && cfjit::wanted((double)nrows * (double)g->m)) {
+        const std::string name = "gram_mvm_tc5_kernel<" + std::to_string(g->D) + ", " + std::to_string((int)CF_ATOM_SOP) + ">";
+        if (cfjit::Kernel* jit = cfjit::get_kernel(g->sop_val, "gram_mvm_tc5.cuh", name))
+            launched = cfjit::launch(jit, &PP, (unsigned)pl.row_tiles, (unsigned)pl.chunks, CF_MVU_THREADS, (unsigned)cfg.smem_bytes, stream) == 0;
+    }
+    if (!launched) CF_CUDA(g->entry->mvm_tc5[slot](PP, dim3(pl.row_tiles, pl.chunks), stream));
+    g->last_launches++;
+    if (!P.direct) {
+        const int blocks = (int)std::min<int64_t>((nrows + 255) / 256, 4096);
+        gram_reduce_partials<float><<<blocks, 256, 0, stream>>>((const double*)sh.partial.p, pl.chunks, nrows, (float*)d_y, (const float*)d_yin,
+                                                                 alpha * g->coef, beta, *peers);
+        CF_CUDA(cudaGetLastError());
+        g->last_launches++;
+    }
+    return CF_OK;
+}
+
 // Float32 value MVM of a single isotropic atom at small d in packed FP32 arithmetic (gram_mvm_f32p.cuh); the transposed copy of the
 // column points it streams is built once per shard
 int launch_mvm_f32p(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const void* d_a, double alpha, double beta,
@@ -1159,7 +1219,10 @@ int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const v
     const int slot = cf_kind_slot(g->kind);
     const bool dmma = dt == CF_F64 && g->use_norms && g->entry->mvm_dmma[slot] != nullptr && !env_flag("COVFN_MVM_SCALAR");
     if (dmma) return launch_mvm_dmma(g, sh, (double*)d_y, (const double*)d_yin, (const double*)d_a, alpha, beta, stream, peers);
-    // the Float32 counterpart: distance GEMM in 3xTF32 (gram_mvm_tf32.cuh)
+    // the Float32 counterpart: dot products on tcgen05 / TMEM in 3xTF32 (gram_mvm_tc5.cuh); COVFN_MVM_LEGACY=1 keeps the mma.sync kernel below
+    if (dt == CF_F32 && g->use_norms && g->entry->mvm_tc5[slot] != nullptr && !env_flag("COVFN_MVM_SCALAR") && !env_flag("COVFN_MVM_LEGACY"))
+        return launch_mvm_tc5(g, sh, d_y, d_yin, d_a, alpha, beta, stream, peers);
+    // ... its predecessor: distance GEMM in 3xTF32 with mma.sync fragments (gram_mvm_tf32.cuh)
     if (dt == CF_F32 && g->use_norms && g->entry->mvm_tf32[slot] != nullptr && !env_flag("COVFN_MVM_SCALAR"))
         return launch_mvm_tf32(g, sh, d_y, d_yin, d_a, alpha, beta, stream, peers);
     // single isotropic atom in Float32 at small d (or ill-scaled points at d <= 8): packed FP32 arithmetic (gram_mvm_f32p.cuh)
@@ -1435,7 +1498,7 @@ int destroy_impl(cf_gramian_s* g) {
         if (sh.yn && sh.yn != sh.xn) dev_free(sh.yn);
         dev_free(sh.xn);
         sh.a.release(); sh.y.release(); sh.partial.release(); sh.apad.release(); sh.ypad.release(); sh.at.release(); sh.sym_items.release(); sh.bsym.release(); sh.sym_col.release(); sh.bd_t.release(); sh.bd_s.release();
-        sh.xp.release(); sh.yp.release(); sh.ap.release(); sh.yc_hi.release(); sh.yc_lo.release(); sh.yc_n.release(); sh.ac_hi.release(); sh.ac_lo.release(); sh.yt.release();
+        sh.xp.release(); sh.yp.release(); sh.ap.release(); sh.yc_hi.release(); sh.yc_lo.release(); sh.yc_n.release(); sh.ac_hi.release(); sh.ac_lo.release(); sh.yt.release(); sh.au.release();
         for (auto& b : sh.cg) b.release();
         if (sh.ev0) cudaEventDestroy(sh.ev0);
         if (sh.ev1) cudaEventDestroy(sh.ev1);
@@ -2188,7 +2251,8 @@ int cf_jit_check(const cf_knode_t* prog, int nnodes, int d, int which, char* log
         case 6: header = "gram_mm_tf32.cuh"; name = "gram_mm_tf32_kernel<" + sD + ">"; break;
         case 4: header = "gram_mvm_tf32.cuh"; name = "gram_mvm_tf32_kernel<" + sD + ", " + sop + ">"; break;
         case 5: header = "grad_mvm_dmma.cuh"; name = "grad_mvm_dmma_kernel<" + sD + ", " + sop + ", false, 0>"; break;
-        default: return fail(CF_ERR_BAD_ARGUMENT, "cf_jit_check: which must be 0..6");
+        case 7: header = "gram_mvm_tc5.cuh"; name = "gram_mvm_tc5_kernel<" + sD + ", " + sop + ">"; break;
+        default: return fail(CF_ERR_BAD_ARGUMENT, "cf_jit_check: which must be 0..7");
     }
     cf_sop_grad sop_grad;
     const bool want_grad = which == 5;

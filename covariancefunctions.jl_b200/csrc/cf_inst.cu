@@ -58,6 +58,8 @@ const cf_kernel_entry entry = {
     cf_mvme_entry<D>::cfg,
     {cf_mvp_entry<D>::fn[0], cf_mvp_entry<D>::fn[1], cf_mvp_entry<D>::fn[2]},
     cf_mvp_entry<D>::cfg,
+    {cf_mvu_entry<D>::fn[0], cf_mvu_entry<D>::fn[1], cf_mvu_entry<D>::fn[2], cf_mvu_entry<D>::fn[3]},
+    cf_mvu_entry<D>::cfg,
     {TU::R, TU::NT, TU::TJ, TU::NS, TU::MINB},
 };
 }  // namespace

@@ -12,6 +12,7 @@
 #include "gram_mvm_eq.cuh"
 #include "gram_mm_tc5.cuh"
 #include "gram_mvm_f32p.cuh"
+#include "gram_mvm_tc5.cuh"
 
 #define CF_NKINDS 4 /* EQ, MATERN, RQ_INT, SOP */
 inline int cf_kind_slot(int kind) {
@@ -53,6 +54,8 @@ struct cf_kernel_entry {
     cf_mvm_config mvm_eq_cfg;
     cf_mvm_launch_fn mvm_f32p[3]; // Float32 value MVM in packed FP32 arithmetic (gram_mvm_f32p.cuh): EQ, MaternP, RQ_INT; nullptr for D > 8
     cf_mvm_config mvm_f32p_cfg;
+    cf_mvu_launch_fn mvm_tc5[CF_NKINDS]; // Float32 value MVM with the dot products on tcgen05 / TMEM in 3xTF32 (gram_mvm_tc5.cuh), nullptr for D < 8
+    cf_mvm_config mvm_tc5_cfg;
     int tune[5];                     // R, NT, TJ, NS, MINB of the value MVM kernel (names the instantiation for cf_jit.h)
 };
 

@@ -138,6 +138,10 @@ __device__ __forceinline__ void cf_tmem_st16(uint32_t taddr, const uint32_t (&v)
                    "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
                  : "memory");
 }
+__device__ __forceinline__ void cf_tmem_st8(uint32_t taddr, const uint32_t (&v)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]) : "memory");
+}
 template <int N> __device__ __forceinline__ void cf_tmem_ld(uint32_t taddr, uint32_t (&v)[N]) {
     if constexpr (N == 32) cf_tmem_ld32(taddr, v); else cf_tmem_ld16(taddr, v);
 }

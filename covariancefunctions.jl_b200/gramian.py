@@ -356,7 +356,7 @@ def jit_stats():
     return {"compiled": c.value, "cache_hits": h.value, "failures": f.value, "compile_seconds": t.value}
 
 
-JIT_KERNELS = {"mvm": 0, "mm_dmma": 1, "mvm_dmma": 2, "mm_tf32": 3, "mvm_tf32": 4, "grad_dmma": 5}
+JIT_KERNELS = {"mvm": 0, "mm_dmma": 1, "mvm_dmma": 2, "mm_tf32": 3, "mvm_tf32": 4, "grad_dmma": 5, "mm_tf32_legacy": 6, "mvm_tc5": 7}
 
 
 def jit_check(kernel, d: int, which: str = "mvm"):

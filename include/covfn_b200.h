@@ -232,7 +232,8 @@ int cf_peak_probe(int kind, int iters, double* lane_ops_per_s, float* ms);
 int cf_jit_stats(int* compiled, int* cache_hits, int* failures, double* compile_seconds);
 /* Compile (only) the run-time specialisation of one kernel for a program, without a GPU: the "does the generated code build"
  * check.  which: 0 value MVM (K1), 1 Float64 tensor-core multi-RHS (K4d), 2 Float64 tensor-core MVM (K1d), 3 Float32 3xTF32
- * multi-RHS (K4t), 4 Float32 3xTF32 MVM (K1t), 5 Float64 tensor-core gradient MVM with generated jets (K5d); d = point dimension.  log (may be NULL) receives the NVRTC log and, on failure,
+ * multi-RHS on tcgen05 (K4u), 4 Float32 3xTF32 MVM with mma.sync (K1t), 5 Float64 tensor-core gradient MVM with generated jets (K5d),
+ * 6 Float32 3xTF32 multi-RHS with mma.sync (K4t), 7 Float32 3xTF32 MVM on tcgen05 (K1u); d = point dimension.  log (may be NULL) receives the NVRTC log and, on failure,
  * the generated evaluator.  CF_ERR_UNSUPPORTED if NVRTC is missing or the kernel does not exist for this d. */
 int cf_jit_check(const cf_knode_t* prog, int nnodes, int d, int which, char* log, int loglen);
 

@@ -13,6 +13,14 @@ pytestmark = pytest.mark.gpu
 TOL32 = 1e-5
 
 
+@pytest.fixture(autouse=True)
+def _legacy_kernel():
+    """This file covers the mma.sync kernel, which the tcgen05 one (tests/test_gpu_mvm_tc5.py) has replaced as the default."""
+    os.environ["COVFN_MVM_LEGACY"] = "1"
+    yield
+    del os.environ["COVFN_MVM_LEGACY"]
+
+
 def _scalar(fn):
     os.environ["COVFN_MVM_SCALAR"] = "1"
     try:
@@ -47,8 +55,8 @@ def test_mvm_tf32_dims_ragged_rectangular(cf, O, d):
         assert relerr(b.astype(np.float64), truth) < TOL32, (d, name)
         bs = _scalar(lambda: G @ a)
         assert relerr(bs.astype(np.float64), truth) < TOL32, (d, name)
-        if name == "exp":
-            assert np.array_equal(b, bs)
+        if name == "exp":  # both are direct-difference kernels (d = 8: the packed-FP32 one, tests/test_gpu_f32p.py)
+            assert relerr(b, bs) < 2e-6
         elif name == "eq":
             assert not np.array_equal(b, bs), "expected the tensor-core kernel"
 

@@ -29,6 +29,73 @@ __device__ __forceinline__ uint64_t cf_fma2(uint64_t a, uint64_t b, uint64_t c) 
     return r;
 }
 
+__device__ __forceinline__ float cf_sqrtf_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+
+// k(r2) of a single isotropic atom for N PAIRS of entries (packed halves), the kind dispatched once: every stage is issued for all N
+// pairs, the Horner / power loops over the atom's integer parameter run once.  r2 >= 0 up to rounding; NONNEG = false clamps at 0
+// (r2 from the norm expansion), CLAMP = true bounds g = sqrt(r2) so that M(g) never overflows before exp(c g) has flushed to 0.
+// MaternP: one MUFU.SQRT and one MUFU.EX2 per entry, everything else packed (src/stationary.jl:148-157 in Float32).
+template <int KIND, int N, bool NONNEG, bool CLAMP>
+__device__ __forceinline__ void cf_atom_value_f32x2_n(const uint64_t (&r2)[N], const cf_atom_val& A, uint64_t (&kv)[N]) {
+    if constexpr (KIND == CF_ATOM_EQ) {
+        const uint64_t cl2 = cf_pk2(A.f_clog2e, A.f_clog2e);
+#pragma unroll
+        for (int u = 0; u < N; u++) {
+            float lo, hi;
+            cf_upk2(cf_mul2(r2[u], cl2), lo, hi);
+            kv[u] = cf_pk2(cf_ex2f(lo), cf_ex2f(hi));
+        }
+    } else if constexpr (KIND == CF_ATOM_MATERN) {
+        const uint64_t cl2 = cf_pk2(A.f_clog2e, A.f_clog2e);
+        uint64_t g2[N], e2[N];
+#pragma unroll
+        for (int u = 0; u < N; u++) {
+            float lo, hi;
+            cf_upk2(r2[u], lo, hi);
+            if (!NONNEG) { lo = fmaxf(lo, 0.f); hi = fmaxf(hi, 0.f); }
+            lo = cf_sqrtf_approx(lo); hi = cf_sqrtf_approx(hi);
+            if (CLAMP) { lo = fminf(lo, A.f_gmax); hi = fminf(hi, A.f_gmax); }
+            g2[u] = cf_pk2(lo, hi);
+            cf_upk2(cf_mul2(g2[u], cl2), lo, hi);
+            e2[u] = cf_pk2(cf_ex2f(lo), cf_ex2f(hi));
+        }
+        const int p = A.p;
+        if (p == 0) {
+#pragma unroll
+            for (int u = 0; u < N; u++) kv[u] = e2[u];
+        } else {
+            uint64_t mp[N];
+            const uint64_t top = cf_pk2(A.f_mat[p], A.f_mat[p]);
+#pragma unroll
+            for (int u = 0; u < N; u++) mp[u] = top;
+#pragma unroll 1
+            for (int i = p - 1; i >= 0; i--) {
+                const uint64_t ci = cf_pk2(A.f_mat[i], A.f_mat[i]);
+#pragma unroll
+                for (int u = 0; u < N; u++) mp[u] = cf_fma2(mp[u], g2[u], ci);
+            }
+#pragma unroll
+            for (int u = 0; u < N; u++) kv[u] = cf_mul2(mp[u], e2[u]);
+        }
+    } else {  // CF_ATOM_RQ_INT: (1 + w r2)^-p
+        const uint64_t w2 = cf_pk2(A.f_w, A.f_w), one2 = cf_pk2(1.f, 1.f);
+        uint64_t ib[N];
+#pragma unroll
+        for (int u = 0; u < N; u++) {
+            float lo, hi;
+            cf_upk2(cf_fma2(r2[u], w2, one2), lo, hi);
+            if (!NONNEG) { lo = fmaxf(lo, 1.f); hi = fmaxf(hi, 1.f); }
+            ib[u] = cf_pk2(cf_rcpf(lo), cf_rcpf(hi));
+            kv[u] = ib[u];
+        }
+#pragma unroll 1
+        for (int i = 1; i < A.p; i++) {
+#pragma unroll
+            for (int u = 0; u < N; u++) kv[u] = cf_mul2(kv[u], ib[u]);
+        }
+    }
+}
+
 #ifndef CF_MVP_UNROLL
 #define CF_MVP_UNROLL 2  // column pairs per loop body
 #endif
@@ -100,8 +167,6 @@ __global__ void __launch_bounds__(NT, MINB) gram_mvm_f32p_kernel(const __grid_co
     double tot[R];
 #pragma unroll
     for (int r = 0; r < R; r++) tot[r] = 0.0;
-    const uint64_t cl2 = cf_pk2(P.atom.f_clog2e, P.atom.f_clog2e);
-
     // one tile: TJ columns as TJ / 2 packed pairs; columns past the end of a ragged tile carry a_j = 0 (and zero points)
     auto compute = [&](const unsigned char* __restrict__ st) {
         const uint64_t* as2 = reinterpret_cast<const uint64_t*>(st + D * S::row_bytes);
@@ -124,21 +189,10 @@ __global__ void __launch_bounds__(NT, MINB) gram_mvm_f32p_kernel(const __grid_co
                     r2[r] = (c == 0) ? cf_mul2(df, df) : cf_fma2(df, df, r2[r]);
                 }
             }
-            if constexpr (KIND == CF_ATOM_EQ) {
+            uint64_t kv[R];
+            cf_atom_value_f32x2_n<KIND, R, true, true>(r2, P.atom, kv);
 #pragma unroll
-                for (int r = 0; r < R; r++) {
-                    float lo, hi;
-                    cf_upk2(cf_mul2(r2[r], cl2), lo, hi);
-                    acc[r] = cf_fma2(cf_pk2(cf_ex2f(lo), cf_ex2f(hi)), a2, acc[r]);
-                }
-            } else {
-                float rr[2 * R], dt[2 * R], kv[2 * R];
-#pragma unroll
-                for (int r = 0; r < R; r++) { cf_upk2(r2[r], rr[2 * r], rr[2 * r + 1]); dt[2 * r] = 0.f; dt[2 * r + 1] = 0.f; }
-                cf_atom_value_f32_n<2 * R>(rr, dt, P.atom, kv);
-#pragma unroll
-                for (int r = 0; r < R; r++) acc[r] = cf_fma2(cf_pk2(kv[2 * r], kv[2 * r + 1]), a2, acc[r]);
-            }
+            for (int r = 0; r < R; r++) acc[r] = cf_fma2(kv[r], a2, acc[r]);
         }
 #pragma unroll
         for (int r = 0; r < R; r++) {  // two-level summation as in K1: Float32 within a tile, Float64 across tiles

@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(CF_MVU_THREADS, 1) gram_mvm_tc5_kernel(const _
                     cf_upk2(cf_fma2(dot2, m2cl2, cf_fma2(yn2[u], cl2, cxn2)), lo, hi);
                     acc = cf_fma2(cf_pk2(cf_ex2f(lo), cf_ex2f(hi)), a2[u], acc);
                 }
-            } else {
+            } else if constexpr (KIND == CF_ATOM_SOP) {
 #pragma unroll
                 for (int g8 = 0; g8 < 4; g8++) {
                     float r2[8], dt[8], kv[8];
@@ -196,9 +196,22 @@ __global__ void __launch_bounds__(CF_MVU_THREADS, 1) gram_mvm_tc5_kernel(const _
                         r2[2 * u] = fmaxf(r2[2 * u], 0.f);
                         r2[2 * u + 1] = fmaxf(r2[2 * u + 1], 0.f);
                     }
-                    cf_values_f32_n<KIND, 8>(r2, dt, P.atom, P.sop, kv);
+                    cf_sop_value_f32_n<8>(r2, dt, P.sop, kv);
 #pragma unroll
                     for (int u = 0; u < 4; u++) acc = cf_fma2(cf_pk2(kv[2 * u], kv[2 * u + 1]), a2[4 * g8 + u], acc);
+                }
+            } else {  // single MaternP / RQ atom: packed evaluation, 8 column pairs at a time (points are well scaled here: no clamp of sqrt(r2))
+#pragma unroll
+                for (int g8 = 0; g8 < 2; g8++) {
+                    uint64_t r2[8], kv[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) {
+                        const uint64_t dot2 = cf_pk2(__uint_as_float(dv[16 * g8 + 2 * u]), __uint_as_float(dv[16 * g8 + 2 * u + 1]));
+                        r2[u] = cf_fma2(dot2, m2, cf_add2(yn2[8 * g8 + u], xn2));
+                    }
+                    cf_atom_value_f32x2_n<KIND, 8, false, false>(r2, P.atom, kv);
+#pragma unroll
+                    for (int u = 0; u < 8; u++) acc = cf_fma2(kv[u], a2[8 * g8 + u], acc);
                 }
             }
             __syncwarp();

@@ -22,7 +22,11 @@ RUNS = {
     "c3:f64": (["--config", "c3"], "gram_mm_dmma_kernel", {}),
     "c4:f64": (["--config", "c4"], "grad_mvm_dmma_kernel", {}),
     "c5:f64": (["--config", "x4", "--n", str(1 << 19)], "gram_mvm_sym_kernel", {}),
-    "c2:f32": (["--config", "c2", "--dtype", "f32"], "gram_mvm_kernel", {}),
+    "c2:f32": (["--config", "c2", "--dtype", "f32", "--n", "262144"], "gram_mvm_f32p_kernel", {}),  # (a sixteenth of the pairs: same rate, shorter capture)
+    "c2:f32:k1": (["--config", "c2", "--dtype", "f32"], "gram_mvm_kernel", {"COVFN_MVM_SCALAR": "1"}),
+    "x2:f32": (["--config", "x2", "--dtype", "f32"], "gram_mvm_tc5_kernel", {}),
+    "x2:f32:legacy": (["--config", "x2", "--dtype", "f32"], "gram_mvm_tf32_kernel", {"COVFN_MVM_LEGACY": "1"}),
+    "x3:f32": (["--config", "x3", "--dtype", "f32"], "gram_mvm_tc5_kernel", {}),
     "c3:f32": (["--config", "c3", "--dtype", "f32"], "gram_mm_tf32", {}),
 }
 only = sys.argv[1:]
@@ -63,6 +67,9 @@ for key, (argv, kregex, env) in RUNS.items():
         "kernel": d.get("Kernel Name", "")[:120], "duration_ms": dur_ms,
         "fp64_pipe_active_pct": num("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", False),
         "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active", False),
+        "pipe_xu_pct": num("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", False),    # MUFU
+        "pipe_fma_pct": num("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", False),
+        "pipe_alu_pct": num("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", False),
         "warps_active_pct": num("sm__warps_active.avg.pct_of_peak_sustained_active", False),
         "inst_executed": num("smsp__inst_executed.sum", False),
         "registers_per_thread": num("launch__registers_per_thread", False),

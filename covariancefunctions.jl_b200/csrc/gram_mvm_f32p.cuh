@@ -31,6 +31,25 @@ __device__ __forceinline__ uint64_t cf_fma2(uint64_t a, uint64_t b, uint64_t c) 
 
 __device__ __forceinline__ float cf_sqrtf_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 
+// 2^x for two values WITHOUT the MUFU pipe: n = round(x) by the magic-number addition, f = x - n in [-1/2, 1/2], degree-5 minimax polynomial
+// of 2^f (relative error 7.5e-8; 2.4e-7 with Float32 Horner rounding -- the same 2 ulp as ex2.approx), n added to the exponent field.
+// 3 FADD2 + 5 FFMA2 + 2 LEA for the pair.  Valid for -126 < x < 128 (no clamp: callers bound x).  Used for a FRACTION of the entries of
+// kernels whose MUFU pipe is saturated while the FMA pipe idles (gram_mvm_tc5.cuh), the softmax trick of recent attention kernels.
+__device__ __forceinline__ uint64_t cf_ex2_poly2(uint64_t x2) {
+    const uint64_t magic2 = cf_pk2(12582912.f, 12582912.f);  // 1.5 * 2^23
+    const uint64_t t2 = cf_add2(x2, magic2);
+    const uint64_t f2 = cf_sub2(x2, cf_sub2(t2, magic2));
+    uint64_t p2 = cf_fma2(cf_pk2(0.001327647129073739f, 0.001327647129073739f), f2, cf_pk2(0.009675541892647743f, 0.009675541892647743f));
+    p2 = cf_fma2(p2, f2, cf_pk2(0.05550713092088699f, 0.05550713092088699f));
+    p2 = cf_fma2(p2, f2, cf_pk2(0.24022120237350464f, 0.24022120237350464f));
+    p2 = cf_fma2(p2, f2, cf_pk2(0.6931469440460205f, 0.6931469440460205f));
+    p2 = cf_fma2(p2, f2, cf_pk2(1.0000001192092896f, 1.0000001192092896f));
+    float plo, phi, tlo, thi;
+    cf_upk2(p2, plo, phi);
+    cf_upk2(t2, tlo, thi);
+    return cf_pk2(__uint_as_float(__float_as_uint(plo) + (__float_as_uint(tlo) << 23)), __uint_as_float(__float_as_uint(phi) + (__float_as_uint(thi) << 23)));
+}
+
 // k(r2) of a single isotropic atom for N PAIRS of entries (packed halves), the kind dispatched once: every stage is issued for all N
 // pairs, the Horner / power loops over the atom's integer parameter run once.  r2 >= 0 up to rounding; NONNEG = false clamps at 0
 // (r2 from the norm expansion), CLAMP = true bounds g = sqrt(r2) so that M(g) never overflows before exp(c g) has flushed to 0.

@@ -24,6 +24,16 @@
 #define CF_MVU_NB 4                        // TMEM dot buffers (64 columns each)
 #define CF_MVU_EW 16                       // evaluation warps: two groups of 8 that take alternate column tiles
 #define CF_MVU_THREADS (32 * CF_MVU_EW + 64)   // + TMA producer warp, MMA issuer warp
+// EQ: which of a thread's 16 column pairs per tile take their two exponentials from the polynomial cf_ex2_poly2 (FMA pipe) instead of
+// MUFU.EX2.  With every exponential on the MUFU pipe that pipe is 84 % busy and the FMA pipe ~37 % (profiles/r2_ncu_x2_f32.md), and per
+// column pair the MUFU path costs 16 MUFU cycles + 6 FMA-pipe cycles against 22 FMA-pipe cycles for the polynomial, so on paper the pipes
+// balance at 5 of 16 pairs.  MEASURED (n = 131072, bench_aux/micro/mvu_variants.sh): d = 8: 4.73 ms with none, 4.64 with 1 pair, 4.53
+// with 3, 4.79 with 5; d = 32: 5.10 / 5.29 / 5.39 / 5.42 ms -- the extra ~10 issue slots per pair cost more than the MUFU cycles they
+// free once the tile hand-over (tcgen05.ld, mbarriers) shares the issue port.  Off by default; kept for kernels with a heavier MUFU load.
+// (The exponent c log2(e) r2 stays above -126 here: these kernels run only on points that passed the scale check, capi.cu set_norm_flags.)
+#ifndef CF_MVU_POLY_MASK
+#define CF_MVU_POLY_MASK 0x0u  // e.g. 0x1084u: pairs 2, 7, 12
+#endif
 
 template <int D>
 struct cf_mvu_layout {
@@ -178,9 +188,14 @@ __global__ void __launch_bounds__(CF_MVU_THREADS, 1) gram_mvm_tc5_kernel(const _
 #pragma unroll
                 for (int u = 0; u < 16; u++) {
                     const uint64_t dot2 = cf_pk2(__uint_as_float(dv[2 * u]), __uint_as_float(dv[2 * u + 1]));
-                    float lo, hi;
-                    cf_upk2(cf_fma2(dot2, m2cl2, cf_fma2(yn2[u], cl2, cxn2)), lo, hi);
-                    acc = cf_fma2(cf_pk2(cf_ex2f(lo), cf_ex2f(hi)), a2[u], acc);
+                    const uint64_t arg2 = cf_fma2(dot2, m2cl2, cf_fma2(yn2[u], cl2, cxn2));
+                    if ((CF_MVU_POLY_MASK >> u) & 1) {  // this column pair's exponentials on the FMA pipe (see CF_MVU_POLY_MASK)
+                        acc = cf_fma2(cf_ex2_poly2(arg2), a2[u], acc);
+                    } else {
+                        float lo, hi;
+                        cf_upk2(arg2, lo, hi);
+                        acc = cf_fma2(cf_pk2(cf_ex2f(lo), cf_ex2f(hi)), a2[u], acc);
+                    }
                 }
             } else if constexpr (KIND == CF_ATOM_SOP) {
 #pragma unroll

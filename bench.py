@@ -39,6 +39,9 @@ sys.path.insert(0, ROOT)
 SLOTS = {"c1": 35, "c2": 23, "c3": 111, "c4": 97, "c5": 45, "x1": 80, "x2": 81, "x3": 61, "x4": 45, "x5": 110, "x6": 125, "x7": 33}  # FP64 issue slots per pair/block
 
 
+MUFU_PER_PAIR = {"c1": 2, "c2": 1, "c3": 1, "x2": 1, "x3": 2, "x4": 2, "x7": 1}  # Float32 kernels: MUFU operations per evaluated entry
+
+
 def workload(name):
     import covfn_b200 as cf
 
@@ -535,6 +538,7 @@ def roofline_block(cf, args, w, world, kernel_ms, my_pairs, alg_bytes):
         "fp64_pipe_active": (rec or {}).get("fp64_pipe_active_pct"),
         "issue_active": (rec or {}).get("issue_active_pct"),
         "ncu_source": (rec or {}).get("source"),
+        "ncu_captured_n": (rec or {}).get("captured_n"),  # set when the recorded pass ran the same kernel at a smaller n (traffic is per launch at that n)
         "peak_lane_fma_per_clk_per_sm": peak_lane_ops / 148.0 / (sm_mhz * 1e6),
         "note": "frac = reference-slot work (SURVEY.md 8d) / measured FMA peak: implementation independent, can exceed 1 when the kernel "
                 "needs fewer instructions than the reference sequence (EQ d=3: 12 FP64 instructions per pair against 23 slots); "
@@ -546,8 +550,19 @@ def roofline_block(cf, args, w, world, kernel_ms, my_pairs, alg_bytes):
                 "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"},
     }
     if not f64:
+        # Float32: the transcendental of every entry is one (EQ: ex2; RQ with integer alpha: rcp) or two (MaternP: sqrt, ex2) MUFU
+        # operations and the MUFU pipe (16 lanes per clock and SM), not the FMA pipe, is the binding unit of the value kernels
+        # (profiles/r2_ncu_c2_f32.md, r2_ncu_x2_f32.md: pipe_xu 84-86 % busy); reported as its own fraction
         mufu, _ = cf.peak_probe("mufu", 1 << 15)
+        per_pair = MUFU_PER_PAIR.get(args.config)
         rl["mufu_peak_lane_ops_per_s"] = mufu
+        if per_pair:
+            ach = per_pair * my_pairs / (kernel_ms * 1e-3)
+            rl["mufu"] = {"ops_per_pair": per_pair, "achieved_lane_ops_per_s": ach, "peak_lane_ops_per_s": mufu, "frac": ach / mufu,
+                          "pipe_xu_active": (rec or {}).get("pipe_xu_pct"), "pipe_fma_inst_active": (rec or {}).get("pipe_fma_pct")}
+        rl["note"] = ("frac = reference-slot work (SURVEY.md 8d) / measured FP32 FMA peak: implementation independent, exceeds 1 because the "
+                      "reference sequence charges 16 slots for an exp that is one MUFU.EX2 here; the binding unit is the MUFU pipe: see `mufu`")
+        rl["peak_source"] = "cf_peak_probe FFMA / MUFU.EX2 microbenchmarks in this run; MEASURED_PEAKS.json has no FP32 FMA or MUFU entry"
     return rl
 
 

@@ -25,11 +25,17 @@ for d in (3, 16):
     (1e-2 * cf.I(n) + Gs).solve(rng.standard_normal(n), maxiter=5)
 Xf = rng.standard_normal((300, 3)).astype(np.float32)
 cf.gramian(cf.EQ(), Xf.T) @ rng.standard_normal(300).astype(np.float32)
-Xf16 = (rng.standard_normal((515, 16)) / 4).astype(np.float32)  # Float32, d = 16: the 3xTF32 tensor-core kernels
+for k in (cf.MaternP(2), cf.RQ(2)):  # packed-FP32 kernel (gram_mvm_f32p.cuh), ragged against its 128-column tile
+    cf.gramian(k, Xf.T, Xf[:211].T) @ rng.standard_normal(211).astype(np.float32)
+cf.gramian(cf.GradientKernel(cf.EQ()), Xf.T) @ rng.standard_normal(900).astype(np.float32)  # Float64 shadow of a Float32 handle
+Xf16 = (rng.standard_normal((515, 16)) / 4).astype(np.float32)  # Float32, d = 16: the tcgen05 kernels (gram_mm_tc5.cuh, gram_mvm_tc5.cuh)
 for k in (cf.EQ(), cf.MaternP(2), 0.5 * cf.RQ(2) + cf.Dot() ** 2):
     Gf = cf.gramian(k, Xf16.T, Xf16[:300].T)
     Gf @ rng.standard_normal(300).astype(np.float32)
     Gf @ rng.standard_normal((300, 5)).astype(np.float32)
+# many column tiles per CTA: the TMA stage ring and the TMEM buffers of the tcgen05 value kernel are re-used several times
+Xl = (rng.standard_normal((128 * 150, 16)) / 4).astype(np.float32)
+cf.gramian(cf.EQ(), Xl.T, Xl[:1500].T) @ rng.standard_normal(1500).astype(np.float32)
 Xb = rng.standard_normal((150, 40)) / 6
 cf.gramian(cf.EQ(), Xb.T) @ rng.standard_normal(150)
 cf.gramian(cf.GradientKernel(cf.EQ()), Xb.T) @ rng.standard_normal(150 * 40)

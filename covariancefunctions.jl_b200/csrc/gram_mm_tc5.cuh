@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(CF_MMU_THREADS, 1) gram_mm_tc5_kernel(const __
     const int ntiles = (int)PP.ntiles;
 
     if (tid == 0) {
-        for (int s = 0; s < NS; s++) { cf_mbar_init(&full[s], 1); cf_mbar_init(&empty[s], 1); }
+        for (int s = 0; s < NS; s++) { cf_mbar_init(&full[s], 1); cf_mbar_init(&empty[s], 1 + CF_MMU_GW); }  // phase-B commit + the tile's evaluation warps
         for (int b = 0; b < 2; b++) {  // one arrival per evaluation warp of the group
             cf_mbar_init(&dotfull[b], 1); cf_mbar_init(&dotfree[b], CF_MMU_GW);
             cf_mbar_init(&kfull[b], CF_MMU_GW); cf_mbar_init(&outfull[b], 1); cf_mbar_init(&outfree[b], CF_MMU_GW);
@@ -322,6 +322,9 @@ __global__ void __launch_bounds__(CF_MMU_THREADS, 1) gram_mm_tc5_kernel(const __
         int last = -1;
         for (int t = grp; t < ntiles; t += 2) {
             const int s = t % NS;
+            // |y|^2 of the tile is read from the stage below: observe the TMA completion directly (it happened long ago -- the MMA issuer
+            // waited for it before the distance GEMM -- but only a wait on full[s] orders the bulk copy's writes before THIS thread's reads)
+            cf_mbar_wait(&full[s], (uint32_t)((t / NS) & 1));
             cf_mbar_wait(&dotfull[grp], (uint32_t)((t >> 1) & 1));
             cf_tc_fence_after();
             uint32_t dv[CW];
@@ -356,7 +359,10 @@ __global__ void __launch_bounds__(CF_MMU_THREADS, 1) gram_mm_tc5_kernel(const __
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             cf_tc_fence_before();
             __syncwarp();
-            if (lane == 0) cf_mbar_arrive(&kfull[grp]);
+            if (lane == 0) {
+                cf_mbar_arrive(&kfull[grp]);
+                cf_mbar_arrive(&empty[s]);  // this warp has read the stage's |y|^2 (the tensor core's share arrives with the phase-B commit)
+            }
             last = t;
         }
         if (last >= 0) drain_out(last);

@@ -11,7 +11,7 @@
 //
 //   per row tile of 128 rows and column chunk (one CTA), per column tile of TJ = 64 points:
 //   TMA producer        Yhi | Ylo images, |y|^2, a  -> stage s                              4 bulk copies, full[s]
-//   MMA issuer          Dot (128 x 64) = Xlo Yhi^T + Xhi Ylo^T + Xhi Yhi^T  -> TMEM dot[t % 4]    dotfull[t % 4]; Y images free: empty[s]
+//   MMA issuer          Dot (128 x 64) = Xlo Yhi^T + Xhi Ylo^T + Xhi Yhi^T  -> TMEM dot[t % 4]    dotfull[t % 4]
 //   evaluation group t & 1 (8 warps: TMEM lane quarter x column half)  tcgen05.ld -> dotfree, kernel, acc2 += k2 a2, empty[s]
 // Row sums: Float32 within a tile (16 terms per accumulator half), Float64 across tiles, as in K1 / K1t.
 #pragma once
@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(CF_MVU_THREADS, 1) gram_mvm_tc5_kernel(const _
     const int ntiles = (int)((c1 + TJ - 1) / TJ - tile0);
 
     if (tid == 0) {
-        for (int s = 0; s < NS; s++) { cf_mbar_init(&full[s], 1); cf_mbar_init(&empty[s], 1 + GW); }  // MMA commit + the tile's evaluation warps
+        for (int s = 0; s < NS; s++) { cf_mbar_init(&full[s], 1); cf_mbar_init(&empty[s], GW); }  // the tile's evaluation warps (see below)
         for (int b = 0; b < NB; b++) { cf_mbar_init(&dotfull[b], 1); cf_mbar_init(&dotfree[b], GW); }
         cf_fence_barrier_init();
     }
@@ -151,8 +151,8 @@ __global__ void __launch_bounds__(CF_MVU_THREADS, 1) gram_mvm_tc5_kernel(const _
                     for (int ks = 0; ks < DK / 8; ks++)
                         cf_umma_tf32_ta(tmem + 64 * b, xa + 8 * ks, yb + (uint64_t)((ks * 2 * LBO_Y) >> 4), idesc, (pr > 0 || ks > 0) ? 1u : 0u);
                 }
-                cf_umma_commit(&dotfull[b]);
-                cf_umma_commit(&empty[s]);  // the tensor core is done with the stage's point images
+                cf_umma_commit(&dotfull[b]);  // (also what frees the stage's point images: the evaluation warps arrive on empty[s] only after they
+                                              // have seen dotfull[b], i.e. after every MMA that reads the stage has completed)
             }
             __syncwarp();
         }

@@ -108,6 +108,32 @@ def test_runtime_specialised_and_tensor_core_kernels_on_two_devices(cf, O, two_g
     assert relerr(b3, O.mul_vec(k.program(), X3, a)) < 1e-12
 
 
+def test_float32_value_kernels_on_two_devices(cf, O, two_gpus):
+    """the Float32 value kernels keep one transposed / canonical point copy per device: packed FP32 (d = 3), tcgen05 (d = 16), and the
+    Float64 shadow of a Float32 handle (gradient operator, CG)"""
+    rng = np.random.default_rng(78)
+    n, m = 2901, 1777
+    for d in (3, 16):
+        X = (rng.standard_normal((n, d)) / np.sqrt(d)).astype(np.float32)
+        Y = (rng.standard_normal((m, d)) / np.sqrt(d)).astype(np.float32)
+        a = rng.standard_normal(m).astype(np.float32)
+        for k in (cf.EQ(), cf.MaternP(2)):
+            G = cf.gramian(k, X.T.copy(), Y.T.copy())
+            truth = O.mul_vec(k.program(), X.astype(np.float64), a.astype(np.float64), Y=Y.astype(np.float64))
+            b = G @ a
+            assert relerr(b.astype(np.float64), truth) < 1e-5, (d, k)
+            assert np.array_equal(b, G @ a)
+    Xg = (rng.standard_normal((400, 4)) / 2).astype(np.float32)
+    ag = rng.standard_normal(400 * 4).astype(np.float32)
+    Gg = cf.gramian(cf.GradientKernel(cf.EQ()), Xg.T.copy())
+    assert relerr(Gg @ ag, O.gradient_mul(cf.EQ().program(), Xg.astype(np.float64), ag.astype(np.float64))) < 1e-5
+    Xc = (rng.standard_normal((900, 3)) * 3).astype(np.float32)
+    y = rng.standard_normal(900).astype(np.float32)
+    x, iters, res = (0.5 * cf.I(900) + cf.gramian(cf.MaternP(2), Xc.T.copy())).solve(y)
+    Kd = O.matrix(cf.MaternP(2).program(), Xc.astype(np.float64)) + 0.5 * np.eye(900)
+    assert np.linalg.norm(Kd @ x - y) < 1e-3 * np.linalg.norm(y)
+
+
 def test_symmetric_variant_over_two_devices(cf, O, two_gpus):
     """y === x on several devices of one process: every device evaluates the unordered pairs of its row tiles, the partial vectors
     are summed with peer loads in device order (csrc/capi.cu mul_host_sym_spmd); bit-reproducible."""

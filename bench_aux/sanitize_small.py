@@ -34,8 +34,9 @@ for k in (cf.EQ(), cf.MaternP(2), 0.5 * cf.RQ(2) + cf.Dot() ** 2):
     Gf @ rng.standard_normal(300).astype(np.float32)
     Gf @ rng.standard_normal((300, 5)).astype(np.float32)
 # many column tiles per CTA: the TMA stage ring and the TMEM buffers of the tcgen05 value kernel are re-used several times
-Xl = (rng.standard_normal((128 * 150, 16)) / 4).astype(np.float32)
-cf.gramian(cf.EQ(), Xl.T, Xl[:1500].T) @ rng.standard_normal(1500).astype(np.float32)
+# (300 row tiles x 3 column chunks of 16 tiles each; the ring has 4 stages)
+Xl = (rng.standard_normal((128 * 300, 16)) / 4).astype(np.float32)
+cf.gramian(cf.EQ(), Xl.T, Xl[:3000].T) @ rng.standard_normal(3000).astype(np.float32)
 Xb = rng.standard_normal((150, 40)) / 6
 cf.gramian(cf.EQ(), Xb.T) @ rng.standard_normal(150)
 cf.gramian(cf.GradientKernel(cf.EQ()), Xb.T) @ rng.standard_normal(150 * 40)

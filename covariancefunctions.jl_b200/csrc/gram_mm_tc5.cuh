@@ -180,7 +180,7 @@ __global__ void __launch_bounds__(CF_MMU_THREADS, 1) gram_mm_tc5_kernel(const __
     const int ntiles = (int)PP.ntiles;
 
     if (tid == 0) {
-        for (int s = 0; s < NS; s++) { cf_mbar_init(&full[s], 1); cf_mbar_init(&empty[s], 1 + CF_MMU_GW); }  // phase-B commit + the tile's evaluation warps
+        for (int s = 0; s < NS; s++) { cf_mbar_init(&full[s], 1); cf_mbar_init(&empty[s], 1 + 32 * CF_MMU_GW); }  // phase-B commit + every thread of the tile's evaluation group
         for (int b = 0; b < 2; b++) {  // one arrival per evaluation warp of the group
             cf_mbar_init(&dotfull[b], 1); cf_mbar_init(&dotfree[b], CF_MMU_GW);
             cf_mbar_init(&kfull[b], CF_MMU_GW); cf_mbar_init(&outfull[b], 1); cf_mbar_init(&outfree[b], CF_MMU_GW);
@@ -359,10 +359,11 @@ __global__ void __launch_bounds__(CF_MMU_THREADS, 1) gram_mm_tc5_kernel(const __
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             cf_tc_fence_before();
             __syncwarp();
-            if (lane == 0) {
-                cf_mbar_arrive(&kfull[grp]);
-                cf_mbar_arrive(&empty[s]);  // this warp has read the stage's |y|^2 (the tensor core's share arrives with the phase-B commit)
-            }
+            if (lane == 0) cf_mbar_arrive(&kfull[grp]);
+            // this thread has read the stage's |y|^2 (the tensor core's share arrives with the phase-B commit).  Every lane arrives itself:
+            // lane 0 arriving after __syncwarp orders the same accesses, but compute-sanitizer's racecheck only follows a thread's OWN
+            // arrival (profiles/r2_sanitizer.txt), and a warp-wide arrive costs the same one instruction.
+            cf_mbar_arrive(&empty[s]);
             last = t;
         }
         if (last >= 0) drain_out(last);

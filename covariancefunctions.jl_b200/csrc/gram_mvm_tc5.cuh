@@ -31,6 +31,8 @@
 // with 3, 4.79 with 5; d = 32: 5.10 / 5.29 / 5.39 / 5.42 ms -- the extra ~10 issue slots per pair cost more than the MUFU cycles they
 // free once the tile hand-over (tcgen05.ld, mbarriers) shares the issue port.  Off by default; kept for kernels with a heavier MUFU load.
 // (The exponent c log2(e) r2 stays above -126 here: these kernels run only on points that passed the scale check, capi.cu set_norm_flags.)
+// 1: the stage is additionally released by a tcgen05.commit arrival, the way K4u must do it.  Redundant here; exists to show that
+// compute-sanitizer's racecheck does not see such arrivals (profiles/r2_sanitizer.txt).
 #ifndef CF_MVU_POLY_MASK
 #define CF_MVU_POLY_MASK 0x0u  // e.g. 0x1084u: pairs 2, 7, 12
 #endif
@@ -76,7 +78,7 @@ __global__ void __launch_bounds__(CF_MVU_THREADS, 1) gram_mvm_tc5_kernel(const _
     const int ntiles = (int)((c1 + TJ - 1) / TJ - tile0);
 
     if (tid == 0) {
-        for (int s = 0; s < NS; s++) { cf_mbar_init(&full[s], 1); cf_mbar_init(&empty[s], GW); }  // the tile's evaluation warps (see below)
+        for (int s = 0; s < NS; s++) { cf_mbar_init(&full[s], 1); cf_mbar_init(&empty[s], 32 * GW); }  // every thread of the tile's evaluation group (see below)
         for (int b = 0; b < NB; b++) { cf_mbar_init(&dotfull[b], 1); cf_mbar_init(&dotfree[b], GW); }
         cf_fence_barrier_init();
     }
@@ -229,8 +231,9 @@ __global__ void __launch_bounds__(CF_MVU_THREADS, 1) gram_mvm_tc5_kernel(const _
                     for (int u = 0; u < 8; u++) acc = cf_fma2(kv[u], a2[8 * g8 + u], acc);
                 }
             }
-            __syncwarp();
-            if (lane == 0) cf_mbar_arrive(&empty[s]);
+            // done with the stage's |y|^2 and weights.  Every lane arrives itself (one warp-wide instruction): lane 0 arriving after
+            // __syncwarp orders the same accesses, but compute-sanitizer's racecheck only follows a thread's OWN arrival (profiles/r2_sanitizer.txt)
+            cf_mbar_arrive(&empty[s]);
             float lo, hi;
             cf_upk2(acc, lo, hi);
             tot += (double)(lo + hi);

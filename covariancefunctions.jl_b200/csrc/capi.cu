@@ -156,6 +156,7 @@ struct cf_gramian_s {
     bool use_norms = false; // multi-RHS kernel may use r2 = |x|^2 + |y|^2 - 2 x.y (well-scaled data, d >= 8)
     bool use_norms_grad = false; // ... and so may the isotropic gradient operator (stricter: needs k'')
     bool eq_fast = false;   // single EQ atom, any d: norm expansion error < 1e-13 and |c| (|x| + |y|)^2 < 600 (gram_mvm_eq.cuh)
+    bool mat_fast = false;  // single MaternP atom, p >= 1, any d: norm expansion error < 1e-13 and |c| (|x| + |y|) < 600 (gram_mvm_eq.cuh, FAST = 2)
     int64_t row_begin = 0, row_end = 0;
     cf_program prog;
     cf_sop_val sop_val;    // parameter-resident program for the value kernels
@@ -932,7 +933,8 @@ int launch_mvm_sym(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin,
     if (!peers) peers = &no_peers;
     const int64_t n = g->n;
     const bool eqf = g->eq_fast && g->entry->sym_eq != nullptr && !env_flag("COVFN_MVM_SCALAR");
-    const cf_mvm_config& cfg = eqf ? g->entry->mvm_eq_cfg : g->entry->mvm_cfg[CF_F64];
+    const bool matf = g->mat_fast && g->entry->sym_mat != nullptr && g->entry->mvm_mat != nullptr && !env_flag("COVFN_MVM_SCALAR");
+    const cf_mvm_config& cfg = eqf ? g->entry->mvm_eq_cfg : (matf ? g->entry->mvm_mat_cfg : g->entry->mvm_cfg[CF_F64]);
     const int64_t TR = cfg.rows_per_cta, TJ = cfg.tj;
     const int64_t T = (n + TR - 1) / TR;
     if (sh.sym_nitems < 0 || sh.sym_tr != TR || sh.sym_part != part || sh.sym_parts != parts) { // build the (row tile, column chunk) list once
@@ -977,7 +979,7 @@ int launch_mvm_sym(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin,
     const long double lam = 0.693147180559945309417232121458176568L / 256.0L;
     P.eqc[0] = (double)lam; P.eqc[1] = (double)(lam * lam / 2); P.eqc[2] = (double)(lam * lam * lam / 6);
     P.eqc[3] = (double)(lam * lam * lam * lam / 24);
-    CF_CUDA((eqf ? g->entry->mvm_eq : g->entry->mvm[CF_F64][cf_kind_slot(g->kind)])(P, dim3((unsigned)T, 1), stream));
+    CF_CUDA((eqf ? g->entry->mvm_eq : (matf ? g->entry->mvm_mat : g->entry->mvm[CF_F64][cf_kind_slot(g->kind)]))(P, dim3((unsigned)T, 1), stream));
     // 2. everything beyond the diagonal blocks, each unordered pair once
     if (sh.sym_nitems > 0) {
         cf_sym_params S;
@@ -987,7 +989,7 @@ int launch_mvm_sym(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin,
         S.items = (const cf_sym_item*)sh.sym_items.p; S.n = n; S.use_tma = 1;
         S.atom = P.atom; S.sop = g->sop_val;
         for (int q = 0; q < 4; q++) S.eqc[q] = P.eqc[q];
-        CF_CUDA((eqf ? g->entry->sym_eq : g->entry->sym[cf_kind_slot(g->kind)])(S, sh.sym_nitems, stream));
+        CF_CUDA((eqf ? g->entry->sym_eq : (matf ? g->entry->sym_mat : g->entry->sym[cf_kind_slot(g->kind)]))(S, sh.sym_nitems, stream));
     }
     // 3. y = alpha (diag + row partials + column partials) + beta y, fixed summation order
     const int blocks = (int)std::min<int64_t>((n + 255) / 256, 8192);
@@ -1230,7 +1232,9 @@ int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const v
         return launch_mvm_f32p(g, sh, d_y, d_yin, d_a, alpha, beta, stream, peers);
     // single EQ atom on well-scaled Float64 points, small d: exponent formed in the scaled domain (gram_mvm_eq.cuh)
     const bool eqf = g->eq_fast && g->entry->mvm_eq != nullptr && !env_flag("COVFN_MVM_SCALAR");
-    Plan pl = make_plan(nrows, g->m, eqf ? g->entry->mvm_eq_cfg : cfg, sh.ctx->sms);
+    // ... and its MaternP form (p >= 1): r2 from the norm expansion, 6-instruction square root, clamp-free exp
+    const bool matf = g->mat_fast && g->entry->mvm_mat != nullptr && !env_flag("COVFN_MVM_SCALAR");
+    Plan pl = make_plan(nrows, g->m, eqf ? g->entry->mvm_eq_cfg : (matf ? g->entry->mvm_mat_cfg : cfg), sh.ctx->sms);
     cf_mvm_params P;
     std::memset(&P, 0, sizeof(P));
     P.X = sh.X; P.Y = sh.Y; P.a = d_a; P.xn = sh.xn; P.yn = sh.yn;
@@ -1241,7 +1245,7 @@ int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const v
     P.alpha = alpha * g->coef; P.beta = beta;
     P.use_tma = (((uintptr_t)d_a) % 16 == 0) ? 1 : 0;
     if (g->prog.single) P.atom = g->prog.atoms[g->prog.terms[0].fac[0].atom].v;
-    if (eqf) {
+    if (eqf || matf) {
         const long double lam = 0.693147180559945309417232121458176568L / 256.0L;
         P.eqc[0] = (double)lam; P.eqc[1] = (double)(lam * lam / 2); P.eqc[2] = (double)(lam * lam * lam / 6);
         P.eqc[3] = (double)(lam * lam * lam * lam / 24);
@@ -1266,7 +1270,7 @@ int launch_mvm(cf_gramian_s* g, Shard& sh, void* d_y, const void* d_yin, const v
             launched = cfjit::launch(jit, &P, (unsigned)pl.row_tiles, (unsigned)pl.chunks, (unsigned)tu[1], (unsigned)cfg.smem_bytes, stream) == 0;
     }
     if (!launched) {
-        cf_mvm_launch_fn fn = eqf ? g->entry->mvm_eq : g->entry->mvm[dt][cf_kind_slot(g->kind)];
+        cf_mvm_launch_fn fn = eqf ? g->entry->mvm_eq : (matf ? g->entry->mvm_mat : g->entry->mvm[dt][cf_kind_slot(g->kind)]);
         CF_CUDA(fn(P, dim3(pl.row_tiles, pl.chunks), stream));
     }
     g->last_launches++;
@@ -1482,6 +1486,14 @@ void set_norm_flags(cf_gramian_s* g, double max_sq) {
         // farthest pair, |c| (|x| + |y|)^2 <= 4 |c| max|x|^2, must stay clear of the 2^-1022 underflow (ln 2^-1022 = -708)
         g->eq_fast = dtype == CF_F64 && g->kind == CF_ATOM_EQ && (growth * eps * 2.0 * max_sq * slope < bound) &&
                      (4.0 * max_sq * slope < 600.0);
+        // the MaternP form of that kernel (FAST = 2): p >= 1 (p = 0 is exp(-sqrt(r2)), not differentiable in r2 at 0: an error of 1e-16 in
+        // r2 of coincident points would become 1e-8 in k), the same cancellation bound with the atom's largest slope |d_1| / l^2, and the
+        // exponent of the farthest pair, |c| (|x| + |y|) <= 2 |c| max|x|, clear of the underflow
+        g->mat_fast = false;
+        if (dtype == CF_F64 && g->kind == CF_ATOM_MATERN && g->prog.single) {
+            const cf_atom& A = g->prog.atoms[g->prog.terms[0].fac[0].atom];
+            g->mat_fast = A.v.p >= 1 && (growth * eps * 2.0 * max_sq * slope < bound) && (2.0 * std::sqrt(max_sq) * std::fabs(A.v.e.c) < 600.0);
+        }
     }
 }
 

@@ -36,9 +36,9 @@ const cf_kernel_entry entry = {
     {&cf_mm_launch<float, D, 512>, &cf_mm_launch<double, D, 256>},
     cf_mmd_entry<D>::fn,
     cf_mmd_entry<D>::smem,
-    {&cf_sym_launch<D, CF_ATOM_EQ, false, TU::R, TU::NT, TU::TJ, TU::NS, 1>, &cf_sym_launch<D, CF_ATOM_MATERN, false, TU::R, TU::NT, TU::TJ, TU::NS, 1>,
-     &cf_sym_launch<D, CF_ATOM_RQ_INT, false, TU::R, TU::NT, TU::TJ, TU::NS, 1>, &cf_sym_launch<D, CF_ATOM_SOP, false, TU::R, TU::NT, TU::TJ, TU::NS, 1>},
-    cf_sym_smem<D, TU::TJ, TU::NS, TU::NT / 32, false>::total,
+    {&cf_sym_launch<D, CF_ATOM_EQ, 0, TU::R, TU::NT, TU::TJ, TU::NS, 1>, &cf_sym_launch<D, CF_ATOM_MATERN, 0, TU::R, TU::NT, TU::TJ, TU::NS, 1>,
+     &cf_sym_launch<D, CF_ATOM_RQ_INT, 0, TU::R, TU::NT, TU::TJ, TU::NS, 1>, &cf_sym_launch<D, CF_ATOM_SOP, 0, TU::R, TU::NT, TU::TJ, TU::NS, 1>},
+    cf_sym_smem<D, TU::TJ, TU::NS, TU::NT / 32, 0>::total,
     cf_syme_entry<D>::fn,
     cf_syme_entry<D>::smem,
     {cf_mvd_entry<D>::fn[0], cf_mvd_entry<D>::fn[1], cf_mvd_entry<D>::fn[2], cf_mvd_entry<D>::fn[3]},
@@ -60,6 +60,10 @@ const cf_kernel_entry entry = {
     cf_mvp_entry<D>::cfg,
     {cf_mvu_entry<D>::fn[0], cf_mvu_entry<D>::fn[1], cf_mvu_entry<D>::fn[2], cf_mvu_entry<D>::fn[3]},
     cf_mvu_entry<D>::cfg,
+    cf_mvmm_entry<D>::fn,
+    cf_mvmm_entry<D>::cfg,
+    cf_symm_entry<D>::fn,
+    cf_symm_entry<D>::smem,
     {TU::R, TU::NT, TU::TJ, TU::NS, TU::MINB},
 };
 }  // namespace

@@ -56,6 +56,10 @@ struct cf_kernel_entry {
     cf_mvm_config mvm_f32p_cfg;
     cf_mvu_launch_fn mvm_tc5[CF_NKINDS]; // Float32 value MVM with the dot products on tcgen05 / TMEM in 3xTF32 (gram_mvm_tc5.cuh), nullptr for D < 8
     cf_mvm_config mvm_tc5_cfg;
+    cf_mvm_launch_fn mvm_mat;  // Float64 MaternP (p >= 1) value MVM from the norm expansion (gram_mvm_eq.cuh, FAST = 2), nullptr for D > 8
+    cf_mvm_config mvm_mat_cfg;
+    cf_sym_launch_fn sym_mat;  // ... and the symmetric variant with that evaluation (row tile = mvm_mat_cfg.rows_per_cta)
+    int sym_mat_smem;
     int tune[5];                     // R, NT, TJ, NS, MINB of the value MVM kernel (names the instantiation for cf_jit.h)
 };
 

@@ -17,8 +17,85 @@
 // No clamp: the host only selects this kernel when |c| (|x| + |y|)^2 < 700 for every pair (exponent field cannot wrap) and when
 // the cancellation error of the norm expansion, eps (|x|^2 + |y|^2) |c|, is below 1e-13 -- the same scale check that guards the
 // tensor-core kernels (capi.cu); otherwise K1 (direct differences, clamped) runs.
+//
+// FAST = 2 (round 2): the same skeleton for a single MaternP atom with p >= 1 (src/stationary.jl:134-158), "K1m".  What carries over is
+// the distance from the norm expansion (D FMAs + one add instead of 2 D), the clamp-free exp with the FMA-rounded exponent and the
+// two-instruction table scaling; what is new is a 6-instruction square root (MUFU.RSQ64H seed, one coupled Newton step, one residual
+// correction with the UNREFINED half-reciprocal, whose 2^-22 error only multiplies the 2^-44 residual) with the |.| and the underflow
+// guard as two integer instructions on the high word.  Per pair: D + 1 (r2) + 6 (sqrt) + 8 (exp) + p (Horner) + 2 = D + p + 17 FP64
+// instructions and ~6 others, against 2 D + 7 + 8 + p + 2 and ~15 in K1 (d = 3, p = 2: 22 + 6 against 25 + 15).  The host selects it
+// under the same kind of scale check as the EQ form (capi.cu set_norm_flags: mat_fast).  A slightly NEGATIVE r2 (cancellation at
+// (nearly) coincident points) is harmless: M(g) e^{-g} is even in g to third order for p >= 1, so sqrt(|r2|) ~ 1e-8 gives 1 - O(1e-16).
 #pragma once
 #include "gram_mvm.cuh"
+
+// MaternP values M(g) exp(c g), g = sqrt(|r2|), for R rows at once; r2 from the norm expansion.  No clamps (host-checked ranges).
+// c1 = 256 c / ln2 (A.e.c1), g0..g2 = the exp polynomial constants of this file (P.eqc), A.mat = Horner coefficients of M in g.
+// `magic` (= CF_MAGIC) and `top` (= A.mat[A.p]) are passed in REGISTERS the caller pins once per kernel: an FP64 instruction takes one
+// non-register operand, so fma(w, c1, CF_MAGIC) with both as constants made the compiler re-materialise one of them per use (4 extra
+// uniform-to-register moves per pair in the first version).
+template <int R>
+__device__ __forceinline__ void cf_matern_fast_n(const double (&r2)[R], const cf_atom_val& A, const double c1, const double g0, const double g1,
+                                                 const double g2, const double magic, const double top, cf_tbl_t tbl_lane, double (&kv)[R]) {
+    constexpr double g3 = 0x1.3b2ab00000000p-39;
+    double w[R], h[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        // the seed instruction (MUFU.RSQ64H) reads only the HIGH word: it gets max(|r2|, 2^-1007) formed with two integer instructions (so
+        // that r2 = 0 yields a finite y and g = 0 * y = 0), everything else uses |r2| as an operand modifier of the FP64 instructions
+        const int hi = max(__double2hiint(r2[r]) & 0x7fffffff, 0x01000000);
+        const double v = fabs(r2[r]);
+        double y;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(__hiloint2double(hi, 0)));
+        double g = v * y;
+        h[r] = 0.5 * y;
+        const double e = fma(-h[r], g, 0.5);
+        g = fma(g, e, g);                    // relative error ~2^-44
+        const double dd = fma(-g, g, v);
+        w[r] = fma(dd, h[r], g);             // h is the unrefined y / 2: its 2^-22 error multiplies dd ~ 2^-44 v
+    }
+    double t[R], f[R], s[R], q[R];
+#pragma unroll
+    for (int r = 0; r < R; r++) t[r] = fma(w[r], c1, magic);
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const double kd = t[r] - magic;
+        f[r] = fma(w[r], c1, -kd);
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        const int kk = __double2loint(t[r]);
+        int addr;
+        asm("mad.lo.s32 %0, %1, 128, %2;" : "=r"(addr) : "r"(kk & (CF_EXP_TBL - 1)), "r"((int)tbl_lane));
+        double tj;
+        asm("ld.shared.f64 %0, [%1];" : "=d"(tj) : "r"(addr));
+        int hi;
+        asm("mad.lo.s32 %0, %1, 4096, %2;" : "=r"(hi) : "r"(kk), "r"(__double2hiint(tj)));
+        s[r] = __hiloint2double(hi, __double2loint(tj));
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+        double p = fma(g3, f[r], g2);
+        p = fma(p, f[r], g1);
+        p = fma(p, f[r], g0);
+        q[r] = fma(f[r], p, 1.0);
+    }
+    const int pm = A.p;  // >= 1
+    double mp[R];
+    {
+        const double c = A.mat[pm - 1];
+#pragma unroll
+        for (int r = 0; r < R; r++) mp[r] = fma(top, w[r], c);
+    }
+#pragma unroll 1
+    for (int i = pm - 2; i >= 0; i--) {
+        const double ci = A.mat[i];
+#pragma unroll
+        for (int r = 0; r < R; r++) mp[r] = fma(mp[r], w[r], ci);
+    }
+#pragma unroll
+    for (int r = 0; r < R; r++) kv[r] = (mp[r] * s[r]) * q[r];
+}
 
 
 template <int D, int TJ, int NS>
@@ -32,7 +109,7 @@ struct cf_mvme_smem {
     static constexpr int total = tbl_bytes + ring_bytes;
 };
 
-template <int D, int R, int NT, int TJ, int NS, int MINB>
+template <int D, int R, int NT, int TJ, int NS, int MINB, int FAST = 1>
 __global__ void __launch_bounds__(NT, MINB) gram_mvm_eq_kernel(const __grid_constant__ cf_mvm_params P) {
     using S = cf_mvme_smem<D, TJ, NS>;
     extern __shared__ __align__(128) unsigned char smem[];
@@ -90,7 +167,7 @@ __global__ void __launch_bounds__(NT, MINB) gram_mvm_eq_kernel(const __grid_cons
         if (i >= rend) i = rend - 1; // clamp: computed but never stored
 #pragma unroll
         for (int c = 0; c < D; c++) xs[r][c] = -2.0 * Xg[i * D + c];
-        mrow[r] = rint(P.atom.e.c1 * xng[i]) + CF_MAGIC;
+        mrow[r] = (FAST == 2) ? xng[i] : rint(P.atom.e.c1 * xng[i]) + CF_MAGIC;  // FAST = 2: |x_i|^2 itself
     }
 
     double tot[R];
@@ -104,6 +181,8 @@ __global__ void __launch_bounds__(NT, MINB) gram_mvm_eq_kernel(const __grid_cons
     // word is zero, which the instruction encodes as an immediate; g2 then is the one uniform operand.
     const double g0 = P.eqc[0], g1 = P.eqc[1], g2 = P.eqc[2];
     constexpr double g3 = 0x1.3b2ab00000000p-39; // (ln2 / 256)^4 / 24 to 3.4e-7
+    double magic = CF_MAGIC, mtop = (FAST == 2) ? P.atom.mat[P.atom.p] : 0.0;  // FAST = 2: pinned in registers (see cf_matern_fast_n)
+    if (FAST == 2) asm volatile("" : "+d"(magic), "+d"(mtop));
 
     double acc[R];
     // one column against the R rows of this thread
@@ -118,6 +197,14 @@ __global__ void __launch_bounds__(NT, MINB) gram_mvm_eq_kernel(const __grid_cons
 #pragma unroll
             for (int r = 0; r < R; r++) i0[r] = fma(xs[r][c], yj[c], i0[r]);
         }
+        if constexpr (FAST == 2) {
+            double r2[R], kv[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) r2[r] = i0[r] + mrow[r];
+            cf_matern_fast_n<R>(r2, P.atom, c1s, g0, g1, g2, magic, mtop, tbl_lane, kv);
+#pragma unroll
+            for (int r = 0; r < R; r++) acc[r] = fma(kv[r], aj, acc[r]);
+        } else {
 #pragma unroll
         for (int r = 0; r < R; r++) t[r] = fma(i0[r], c1s, mrow[r]);
 #pragma unroll
@@ -150,6 +237,7 @@ __global__ void __launch_bounds__(NT, MINB) gram_mvm_eq_kernel(const __grid_cons
             const double e = s[r] * q;
             acc[r] = fma(e, aj, acc[r]);
         }
+        }  // FAST == 1
     };
     // a tile: columns two at a time, every operand load a 16-byte shared-memory broadcast (stage buffers are 128-byte aligned)
     auto compute = [&](const double* __restrict__ ys, const double* __restrict__ ns, const double* __restrict__ as, int cnt) {
@@ -223,7 +311,7 @@ __global__ void __launch_bounds__(NT, MINB) gram_mvm_eq_kernel(const __grid_cons
             const double lo = (w - rint(w)) + fma(P.atom.e.c1, nx, -w); // c1 |x|^2 - rint(c1 |x|^2), with the product's rounding error
             const double z = lo * (0.693147180559945309417232121458 / 256.0);    // |z| <= 0.00136
             const double ez = 1.0 + z * (1.0 + z * (0.5 + z * (1.0 / 6.0 + z * (1.0 / 24.0 + z * (1.0 / 120.0)))));
-            const double v0 = tot[r] * ez;
+            const double v0 = (FAST == 2) ? tot[r] : tot[r] * ez;
             const int64_t o = i - P.row0;
             if (P.direct) {
                 double v = P.alpha * v0;
@@ -238,10 +326,10 @@ __global__ void __launch_bounds__(NT, MINB) gram_mvm_eq_kernel(const __grid_cons
 }
 
 #ifndef __CUDACC_RTC__
-template <int D, int R, int NT, int TJ, int NS, int MINB>
+template <int D, int R, int NT, int TJ, int NS, int MINB, int FAST = 1>
 cudaError_t cf_mvme_launch(const cf_mvm_params& P, dim3 grid, cudaStream_t stream) {
     using S = cf_mvme_smem<D, TJ, NS>;
-    auto kern = gram_mvm_eq_kernel<D, R, NT, TJ, NS, MINB>;
+    auto kern = gram_mvm_eq_kernel<D, R, NT, TJ, NS, MINB, FAST>;
     static bool configured[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -266,6 +354,21 @@ struct cf_mvme_entry {
 };
 template <int D>
 struct cf_mvme_entry<D, false> {
+    static constexpr cf_mvm_launch_fn fn = nullptr;
+    static constexpr cf_mvm_config cfg = {0, 0, 0, 0};
+};
+// the MaternP form (FAST = 2), padded D <= 8 (D = 8 serves the symmetric variant: the plain product at D >= 8 takes the tensor-core kernel)
+#ifndef CF_MVMM_R
+#define CF_MVMM_R 6
+#endif
+template <int D, bool OK = (D <= 8)>
+struct cf_mvmm_entry {
+    static constexpr int R = (D <= 4) ? CF_MVMM_R : (D <= 6 ? 4 : 3), NT = 128, TJ = 128, NS = 3, MINB = 2;
+    static constexpr cf_mvm_launch_fn fn = &cf_mvme_launch<D, R, NT, TJ, NS, MINB, 2>;
+    static constexpr cf_mvm_config cfg = {NT * R, TJ, cf_mvme_smem<D, TJ, NS>::total, MINB};
+};
+template <int D>
+struct cf_mvmm_entry<D, false> {
     static constexpr cf_mvm_launch_fn fn = nullptr;
     static constexpr cf_mvm_config cfg = {0, 0, 0, 0};
 };

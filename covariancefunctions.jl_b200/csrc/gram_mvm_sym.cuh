@@ -18,9 +18,10 @@
 // The column partials take n^2 / (2 NT R) doubles (4.3 GB at n = 2^20, written and read once per product: ~1.5 ms of HBM time
 // against ~0.5 s of arithmetic); the host only selects this variant while that stays below a quarter of the device memory.
 //
-// EQF = true evaluates the EQ kernel in the scaled domain (gram_mvm_eq.cuh: exponent from |x|^2 + |y|^2 - 2 x.y, 12 FP64
+// EQF = 1 evaluates the EQ kernel in the scaled domain (gram_mvm_eq.cuh: exponent from |x|^2 + |y|^2 - 2 x.y, 12 FP64
 // instructions per pair); the row's leftover factor exp(lo_i ln2 / 256) multiplies the row sum in the epilogue and the row's weight
-// on the column side.  EQF = false evaluates any kernel kind through cf_rows_value (direct differences).
+// on the column side.  EQF = 2 evaluates a single MaternP atom (p >= 1) from the norm expansion with cf_matern_fast_n (gram_mvm_eq.cuh,
+// FAST = 2).  EQF = 0 evaluates any kernel kind through cf_rows_value (direct differences).
 #pragma once
 #include "gram_mvm_eq.cuh"
 
@@ -46,7 +47,7 @@ struct cf_sym_params {
     double eqc[4];         // EQF: polynomial constants (see gram_mvm_eq.cuh)
 };
 
-template <int D, int TJ, int NS, int NW, bool EQF>
+template <int D, int TJ, int NS, int NW, int EQF>
 struct cf_sym_smem {
     static constexpr int tbl_bytes = CF_EXP_TBL_DOUBLES * 8;
     static constexpr int bar_bytes = 128;
@@ -57,7 +58,7 @@ struct cf_sym_smem {
     static constexpr int total = tbl_bytes + bar_bytes + NS * stage_bytes + col_bytes;
 };
 
-template <int D, int KIND, bool EQF, int R, int NT, int TJ, int NS, int MINB>
+template <int D, int KIND, int EQF, int R, int NT, int TJ, int NS, int MINB>
 __global__ void __launch_bounds__(NT, MINB) gram_mvm_sym_kernel(const __grid_constant__ cf_sym_params P) {
     constexpr int NW = NT / 32;
     using S = cf_sym_smem<D, TJ, NS, NW, EQF>;
@@ -103,7 +104,11 @@ __global__ void __launch_bounds__(NT, MINB) gram_mvm_sym_kernel(const __grid_con
         const bool ok = i < P.n;
         if (!ok) i = P.n - 1;
         const double ai = ok ? P.a[i] : 0.0;
-        if (EQF) {
+        if (EQF == 2) {
+#pragma unroll
+            for (int c = 0; c < D; c++) x[r][c] = -2.0 * P.X[i * D + c];
+            mrow[r] = P.xn[i]; ez[r] = 1.0; at[r] = ai;
+        } else if (EQF == 1) {
 #pragma unroll
             for (int c = 0; c < D; c++) x[r][c] = -2.0 * P.X[i * D + c];
             const double nx = P.xn[i];
@@ -122,13 +127,28 @@ __global__ void __launch_bounds__(NT, MINB) gram_mvm_sym_kernel(const __grid_con
     }
     const double g0 = P.eqc[0], g1 = P.eqc[1], g2 = P.eqc[2];
     constexpr double g3 = 0x1.3b2ab00000000p-39;
+    double magic = CF_MAGIC, mtop = (EQF == 2) ? P.atom.mat[P.atom.p] : 0.0;  // EQF = 2: pinned in registers (see cf_matern_fast_n)
+    if (EQF == 2) asm volatile("" : "+d"(magic), "+d"(mtop));
 
     // k (without the row factor in EQF mode) of one column against the R rows
     auto column = [&](const double* __restrict__ ys, const double* __restrict__ ns, int j, double (&kv)[R]) {
         double yj[D];
 #pragma unroll
         for (int c = 0; c < D; c++) yj[c] = ys[j * D + c];
-        if constexpr (EQF) {
+        if constexpr (EQF == 2) {
+            const double nj = ns[j];
+            double r2[R];
+#pragma unroll
+            for (int r = 0; r < R; r++) r2[r] = fma(x[r][D - 1], yj[D - 1], nj);
+#pragma unroll
+            for (int c = D - 2; c >= 0; c--) {
+#pragma unroll
+                for (int r = 0; r < R; r++) r2[r] = fma(x[r][c], yj[c], r2[r]);
+            }
+#pragma unroll
+            for (int r = 0; r < R; r++) r2[r] += mrow[r];
+            cf_matern_fast_n<R>(r2, P.atom, c1s, g0, g1, g2, magic, mtop, tbl_lane, kv);
+        } else if constexpr (EQF == 1) {
             const double nj = ns[j];
             double i0[R], t[R], f[R], p[R], s[R];
 #pragma unroll
@@ -314,7 +334,7 @@ static __global__ void cf_sum_parts_kernel(const cf_parts_in in, int64_t o0, int
 
 #ifndef __CUDACC_RTC__
 typedef cudaError_t (*cf_sym_launch_fn)(const cf_sym_params& P, int nitems, cudaStream_t stream);
-template <int D, int KIND, bool EQF, int R, int NT, int TJ, int NS, int MINB>
+template <int D, int KIND, int EQF, int R, int NT, int TJ, int NS, int MINB>
 cudaError_t cf_sym_launch(const cf_sym_params& P, int nitems, cudaStream_t stream) {
     using S = cf_sym_smem<D, TJ, NS, NT / 32, EQF>;
     auto kern = gram_mvm_sym_kernel<D, KIND, EQF, R, NT, TJ, NS, MINB>;
@@ -333,11 +353,23 @@ cudaError_t cf_sym_launch(const cf_sym_params& P, int nitems, cudaStream_t strea
 template <int D, bool OK = (D <= 6)>
 struct cf_syme_entry {
     using E = cf_mvme_entry<D>;
-    static constexpr cf_sym_launch_fn fn = &cf_sym_launch<D, CF_ATOM_EQ, true, E::R, E::NT, E::TJ, E::NS, E::MINB>;
-    static constexpr int smem = cf_sym_smem<D, E::TJ, E::NS, E::NT / 32, true>::total;
+    static constexpr cf_sym_launch_fn fn = &cf_sym_launch<D, CF_ATOM_EQ, 1, E::R, E::NT, E::TJ, E::NS, E::MINB>;
+    static constexpr int smem = cf_sym_smem<D, E::TJ, E::NS, E::NT / 32, 1>::total;
 };
 template <int D>
 struct cf_syme_entry<D, false> {
+    static constexpr cf_sym_launch_fn fn = nullptr;
+    static constexpr int smem = 0;
+};
+// MaternP form: same row tile as the FAST = 2 instantiation of gram_mvm_eq_kernel (cf_mvmm_entry)
+template <int D, bool OK = (D <= 8)>
+struct cf_symm_entry {
+    using E = cf_mvmm_entry<D>;
+    static constexpr cf_sym_launch_fn fn = &cf_sym_launch<D, CF_ATOM_MATERN, 2, E::R, E::NT, E::TJ, E::NS, E::MINB>;
+    static constexpr int smem = cf_sym_smem<D, E::TJ, E::NS, E::NT / 32, 2>::total;
+};
+template <int D>
+struct cf_symm_entry<D, false> {
     static constexpr cf_sym_launch_fn fn = nullptr;
     static constexpr int smem = 0;
 };

@@ -357,13 +357,18 @@ struct cf_mvme_entry<D, false> {
     static constexpr cf_mvm_launch_fn fn = nullptr;
     static constexpr cf_mvm_config cfg = {0, 0, 0, 0};
 };
-// the MaternP form (FAST = 2), padded D <= 8 (D = 8 serves the symmetric variant: the plain product at D >= 8 takes the tensor-core kernel)
+// the MaternP form (FAST = 2), padded D <= 8 (D = 8 serves the symmetric variant: the plain product at D >= 8 takes the tensor-core kernel).
+// Rows per thread measured with MaternP(2) (bench_aux/micro/k1m_variants.sh; d = 3 at n = 16384 / 131072, d = 8 at n = 131072):
+// R = 8 / 4 (254 and 242 registers, no spills): 0.453 / 14.46 / 18.92 ms; R = 6 / 3: 0.486 / 14.77 / 19.74; R = 4 / 2: 0.455 / 15.72 / 21.87.
 #ifndef CF_MVMM_R
-#define CF_MVMM_R 6
+#define CF_MVMM_R 8
+#endif
+#ifndef CF_MVMM_R8
+#define CF_MVMM_R8 4
 #endif
 template <int D, bool OK = (D <= 8)>
 struct cf_mvmm_entry {
-    static constexpr int R = (D <= 4) ? CF_MVMM_R : (D <= 6 ? 4 : 3), NT = 128, TJ = 128, NS = 3, MINB = 2;
+    static constexpr int R = (D <= 4) ? CF_MVMM_R : (D <= 6 ? 4 : CF_MVMM_R8), NT = 128, TJ = 128, NS = 3, MINB = 2;
     static constexpr cf_mvm_launch_fn fn = &cf_mvme_launch<D, R, NT, TJ, NS, MINB, 2>;
     static constexpr cf_mvm_config cfg = {NT * R, TJ, cf_mvme_smem<D, TJ, NS>::total, MINB};
 };

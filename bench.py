@@ -208,7 +208,23 @@ CPU_NOTE = ("C/OpenMP restatement of the reference loop (oracle/: src/gramian.jl
             "the GPU box (profiles/r2_julia_probe.txt), so the reference binary cannot run")
 
 
+_RESULT_STREAM = None
+
+
+def emit(obj):
+    """the ONE JSON line of the contract, on the process's original stdout"""
+    stream = _RESULT_STREAM or sys.stdout
+    stream.write(json.dumps(obj) + "\n")
+    stream.flush()
+
+
 def main():
+    # Libraries may write to file descriptor 1 (NCCL prints its version banner there when NCCL_DEBUG is set): keep the original stdout for
+    # the result line only and send everything else to stderr
+    global _RESULT_STREAM
+    sys.stdout.flush()
+    _RESULT_STREAM = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -259,7 +275,7 @@ def main():
         value = rows * float(n) / t
         products = (args.cg_iters + 1) if w["cg"] else 1
         sample = f"rows 0..{rows} of the n={n} row product ({rows * float(n):.3g} pairs per timed sample), all {n} columns"
-        print(json.dumps({
+        emit(({
             "impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": t * 1e3 * (n / rows) * products, "ms_per_step_is_extrapolated": True,
             "higher_is_better": True, "scaling": "strong",
@@ -507,7 +523,7 @@ def main():
             "sample": f"rows 0..{rows} of the same n={n} product ({rows * float(n):.3g} pairs, {secs:.1f} s)",
             "note": CPU_NOTE + "; README.md:37-38 publishes 4.59e8 pairs/s for MaternP(2), d=3, n=16384 on unstated hardware",
         }
-    print(json.dumps(out))
+    emit(out)
     if dist is not None:
         if sym_capable:
             D.comm_destroy()
@@ -725,7 +741,7 @@ def run_cg(args, w, cfg, rank, world, local_rank, dev, dist, metric, unit):
         out["cpu_baseline"] = {"value": rate, "unit": unit, "cores": nt, "kind": "port",
                                "sample": f"rows 0..{rows} of one n={n} operator product ({rows * float(n):.3g} pairs, {secs:.1f} s)",
                                "note": CPU_NOTE}
-    print(json.dumps(out))
+    emit(out)
     if dist is not None:
         D.comm_destroy()
         dist.destroy_process_group()

@@ -18,10 +18,12 @@ RUNS = {
     "c2:f64": (["--config", "c2"], "gram_mvm_eq_kernel", {"COVFN_SYMMETRIC": "0"}),
     "c2:f64:sym": (["--config", "c2"], "gram_mvm_sym_kernel", {"COVFN_SYMMETRIC": "1"}),
     "c2:f64:k1": (["--config", "c2"], "gram_mvm_kernel", {"COVFN_SYMMETRIC": "0", "COVFN_MVM_SCALAR": "1"}),
-    "c1:f64": (["--config", "c1"], "gram_mvm_kernel", {}),
+    "c1:f64": (["--config", "c1"], "gram_mvm_eq_kernel", {}),  # K1m: the MaternP form of the scaled-domain kernel
+    "c1:f64:k1": (["--config", "c1"], "gram_mvm_kernel", {"COVFN_MVM_SCALAR": "1"}),
     "c3:f64": (["--config", "c3"], "gram_mm_dmma_kernel", {}),
     "c4:f64": (["--config", "c4"], "grad_mvm_dmma_kernel", {}),
-    "c5:f64": (["--config", "x4", "--n", str(1 << 19)], "gram_mvm_sym_kernel", {}),
+    "c5:f64": (["--config", "x4"], "gram_mvm_sym_kernel", {}),  # config 5's operator at n = 131072 (a sixteenth of the pairs: shorter capture)
+    "c5:f64:k1": (["--config", "x4"], "gram_mvm_sym_kernel", {"COVFN_MVM_SCALAR": "1"}),
     "c2:f32": (["--config", "c2", "--dtype", "f32", "--n", "262144"], "gram_mvm_f32p_kernel", {}),  # (a sixteenth of the pairs: same rate, shorter capture)
     "c2:f32:k1": (["--config", "c2", "--dtype", "f32"], "gram_mvm_kernel", {"COVFN_MVM_SCALAR": "1"}),
     "x2:f32": (["--config", "x2", "--dtype", "f32"], "gram_mvm_tc5_kernel", {}),

@@ -197,11 +197,11 @@ LinearAlgebra.mul!(Y::StridedMatrix{T}, G::Gramian{T, <:Lowerable}, X::StridedMa
 const DerivKernel{K} = Union{GradientKernel{<:Any, K, IsotropicInput}, GradientKernel{<:Any, K, DotProductInput},
                              ValueGradientKernel{<:Any, K, IsotropicInput}, ValueGradientKernel{<:Any, K, DotProductInput}}
 
-# the flat Vector{Float64} behind a vector of contiguous equal-length views that tile it exactly, or `nothing`
-function flat_parent(v::AbstractVector{<:AbstractVector{Float64}}, blk::Int)
+# the flat Vector{T} behind a vector of contiguous equal-length views that tile it exactly, or `nothing`
+function flat_parent(v::AbstractVector{<:AbstractVector{T}}, blk::Int) where {T<:F}
     isempty(v) && return nothing
     p = parent(first(v))
-    (p isa Vector{Float64} && length(p) == blk * length(v)) || return nothing
+    (p isa Vector{T} && length(p) == blk * length(v)) || return nothing
     for (i, vi) in enumerate(v)
         (vi isa SubArray && parent(vi) === p && length(vi) == blk && first(parentindices(vi)[1]) == (i - 1) * blk + 1 &&
          stride(vi, 1) == 1) || return nothing
@@ -209,10 +209,13 @@ function flat_parent(v::AbstractVector{<:AbstractVector{Float64}}, blk::Int)
     return p
 end
 
-function BlockFactorizations.blockmul!(y::AbstractVector{<:AbstractVector{Float64}},
+# T is the element type of the flat vectors; the device path is taken when the points have the same element type (otherwise the reference's
+# promotion rules apply and its method runs).  The derivative operators compute in Float64 inside the library for either T [S10].
+points_eltype(G::Gramian) = isempty(G.x) ? Nothing : eltype(first(G.x))
+function BlockFactorizations.blockmul!(y::AbstractVector{<:AbstractVector{T}},
                                        G::Gramian{<:Any, <:DerivKernel{<:Lowerable}},
-                                       x::AbstractVector{<:AbstractVector{Float64}}, α::Real = 1, β::Real = 0)
-    prog = program(G.k.k)
+                                       x::AbstractVector{<:AbstractVector{T}}, α::Real = 1, β::Real = 0) where {T<:F}
+    prog = points_eltype(G) === T ? program(G.k.k) : nothing
     vg = G.k isa ValueGradientKernel
     blk = length(first(G.x)) + (vg ? 1 : 0)
     yf = prog === nothing ? nothing : flat_parent(y, blk)
@@ -220,8 +223,7 @@ function BlockFactorizations.blockmul!(y::AbstractVector{<:AbstractVector{Float6
     (yf === nothing || xf === nothing || length(y) != length(G.x) || length(x) != length(G.y)) &&
         return @invoke BlockFactorizations.blockmul!(y::AbstractVector{<:AbstractVecOrMat}, G::Gramian,
                                                       x::AbstractVector{<:AbstractVecOrMat}, α::Real, β::Real)
-    h = handle(G, Float64, prog)
-    sym = vg ? :cf_value_gradient_mul : :cf_gradient_mul
+    h = handle(G, T, prog)
     GC.@preserve yf xf h begin
         if vg
             check(ccall((:cf_value_gradient_mul, libcovfn), Cint,                                      # [S5]
@@ -244,10 +246,11 @@ end
 cg_kwargs_ok(kw) = all(k -> k in (:reltol, :maxiter) || (k == :abstol && iszero(kw[k])) || (k == :log && kw[k] == false) ||
                              (k == :initially_zero), keys(kw))
 
-function device_cg!(x::StridedVector{Float64}, G::Gramian, prog, σ²::Float64, b::StridedVector{Float64}, deriv::Int, kw)
+# (reltol = 0 selects the library's default: sqrt(eps(T)), as cg! does for vectors of element type T)
+function device_cg!(x::StridedVector{T}, G::Gramian, prog, σ²::Float64, b::StridedVector{T}, deriv::Int, kw) where {T<:F}
     length(x) == length(b) || throw(DimensionMismatch("ldiv!: x $(length(x)), b $(length(b))"))
     get(kw, :initially_zero, false) && fill!(x, 0)       # cg! semantics: x is the initial guess unless initially_zero
-    h = handle(G, Float64, prog)
+    h = handle(G, T, prog)
     iters = Ref{Cint}(0); res = Ref{Cdouble}(0)
     GC.@preserve x b h begin
         check(ccall((:cf_cg_solve, libcovfn), Cint,                                                    # [S6] [S7]
@@ -258,8 +261,8 @@ function device_cg!(x::StridedVector{Float64}, G::Gramian, prog, σ²::Float64, 
 end
 
 # σ²I + K (either order).  Diagonals that are not a multiple of the identity are left to the reference.
-const DiagGram = Union{Tuple{<:Diagonal, <:Gramian{Float64, <:Lowerable}}, Tuple{<:Gramian{Float64, <:Lowerable}, <:Diagonal}}
-function LinearAlgebra.ldiv!(x::StridedVector{Float64}, A::LazyMatrixSum{<:Any, <:DiagGram}, b::StridedVector{Float64}; kwargs...)
+const DiagGram{T} = Union{Tuple{<:Diagonal, <:Gramian{T, <:Lowerable}}, Tuple{<:Gramian{T, <:Lowerable}, <:Diagonal}}
+function LinearAlgebra.ldiv!(x::StridedVector{T}, A::LazyMatrixSum{<:Any, <:DiagGram{T}}, b::StridedVector{T}; kwargs...) where {T<:F}
     D, G = A.args[1] isa Diagonal ? (A.args[1], A.args[2]) : (A.args[2], A.args[1])
     prog = program(G.k)
     d = D.diag
@@ -270,11 +273,11 @@ function LinearAlgebra.ldiv!(x::StridedVector{Float64}, A::LazyMatrixSum{<:Any, 
 end
 
 # BlockGramian of a (value-)gradient kernel: G \ b (src/gramian.jl:229-238)
-function LinearAlgebra.ldiv!(x::StridedVector{Float64},
+function LinearAlgebra.ldiv!(x::StridedVector{T},
                              B::BlockFactorization{<:Any, <:Gramian{<:Any, <:DerivKernel{<:Lowerable}}},
-                             b::StridedVector{Float64}; kwargs...)
+                             b::StridedVector{T}; kwargs...) where {T<:F}
     G = B.A                                  # the wrapped Gramian (field `A` of BlockFactorization [upstream 1.2.2])
-    prog = program(G.k.k)
+    prog = points_eltype(G) === T ? program(G.k.k) : nothing
     (prog === nothing || !cg_kwargs_ok(kwargs) || stride(x, 1) != 1 || stride(b, 1) != 1) &&
         return @invoke ldiv!(x::AbstractVector, B::BlockFactorization{<:Any, <:Gramian}, b::AbstractVector; kwargs...)
     device_cg!(x, G, prog, 0.0, b, G.k isa ValueGradientKernel ? 2 : 1, kwargs)                        # [S7]

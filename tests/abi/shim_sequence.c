@@ -216,6 +216,34 @@ int main(int argc, char** argv) {
         free(prog);
     }
 
+    /* [S10] Float32 Gramians through blockmul! and ldiv!: the shim's methods are generic in T = Float32 / Float64; inside the library the
+     * derivative operators and the solves compute in Float64 on a copy of the points (vectors stay Float32).  reltol = 0 selects
+     * sqrt(eps(Float32)), the cg! default for Float32 vectors. */
+    {
+        const int64_t nd = n * d;
+        float* X32 = (float*)malloc(sizeof(float) * (size_t)nd);
+        float* v32 = (float*)malloc(sizeof(float) * (size_t)nd);
+        float* y32 = (float*)malloc(sizeof(float) * (size_t)nd);
+        for (int64_t q = 0; q < nd; q++) { X32[q] = (float)(2.0 * Y2[q]); v32[q] = (float)ag[q]; y32[q] = 0.f; }
+        cf_gramian_t h = NULL;
+        CHECK(p_create(&h, prog_eq, 1, CF_F32, (int)d, n, X32, d, n, NULL, d));
+        CHECK(p_gradient_mul(h, y32, nd, v32, nd, 1, 1.0, 0.0));
+        for (int64_t q = 0; q < nd; q++) y[q] = (double)y32[q];
+        record("S10_f32_gradient", y, nd);
+        CHECK(p_destroy(h));
+        h = NULL;
+        CHECK(p_create(&h, prog_m2, 1, CF_F32, (int)d, n, X32, d, n, NULL, d));
+        int iters = -1;
+        double res = -1;
+        for (int64_t q = 0; q < n; q++) { v32[q] = (float)rhs[q]; y32[q] = 0.f; }
+        CHECK(p_cg_solve(h, 0.5, y32, v32, 0.0, 0, 0, &iters, &res));
+        for (int64_t q = 0; q < n; q++) y[q] = (double)y32[q];
+        y[n] = (double)iters; y[n + 1] = res;
+        record("S10_f32_ldiv", y, n + 2);
+        CHECK(p_destroy(h));
+        free(X32); free(v32); free(y32);
+    }
+
     CHECK(p_destroy(h1)); CHECK(p_destroy(h2)); CHECK(p_destroy(h3));
 
     /* [S8] init(devices): rows sharded inside the library over every visible device; handles created afterwards use all of them */

@@ -1,6 +1,6 @@
 """The Julia shim's ccall sequences, replayed by the C harness tests/abi/shim_sequence.c (gcc, dlopen of the product library)
 and checked against the oracle: the executable stand-in for julia/CovarianceFunctionsB200.jl, which cannot run here (no Julia
-in the image or on the GPU box).  Scenario tags S1..S9 are the ones the shim's comments carry."""
+in the image or on the GPU box).  Scenario tags S1..S10 are the ones the shim's comments carry."""
 import os
 import struct
 import subprocess
@@ -98,6 +98,14 @@ def test_shim_call_sequences_match_oracle(tmp_path, cf, O):
     # S9: ARD node and the error codes the shim turns into exceptions
     assert relerr(R["S9_ard"], O.mul_vec(cf.ARD(cf.MaternP(2), l).program(), X, a)) < 1e-12
     assert list(R["S9_errors"]) == [-2.0, -2.0, 1.0]
+    # S10: Float32 Gramians through blockmul! and ldiv! (Float64 arithmetic inside the library, Float32 vectors)
+    X32s = (2.0 * Y2).astype(np.float32)
+    ag32 = ag.astype(np.float32)
+    assert relerr(R["S10_f32_gradient"], O.derivative_mul(eq, X32s.astype(np.float64), ag32.astype(np.float64))) < 1e-5
+    S10 = R["S10_f32_ldiv"]
+    K32 = O.matrix(m2, X32s.astype(np.float64)) + 0.5 * np.eye(n)
+    rhs32 = rhs.astype(np.float32).astype(np.float64)
+    assert int(S10[n]) > 0 and np.linalg.norm(K32 @ S10[:n] - rhs32) < 2e-3 * np.linalg.norm(rhs32)
     # S8: every visible device
     S8 = R["S8_init_all_devices"]
     assert int(S8[n]) == cf.device_count() or int(S8[n]) == 8

@@ -4,15 +4,16 @@
 // Replaces mul!(y::AbstractVector, G::Gramian{Float32}, x::AbstractVector, alpha, beta) (reference src/gramian.jl:78-87) for well-scaled
 // points, like gram_mvm_tf32.cuh (K1t), whose legacy mma.sync distance GEMM it supersedes: there every warp loads fragments, splits
 // them and issues 3 D / 8 mma.sync per 16 x 8 entries before it can evaluate anything (EQ, d = 32: 8.7e11 pairs/s); here one thread
-// issues 3 D / 8 asynchronous MMAs per 128 x 64 tile, the operands are read by the tensor core from the canonical shared-memory images
-// that gram_mm_tc5.cuh (K4u) already keeps per handle, and the sixteen evaluation warps only evaluate: tcgen05.ld of 32 dot products,
+// issues 3 D / 8 asynchronous MMAs per 128 x 64 tile -- A operand: the CTA's row tile, written ONCE to tensor memory; B operand: the
+// canonical shared-memory images that gram_mm_tc5.cuh (K4u) already keeps per handle, delivered by TMA -- and the sixteen evaluation
+// warps only evaluate: tcgen05.ld of 32 dot products,
 // r2 = |x|^2 + |y|^2 - 2 x.y, the kernel, the weighted sum -- in packed FP32 instructions over column pairs (gram_mvm_f32p.cuh).
 // For EQ that is 3 FFMA2 + 2 MUFU.EX2 + 2 LDS.64 per two pairs: the MUFU pipe (one ex2 per pair, 16 per clock and SM) is the bound.
 //
 //   per row tile of 128 rows and column chunk (one CTA), per column tile of TJ = 64 points:
 //   TMA producer        Yhi | Ylo images, |y|^2, a  -> stage s                              4 bulk copies, full[s]
 //   MMA issuer          Dot (128 x 64) = Xlo Yhi^T + Xhi Ylo^T + Xhi Yhi^T  -> TMEM dot[t % 4]    dotfull[t % 4]
-//   evaluation group t & 1 (8 warps: TMEM lane quarter x column half)  tcgen05.ld -> dotfree, kernel, acc2 += k2 a2, empty[s]
+//   evaluation group t & 1 (8 warps: TMEM lane quarter x column half)  tcgen05.ld -> dotfree, kernel, acc2 += k2 a2, every lane -> empty[s]
 // Row sums: Float32 within a tile (16 terms per accumulator half), Float64 across tiles, as in K1 / K1t.
 #pragma once
 #include "gram_mm_tc5.cuh"
@@ -31,8 +32,6 @@
 // with 3, 4.79 with 5; d = 32: 5.10 / 5.29 / 5.39 / 5.42 ms -- the extra ~10 issue slots per pair cost more than the MUFU cycles they
 // free once the tile hand-over (tcgen05.ld, mbarriers) shares the issue port.  Off by default; kept for kernels with a heavier MUFU load.
 // (The exponent c log2(e) r2 stays above -126 here: these kernels run only on points that passed the scale check, capi.cu set_norm_flags.)
-// 1: the stage is additionally released by a tcgen05.commit arrival, the way K4u must do it.  Redundant here; exists to show that
-// compute-sanitizer's racecheck does not see such arrivals (profiles/r2_sanitizer.txt).
 #ifndef CF_MVU_POLY_MASK
 #define CF_MVU_POLY_MASK 0x0u  // e.g. 0x1084u: pairs 2, 7, 12
 #endif

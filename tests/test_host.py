@@ -187,7 +187,7 @@ def test_runtime_specialisations_compile_without_a_gpu():
         pytest.skip(str(e))
     for name, k in programs.items():
         cf.jit_check(k, 3, "mvm")                 # K1, d = 3 (R = 4)
-        for which in ("mm_dmma", "mvm_dmma", "mm_tf32", "mvm_tf32"):
+        for which in ("mm_dmma", "mvm_dmma", "mm_tf32", "mvm_tf32", "mm_tf32_legacy", "mvm_tc5"):  # incl. the tcgen05 kernels (K4u, K1u)
             cf.jit_check(k, 16, which)
     with pytest.raises(UnsupportedKernel):
         cf.jit_check(cf.EQ(), 3, "mm_dmma")       # no tensor-core kernel below d = 8

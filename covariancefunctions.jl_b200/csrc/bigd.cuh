@@ -5,9 +5,11 @@
 //                         reference's r'a / x'a, src/gradient.jl:90,113)  or  x_i . y_j (value kernels that need both)
 //   bigd_value_kernel     y_i = alpha sum_j k(T_ij, S_ij) a_j + beta y_i                      (src/gramian.jl:78-87)
 //   bigd_jet_kernel       (T, S) -> (ca, cw) in place: ISO ca = -2 k', cw = -4 k'' S;  DOT ca = k', cw = k'' S
+//   bigd_jet_vg_kernel    the same for the ValueGradientKernel ((d + 1)-blocks, entry 0 = value: src/gradient.jl:400-474): the value weight
+//                         a0_j adds 2 k' a0_j (ISO) / k' a0_j (DOT) to cw, and the value row b0_i = sum_j k a0_j + ca S is reduced per row
 //   bigd_update_kernel    b_i[c] = sum_j ca_ij a_j[c] + cw_ij w_ij[c],  w = x_i - y_j (ISO) or y_j (DOT)   (src/gradient.jl:91,114)
 // The host walks row blocks so that the two [rows][m] scratch matrices stay bounded.  Points are padded to a multiple of
-// 16 coordinates.  Float64 only.  64 x 64 output tiles, 16-deep chunks staged through shared memory, 4 x 4 register tiles.
+// 16 coordinates.  Float64 only (Float32 handles: Float64 shadow).  64 x 64 output tiles, 16-deep chunks staged through shared memory, 4 x 4 register tiles.
 #pragma once
 #include "grad_mvm.cuh"
 
@@ -128,13 +130,55 @@ __global__ void __launch_bounds__(256) bigd_jet_kernel(double* __restrict__ Tm, 
     }
 }
 
-// out[i][c] = alpha sum_j (ca_ij a_j[c] + cw_ij w_ij[c]) + beta out[i][c];  out/yin are unpadded flat vectors (stride d)
+// ValueGradientKernel: one CTA per row of the block.  (T, S) -> (ca, cw) in place with the value weight's share in cw, and
+// out0[i * ostride] = alpha sum_j (k a0_j + ca S_ij) + beta yin0[i * ostride]   (the value entry of row block i; fixed reduction order)
+template <int MODE>
+__global__ void __launch_bounds__(256) bigd_jet_vg_kernel(double* __restrict__ Tm, double* __restrict__ Sm, const double* __restrict__ a0,
+                                                          int64_t nrows, int64_t m, const __grid_constant__ cf_sop_grad prog,
+                                                          const double* __restrict__ exp2_tbl, double* __restrict__ out0,
+                                                          const double* __restrict__ yin0, int64_t ostride, double alpha, double beta) {
+    extern __shared__ __align__(128) unsigned char bd_smem[];
+    double* tbl = reinterpret_cast<double*>(bd_smem);
+    __shared__ double red[8];
+    cf_fill_exp_table(tbl, exp2_tbl, threadIdx.x, 256);
+    __syncthreads();
+    cf_tbl_t tbl_lane = cf_tbl_lane(tbl, threadIdx.x);
+    cf_tbl_publish(tbl_lane);
+    for (int64_t i = blockIdx.x; i < nrows; i += gridDim.x) {
+        double acc = 0.0;
+        for (int64_t j = threadIdx.x; j < m; j += 256) {
+            const int64_t q = i * m + j;
+            double k, k1, k2;
+            cf_sop_jet(Tm[q], prog, tbl_lane, k, k1, k2);
+            const double sd = Sm[q], aj = a0[j];
+            const double ca = (MODE == CF_GRAD_ISO) ? -2.0 * k1 : k1;
+            Tm[q] = ca;
+            Sm[q] = (MODE == CF_GRAD_ISO) ? fma(-4.0 * k2, sd, 2.0 * k1 * aj) : fma(k2, sd, k1 * aj);
+            acc = fma(k, aj, fma(ca, sd, acc));
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += cf_shfl_xor_f64(acc, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double v = 0.0;
+            for (int w = 0; w < 8; w++) v += red[w];
+            v *= alpha;
+            if (beta != 0.0) v += beta * yin0[i * ostride];
+            out0[i * ostride] = v;
+        }
+        __syncthreads();
+    }
+}
+
+// out[i * ostride + c] = alpha sum_j (ca_ij a_j[c] + cw_ij w_ij[c]) + beta yin[i * ostride + c];  out / yin are unpadded flat vectors with
+// blocks of ostride entries (d for the GradientKernel; d + 1 for the ValueGradientKernel, whose callers pass pointers to entry 1)
 template <int MODE>
 __global__ void __launch_bounds__(256) bigd_update_kernel(const double* __restrict__ X, const double* __restrict__ Y,
                                                           const double* __restrict__ A, int D, int d, int64_t i0, int64_t nrows,
                                                           int64_t m, const double* __restrict__ CA, const double* __restrict__ CW,
                                                           double* __restrict__ out, const double* __restrict__ yin, double alpha,
-                                                          double beta) {
+                                                          double beta, int64_t ostride) {
     __shared__ __align__(16) double cas[CF_BD_K][CF_BD_T + 2], cws[CF_BD_K][CF_BD_T + 2], as[CF_BD_K][CF_BD_T], ys[CF_BD_K][CF_BD_T];
     const int tid = threadIdx.x, ti = tid & 15, tc = tid >> 4;
     const int64_t ib = (int64_t)blockIdx.y * CF_BD_T;
@@ -193,7 +237,7 @@ __global__ void __launch_bounds__(256) bigd_update_kernel(const double* __restri
         for (int b = 0; b < 4; b++) {
             const int c = cb + 4 * tc + b;
             if (c >= d) continue;
-            const int64_t o = i * d + c;
+            const int64_t o = i * ostride + c;
             double v = alpha * acc[a][b];
             if (beta != 0.0) v += beta * yin[o];
             out[o] = v;

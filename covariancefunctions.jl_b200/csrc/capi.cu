@@ -137,7 +137,7 @@ struct Shard {
     void* Y = nullptr;  // m x D (== X when symmetric)
     void* xn = nullptr;  // squared norms of the padded points (multi-RHS kernel)
     void* yn = nullptr;
-    Buf a, y, partial, apad, ypad, at, cg[6], sym_items, bsym, sym_col, bd_t, bd_s, xp, yp, ap, yc_hi, yc_lo, yc_n, ac_hi, ac_lo, yt, au;
+    Buf a, y, partial, apad, ypad, at, cg[6], sym_items, bsym, sym_col, bd_t, bd_s, xp, yp, ap, yc_hi, yc_lo, yc_n, ac_hi, ac_lo, yt, au, cv_in, cv_out;
     int64_t yt_ld = 0;      // > 0: yt holds the transposed Float32 column points with this leading dimension (gram_mvm_f32p.cuh)
     bool tc5_ready = false; // yc_* hold the canonical column-point images of the tcgen05 multi-RHS kernel
     bool mmd_ready = false; // xp / yp hold the padded point copies of the DMMA multi-RHS kernel
@@ -885,14 +885,16 @@ int launch_bigd_mvm(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin
 }
 
 int launch_bigd_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, const double* d_a, double alpha, double beta,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int vg) {
     const int64_t nrows = sh.r1 - sh.r0, m = g->m;
-    const int d = g->d, D = g->D;
+    const int d = g->d, D = g->D, bs = d + vg;
     const int64_t rb = bigd_row_block(nrows, m);
     if (int rc = sh.bd_t.ensure((size_t)rb * m * 8)) return rc;
     if (int rc = sh.bd_s.ensure((size_t)rb * m * 8)) return rc;
-    if (int rc = sh.apad.ensure((size_t)m * D * 8)) return rc;
-    cf_pad_points<double><<<(int)std::min<int64_t>((m * D + 255) / 256, 8192), 256, 0, stream>>>(d_a, d, d, (double*)sh.apad.p, D, m);
+    if (int rc = sh.apad.ensure(((size_t)m * D + (size_t)m) * 8)) return rc;  // padded gradient weights, then the value weights (ValueGradient)
+    double* a0 = (double*)sh.apad.p + (size_t)m * D;
+    cf_pad_points<double><<<(int)std::min<int64_t>((m * D + 255) / 256, 8192), 256, 0, stream>>>(d_a + vg, bs, d, (double*)sh.apad.p, D, m);
+    if (vg) cf_pad_points<double><<<(int)std::min<int64_t>((m + 255) / 256, 8192), 256, 0, stream>>>(d_a, bs, 1, a0, 1, m);
     CF_CUDA(cudaGetLastError());
     const bool dot = g->prog.dotproduct != 0;
     for (int64_t b0 = 0; b0 < nrows; b0 += rb) {
@@ -900,21 +902,24 @@ int launch_bigd_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yi
         const dim3 grid((unsigned)((m + CF_BD_T - 1) / CF_BD_T), (unsigned)((nb + CF_BD_T - 1) / CF_BD_T));
         const dim3 ugrid((unsigned)((D + CF_BD_T - 1) / CF_BD_T), (unsigned)((nb + CF_BD_T - 1) / CF_BD_T));
         const int jb = (int)std::min<int64_t>((nb * m + 255) / 256, 148 * 16);
+        const int vb = (int)std::min<int64_t>(nb, 148 * 8);
         double* T = (double*)sh.bd_t.p;
         double* S = (double*)sh.bd_s.p;
         const double* X = (const double*)sh.X;
         const double* Y = (const double*)sh.Y;
         const double* A = (const double*)sh.apad.p;
-        double* out = d_y + b0 * d;
-        const double* yin = d_yin ? d_yin + b0 * d : nullptr;
+        double* out = d_y + b0 * bs;                             // entry 0 of row block b0 (the value entry when vg)
+        const double* yin = d_yin ? d_yin + b0 * bs : nullptr;
         if (dot) {
             bigd_pair_kernel<CF_GRAD_DOT, true><<<grid, 256, 0, stream>>>(X, Y, A, D, sh.r0 + b0, nb, m, T, S);
-            bigd_jet_kernel<CF_GRAD_DOT><<<jb, 256, CF_EXP_TBL_DOUBLES * 8, stream>>>(T, S, nb * m, g->sop_grad, sh.ctx->exp2_tbl);
-            bigd_update_kernel<CF_GRAD_DOT><<<ugrid, 256, 0, stream>>>(X, Y, A, D, d, sh.r0 + b0, nb, m, T, S, out, yin, alpha, beta);
+            if (vg) bigd_jet_vg_kernel<CF_GRAD_DOT><<<vb, 256, CF_EXP_TBL_DOUBLES * 8, stream>>>(T, S, a0, nb, m, g->sop_grad, sh.ctx->exp2_tbl, out, yin, bs, alpha, beta);
+            else bigd_jet_kernel<CF_GRAD_DOT><<<jb, 256, CF_EXP_TBL_DOUBLES * 8, stream>>>(T, S, nb * m, g->sop_grad, sh.ctx->exp2_tbl);
+            bigd_update_kernel<CF_GRAD_DOT><<<ugrid, 256, 0, stream>>>(X, Y, A, D, d, sh.r0 + b0, nb, m, T, S, out + vg, yin ? yin + vg : nullptr, alpha, beta, bs);
         } else {
             bigd_pair_kernel<CF_GRAD_ISO, true><<<grid, 256, 0, stream>>>(X, Y, A, D, sh.r0 + b0, nb, m, T, S);
-            bigd_jet_kernel<CF_GRAD_ISO><<<jb, 256, CF_EXP_TBL_DOUBLES * 8, stream>>>(T, S, nb * m, g->sop_grad, sh.ctx->exp2_tbl);
-            bigd_update_kernel<CF_GRAD_ISO><<<ugrid, 256, 0, stream>>>(X, Y, A, D, d, sh.r0 + b0, nb, m, T, S, out, yin, alpha, beta);
+            if (vg) bigd_jet_vg_kernel<CF_GRAD_ISO><<<vb, 256, CF_EXP_TBL_DOUBLES * 8, stream>>>(T, S, a0, nb, m, g->sop_grad, sh.ctx->exp2_tbl, out, yin, bs, alpha, beta);
+            else bigd_jet_kernel<CF_GRAD_ISO><<<jb, 256, CF_EXP_TBL_DOUBLES * 8, stream>>>(T, S, nb * m, g->sop_grad, sh.ctx->exp2_tbl);
+            bigd_update_kernel<CF_GRAD_ISO><<<ugrid, 256, 0, stream>>>(X, Y, A, D, d, sh.r0 + b0, nb, m, T, S, out + vg, yin ? yin + vg : nullptr, alpha, beta, bs);
         }
         CF_CUDA(cudaGetLastError());
         g->last_launches += 3;
@@ -1302,7 +1307,7 @@ int launch_grad(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin, co
         launch_scale(CF_F64, d_y, d_yin, nrows * bs, beta, stream);
         return CF_OK;
     }
-    if (!g->entry) return launch_bigd_grad(g, sh, d_y, d_yin, d_a, alpha, beta, stream);
+    if (!g->entry) return launch_bigd_grad(g, sh, d_y, d_yin, d_a, alpha, beta, stream, vg);
     {   // isotropic GradientKernel on well-scaled Float64 points: every d-dependent operation on the FP64 tensor cores
         // (grad_mvm_dmma.cuh); COVFN_GRAD_SCALAR=1 keeps the scalar kernel
         const bool eq = g->prog.single && g->prog.atoms[g->prog.terms[0].fac[0].atom].v.kind == CF_ATOM_EQ;
@@ -1510,7 +1515,7 @@ int destroy_impl(cf_gramian_s* g) {
         if (sh.yn && sh.yn != sh.xn) dev_free(sh.yn);
         dev_free(sh.xn);
         sh.a.release(); sh.y.release(); sh.partial.release(); sh.apad.release(); sh.ypad.release(); sh.at.release(); sh.sym_items.release(); sh.bsym.release(); sh.sym_col.release(); sh.bd_t.release(); sh.bd_s.release();
-        sh.xp.release(); sh.yp.release(); sh.ap.release(); sh.yc_hi.release(); sh.yc_lo.release(); sh.yc_n.release(); sh.ac_hi.release(); sh.ac_lo.release(); sh.yt.release(); sh.au.release();
+        sh.xp.release(); sh.yp.release(); sh.ap.release(); sh.yc_hi.release(); sh.yc_lo.release(); sh.yc_n.release(); sh.ac_hi.release(); sh.ac_lo.release(); sh.yt.release(); sh.au.release(); sh.cv_in.release(); sh.cv_out.release();
         for (auto& b : sh.cg) b.release();
         if (sh.ev0) cudaEventDestroy(sh.ev0);
         if (sh.ev1) cudaEventDestroy(sh.ev1);
@@ -1767,10 +1772,7 @@ static int check_derivative(cf_gramian_s* g) {
     if (!g->grad_ok) return fail(CF_ERR_UNSUPPORTED, "derivative operators: kernel too complex (more than 4 terms or 3 base kernels)");
     return CF_OK;
 }
-static int check_vg_dim(cf_gramian_s* g, int deriv) {
-    if (deriv == 2 && !g->entry) return fail(CF_ERR_UNSUPPORTED, "ValueGradientKernel: d > 32 is not supported yet");
-    return CF_OK;
-}
+static int check_vg_dim(cf_gramian_s*, int) { return CF_OK; }  // (the ValueGradientKernel covers every d since round 2: bigd_jet_vg_kernel)
 
 static int mul_host_impl(cf_gramian_t g, void* y, int64_t ldy, const void* x, int64_t ldx, int64_t nrhs, double alpha,
                          double beta, int deriv) {
@@ -2001,17 +2003,18 @@ static int mul_device_impl(cf_gramian_t g, void* d_y, int64_t ldy, const void* d
         CF_CUDA(cudaSetDevice(hs.ctx->dev));
         cudaStream_t st = stream ? (cudaStream_t)stream : hs.stream;
         if (stream) { g->user_stream = stream; h->user_stream = stream; }
-        if (int rc = hs.apad.ensure((size_t)cols * nrhs * 8 + 16)) return rc;
-        if (int rc = hs.ypad.ensure((size_t)rows * nrhs * 8 + 16)) return rc;
+        // (buffers of their own: the operator launched below pads its input into apad / reduces through ypad)
+        if (int rc = hs.cv_in.ensure((size_t)cols * nrhs * 8 + 16)) return rc;
+        if (int rc = hs.cv_out.ensure((size_t)rows * nrhs * 8 + 16)) return rc;
         const int cb = (int)std::min<int64_t>((std::max(rows, cols) + 255) / 256, 8192);
         for (int64_t c = 0; c < nrhs; c++) {
-            cf_convert_kernel<float, double><<<cb, 256, 0, st>>>((const float*)d_x + c * ldx, (double*)hs.apad.p + c * cols, cols);
-            if (beta != 0.0) cf_convert_kernel<float, double><<<cb, 256, 0, st>>>((const float*)d_y + c * ldy, (double*)hs.ypad.p + c * rows, rows);
+            cf_convert_kernel<float, double><<<cb, 256, 0, st>>>((const float*)d_x + c * ldx, (double*)hs.cv_in.p + c * cols, cols);
+            if (beta != 0.0) cf_convert_kernel<float, double><<<cb, 256, 0, st>>>((const float*)d_y + c * ldy, (double*)hs.cv_out.p + c * rows, rows);
         }
         CF_CUDA(cudaGetLastError());
-        if (int rc = mul_device_impl(h, hs.ypad.p, rows, hs.apad.p, cols, nrhs, alpha, beta, (void*)st, deriv)) return rc;
+        if (int rc = mul_device_impl(h, hs.cv_out.p, rows, hs.cv_in.p, cols, nrhs, alpha, beta, (void*)st, deriv)) return rc;
         for (int64_t c = 0; c < nrhs; c++)
-            cf_convert_kernel<double, float><<<cb, 256, 0, st>>>((const double*)hs.ypad.p + c * rows, (float*)d_y + c * ldy, rows);
+            cf_convert_kernel<double, float><<<cb, 256, 0, st>>>((const double*)hs.cv_out.p + c * rows, (float*)d_y + c * ldy, rows);
         CF_CUDA(cudaGetLastError());
         if (!stream) CF_CUDA(cudaStreamSynchronize(st));
         g->last_launches = h->last_launches;

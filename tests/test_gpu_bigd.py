@@ -46,8 +46,32 @@ def test_gradient_mvm_bigd(cf, O, d):
         y = y0.copy()
         cf.mul_(y, G, a, -0.4, 1.7)
         assert relerr(y, O.derivative_mul(k.program(), X, a, Y=Y, trait=trait, alpha=-0.4, beta=1.7, y0=y0)) < 1e-12
-    with pytest.raises(cf.UnsupportedKernel):
-        cf.gramian(cf.ValueGradientKernel(cf.EQ()), X.T.copy()) @ np.ones(n * (d + 1))
+
+
+@pytest.mark.parametrize("d", [33, 70, 129])
+def test_value_gradient_mvm_bigd(cf, O, d):
+    # ValueGradientKernel ((d + 1)-blocks, entry 0 = value: src/gradient.jl:400-474) beyond 32 dimensions: bigd_jet_vg_kernel
+    rng = np.random.default_rng(3000 + d)
+    n, m = 90, 133
+    X = rng.standard_normal((n, d)) / np.sqrt(d)
+    Y = rng.standard_normal((m, d)) / np.sqrt(d)
+    a = rng.standard_normal(m * (d + 1))
+    for k, trait in ((cf.EQ(), "isotropic"), (cf.MaternP(2), "isotropic"), (0.5 * cf.EQ() + cf.RQ(2), "isotropic"), (cf.Dot() ** 3, "dot")):
+        G = cf.gramian(cf.ValueGradientKernel(k), X.T.copy(), Y.T.copy())
+        assert G.shape == (n * (d + 1), m * (d + 1))
+        ref = O.derivative_mul(k.program(), X, a, Y=Y, trait=trait, value_gradient=True)
+        assert relerr(G @ a, ref) < 1e-12, repr(k)
+        y0 = rng.standard_normal(n * (d + 1))
+        y = y0.copy()
+        cf.mul_(y, G, a, -0.4, 1.7)
+        assert relerr(y, -0.4 * ref + 1.7 * y0) < 1e-12
+    # a square system solved on the device: (sigma^2 I + K_vg) x = b
+    Xs = rng.standard_normal((40, d)) * 1.5 / np.sqrt(d)
+    Gs = cf.gramian(cf.ValueGradientKernel(cf.EQ()), Xs.T.copy())
+    N = 40 * (d + 1)
+    b = rng.standard_normal(N)
+    x, iters, res = (0.3 * cf.I(N) + Gs).solve(b, reltol=1e-10)
+    assert relerr(Gs @ x + 0.3 * x, b) < 1e-8
 
 
 def test_readme_gradient_example_shape(cf, O):

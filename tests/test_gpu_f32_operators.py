@@ -70,3 +70,27 @@ def test_float32_points_beyond_32_dimensions(cf, O):
     Gg = cf.gramian(cf.GradientKernel(cf.EQ()), X.T.copy(), Y.T.copy())
     ref = O.derivative_mul(cf.EQ().program(), X.astype(np.float64), ag.astype(np.float64), Y=Y.astype(np.float64))
     assert relerr(Gg @ ag, ref) < 1e-5
+
+
+def test_float32_device_pointers_with_padded_blocks(cf, O):
+    """cf_gradient_mul_device / cf_value_gradient_mul_device on a Float32 handle: the device-side conversion buffers must not alias the
+    scratch the Float64 operator pads its input into (d = 5 is padded to 6; the value-gradient form always repacks)"""
+    torch = pytest.importorskip("torch")
+    rng = np.random.default_rng(94)
+    n, d = 700, 5
+    X = (rng.standard_normal((n, d)) / np.sqrt(d)).astype(np.float32)
+    dev = torch.device("cuda", 0)
+    for vg in (False, True):
+        bs = d + (1 if vg else 0)
+        a = rng.standard_normal(n * bs).astype(np.float32)
+        K = cf.ValueGradientKernel(cf.EQ()) if vg else cf.GradientKernel(cf.EQ())
+        G = cf.gramian(K, X.T.copy())
+        a_dev = torch.from_numpy(a).to(dev)
+        y0 = rng.standard_normal(n * bs).astype(np.float32)
+        b_dev = torch.from_numpy(y0).to(dev)
+        torch.cuda.synchronize()
+        G.mul_device(b_dev.data_ptr(), a_dev.data_ptr(), alpha=1.5, beta=-0.5)
+        torch.cuda.synchronize()
+        ref = O.derivative_mul(cf.EQ().program(), X.astype(np.float64), a.astype(np.float64), value_gradient=vg)
+        assert relerr(b_dev.cpu().numpy(), 1.5 * ref - 0.5 * y0) < 1e-5, vg
+        assert relerr(a_dev.cpu().numpy(), a) == 0.0  # the input vector is untouched

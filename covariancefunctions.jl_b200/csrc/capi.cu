@@ -943,7 +943,9 @@ int launch_mvm_sym(cf_gramian_s* g, Shard& sh, double* d_y, const double* d_yin,
     const int64_t TR = cfg.rows_per_cta, TJ = cfg.tj;
     const int64_t T = (n + TR - 1) / TR;
     if (sh.sym_nitems < 0 || sh.sym_tr != TR || sh.sym_part != part || sh.sym_parts != parts) { // build the (row tile, column chunk) list once
-        int64_t ch = ((T * n / 2 / 8192) / TJ) * TJ;
+        // column chunk: ~8192 work items PER DEVICE.  (With a chunk length independent of the device count a device of eight had ~1000
+        // items for its 296 resident CTAs, 3.7 waves: the last, partly filled wave cost ~9 % at N = 8.)
+        int64_t ch = ((T * n / 2 / (8192 * (int64_t)parts)) / TJ) * TJ;
         if (ch < 8 * TJ) ch = 8 * TJ;
         std::vector<cf_sym_item> items;
         int64_t colpart_elems = 0, maxchunks = 0;

@@ -6,6 +6,8 @@
 //   MODE 4: MODE 2 + one IMAD per DFMA (independent integer chain)
 //   MODE 5: MODE 0 + one IMAD per DFMA
 //   MODE 6: x = x + y (DADD), MODE 7: x = x * y (DMUL)
+//   MODE 12: x = fma(x, x, y)  MODE 13: x = fma(y, y, x)  MODE 14: x = fma(x, y, x)   (the same register in two operand slots: the
+//            Newton steps of the square root have this form)
 // nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o fp64_issue_probe fp64_issue_probe.cu && ./fp64_issue_probe
 #include <cstdio>
 #include <cuda_runtime.h>
@@ -30,6 +32,9 @@ __global__ void __launch_bounds__(256, 2) probe(double* out, int iters, double c
                 if (MODE == 7) x[q] = x[q] * y[q];
                 if (MODE == 8 || MODE == 11) x[q] = fma(x[q], y[q], cb);
                 if (MODE == 10) x[q] = x[q] + y[q];
+                if (MODE == 12) x[q] = fma(x[q], x[q], y[q]);
+                if (MODE == 13) x[q] = fma(y[q], y[q], x[q]);
+                if (MODE == 14) x[q] = fma(x[q], y[q], x[q]);
                 if (MODE == 4 || MODE == 5 || MODE == 8 || MODE == 10 || MODE == 11) w[q] = w[q] * ia + 12345;
                 if (MODE == 11) w[q] = w[q] * ia + 777;
             }
@@ -78,6 +83,9 @@ int main() {
     run<8, 8>("DFMA(x,y,c) + 1 IMAD each", 2);
     run<10, 8>("DADD(x,y) + 1 IMAD each", 2);
     run<11, 8>("DFMA(x,y,c) + 2 IMAD each", 2);
+    run<12, 16>("DFMA x = fma(x, x, y)  (one register twice)", 2);
+    run<13, 16>("DFMA x = fma(y, y, x)  (one register twice)", 2);
+    run<14, 16>("DFMA x = fma(x, y, x)  (one register twice)", 2);
     run<1, 8>("DFMA x = fma(x, y, c)", 2);
     return 0;
 }

@@ -1,6 +1,6 @@
 """Estimate the issue cost of a SASS loop on a B200 sub-partition with the model measured by bench_aux/micro/fp64_issue_probe.cu:
-an FP64 instruction costs max(2, number of 64-bit REGISTER source operands actually read) cycles (operand-reuse hits, uniform
-registers, constants and immediates are free), every other instruction 1 cycle.
+an FP64 instruction costs max(2, number of DISTINCT 64-bit source REGISTERS actually fetched) cycles (operand-reuse hits, uniform
+registers, constants and immediates are free; a register named in two slots is fetched once), every other instruction 1 cycle.
     python bench_aux/sass_cost.py loop.txt [pairs_per_iteration]"""
 import re
 import sys
@@ -21,7 +21,7 @@ for l in lines:
     ops = [o.strip() for o in t[1].split(",")] if len(t) > 1 else []
     srcs = ops[1:]
     if op.split(".")[0] in ("DFMA", "DADD", "DMUL"):
-        reads = 0
+        fetched = set()  # DISTINCT registers fetched: a register named in two operand slots is read once (fma(x, x, y): 2.02 cycles, measured)
         for slot, o in enumerate(srcs):
             m = re.match(r"[-|]*R(\d+)", o)
             if not m:
@@ -30,11 +30,12 @@ for l in lines:
             if cache.get(slot) == reg:
                 pass  # reuse hit
             else:
-                reads += 1
+                fetched.add(reg)
             if "reuse" in o:
                 cache[slot] = reg
             else:
                 cache.pop(slot, None)
+        reads = len(fetched)
         c = max(2, reads)
         hist[c] = hist.get(c, 0) + 1
         cost += c

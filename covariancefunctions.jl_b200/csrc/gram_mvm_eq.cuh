@@ -188,8 +188,11 @@ __global__ void __launch_bounds__(NT, MINB) gram_mvm_eq_kernel(const __grid_cons
     // one column against the R rows of this thread
     auto column = [&](const double (&yj)[D], const double nj, const double aj) {
         double i0[R], t[R], f[R], p[R], s[R];
-        // coordinate-major: the R consecutive FMAs of a coordinate share y_c (and |y|^2) in the same operand slot, so all but the
-        // first are served by the operand-reuse cache and read two registers
+        // coordinate-major: the R consecutive FMAs of a coordinate share y_c (and |y|^2) in the same operand slot, so that all but the
+        // first CAN be served by the operand-reuse cache and read two registers.  ptxas interleaves them with other work, though: in the
+        // shipped SASS ~16 of the 24 distance FMAs per column still fetch three registers (82 of 384 FP64 instructions per 32 pairs;
+        // bench_aux/k1e_model.py).  Source order does not change that (volatile asm statements in this order give identical SASS);
+        // grouping them would be worth ~2 of the 31 cycles per pair.
 #pragma unroll
         for (int r = 0; r < R; r++) i0[r] = fma(xs[r][D - 1], yj[D - 1], nj);
 #pragma unroll
